@@ -1,0 +1,183 @@
+"""ctypes front-end of the plain-C oracle (oracle/raft_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package ``raft_b200`` never imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "raft_oracle.c")
+LIB = os.path.join(HERE, "_build", "libraft_oracle.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class RoDesign(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int), ("n_members", C.c_int), ("nw", C.c_int), ("n_bem_head", C.c_int),
+        ("depth", C.c_double), ("rho", C.c_double), ("g", C.c_double), ("dw", C.c_double),
+        ("x_ref", C.c_double), ("y_ref", C.c_double), ("heading_adjust", C.c_double),
+        ("prp", c_double_p), ("w", c_double_p), ("k", c_double_p),
+        ("mem_q", c_double_p), ("mem_p1", c_double_p), ("mem_p2", c_double_p), ("mem_rA", c_double_p),
+        ("mem_circ", c_int_p),
+        ("node_r", c_double_p), ("node_mem", c_int_p), ("node_Imat", c_double_p), ("node_a_i", c_double_p),
+        ("a_q", c_double_p), ("a_p1", c_double_p), ("a_p2", c_double_p), ("a_End", c_double_p),
+        ("Cd_q", c_double_p), ("Cd_p1", c_double_p), ("Cd_p2", c_double_p), ("Cd_End", c_double_p),
+        ("M0", c_double_p), ("B0", c_double_p), ("C0", c_double_p),
+        ("A_w", c_double_p), ("B_w", c_double_p),
+        ("X_BEM", C.c_void_p), ("bem_headings", c_double_p),
+    ]
+
+
+def build(force=False):
+    """Compile the C oracle with gcc (no -march flags: plain IEEE double, no FMA contraction)."""
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
+                               "-o", LIB, SRC, "-lm"])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.ro_wave_number.restype = C.c_double
+        _lib.ro_wave_number.argtypes = [C.c_double, C.c_double]
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+class OracleDesign:
+    """Holds contiguous copies of a packed design (raft_b200.packer.pack_fowt output) + the C struct."""
+
+    def __init__(self, P):
+        f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i4 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        self.keep = k = {}
+        for name in ("prp", "w", "k", "mem_q", "mem_p1", "mem_p2", "mem_rA", "node_r", "node_Imat", "node_a_i",
+                     "node_a_q", "node_a_p1", "node_a_p2", "node_a_End", "node_Cd_q", "node_Cd_p1", "node_Cd_p2",
+                     "node_Cd_End", "M0", "B0", "C0"):
+            k[name] = f8(P[name])
+        k["mem_circ"] = i4(P["mem_circ"])
+        k["node_mem"] = i4(P["node_mem"])
+        self.nw = len(k["w"])
+        self.Ns = len(k["node_mem"])
+        d = RoDesign()
+        d.n_nodes, d.n_members, d.nw = self.Ns, len(k["mem_circ"]), self.nw
+        d.depth, d.rho, d.g, d.dw = float(P["depth"]), float(P["rho"]), float(P["g"]), float(P["dw"])
+        d.x_ref, d.y_ref = float(P.get("x_ref", 0.0)), float(P.get("y_ref", 0.0))
+        d.heading_adjust = float(P.get("heading_adjust", 0.0))
+        d.prp, d.w, d.k = _dp(k["prp"]), _dp(k["w"]), _dp(k["k"])
+        d.mem_q, d.mem_p1, d.mem_p2, d.mem_rA = _dp(k["mem_q"]), _dp(k["mem_p1"]), _dp(k["mem_p2"]), _dp(k["mem_rA"])
+        d.mem_circ = _ip(k["mem_circ"])
+        d.node_r, d.node_mem, d.node_Imat, d.node_a_i = _dp(k["node_r"]), _ip(k["node_mem"]), _dp(k["node_Imat"]), _dp(k["node_a_i"])
+        d.a_q, d.a_p1, d.a_p2, d.a_End = _dp(k["node_a_q"]), _dp(k["node_a_p1"]), _dp(k["node_a_p2"]), _dp(k["node_a_End"])
+        d.Cd_q, d.Cd_p1, d.Cd_p2, d.Cd_End = _dp(k["node_Cd_q"]), _dp(k["node_Cd_p1"]), _dp(k["node_Cd_p2"]), _dp(k["node_Cd_End"])
+        d.M0, d.B0, d.C0 = _dp(k["M0"]), _dp(k["B0"]), _dp(k["C0"])
+        if "A_w" in P and P["A_w"] is not None:
+            k["A_w"], k["B_w"] = f8(P["A_w"]), f8(P["B_w"])
+            d.A_w, d.B_w = _dp(k["A_w"]), _dp(k["B_w"])
+        if "X_BEM" in P and P["X_BEM"] is not None:
+            k["X_BEM"] = np.ascontiguousarray(P["X_BEM"], dtype=np.complex128)
+            k["bem_headings"] = f8(P["bem_headings"])
+            d.X_BEM = k["X_BEM"].ctypes.data_as(C.c_void_p)
+            d.bem_headings = _dp(k["bem_headings"])
+            d.n_bem_head = len(k["bem_headings"])
+        self.c = d
+
+
+def wave_number(omega, h):
+    return lib().ro_wave_number(float(omega), float(h))
+
+
+def jonswap(w, Hs, Tp, gamma=0.0):
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    S = np.zeros_like(w)
+    lib().ro_jonswap(_dp(w), C.c_int(len(w)), C.c_double(Hs), C.c_double(Tp), C.c_double(gamma), _dp(S))
+    return S
+
+
+def calc_hydro_excitation(od, spec, Hs, Tp, gamma, beta_deg):
+    """-> zeta[nw], F_BEM[6,nw], F_iner[6,nw], u[Ns,3,nw]  (FOWT.calcHydroExcitation, one wave train)."""
+    nw, Ns = od.nw, od.Ns
+    zeta = np.zeros(nw)
+    F_BEM = np.zeros([6, nw], dtype=np.complex128)
+    F_iner = np.zeros([6, nw], dtype=np.complex128)
+    u = np.zeros([max(Ns, 1), 3, nw], dtype=np.complex128)
+    rc = lib().ro_calc_hydro_excitation(C.byref(od.c), C.c_int(spec), C.c_double(Hs), C.c_double(Tp), C.c_double(gamma),
+                                        C.c_double(beta_deg), _dp(zeta), F_BEM.ctypes.data_as(C.c_void_p),
+                                        F_iner.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise ValueError("Wave spectrum input not recognized.")
+    return zeta, F_BEM, F_iner, u[:Ns]
+
+
+def calc_hydro_linearization(od, u, Xi):
+    """-> Bmat[Ns,3,3], B_drag[6,6], F_drag[6,nw]  (FOWT.calcHydroLinearization)."""
+    nw, Ns = od.nw, od.Ns
+    u = np.ascontiguousarray(u, dtype=np.complex128)
+    Xi = np.ascontiguousarray(Xi, dtype=np.complex128)
+    Bmat = np.zeros([max(Ns, 1), 3, 3])
+    B = np.zeros([6, 6])
+    F = np.zeros([6, nw], dtype=np.complex128)
+    lib().ro_calc_hydro_linearization(C.byref(od.c), u.ctypes.data_as(C.c_void_p), Xi.ctypes.data_as(C.c_void_p),
+                                      _dp(Bmat), _dp(B), F.ctypes.data_as(C.c_void_p))
+    return Bmat[:Ns], B, F
+
+
+def solve_dynamics(od, spec, Hs, Tp, gamma, beta_deg, nIter=10, tol=0.01, XiStart=0.0, want_Z=False):
+    """-> Xi[6,nw], status(passes, converged, nan) [, Z[nw,6,6], B_drag[6,6]]  (Model.solveDynamics, 1 FOWT)."""
+    nw = od.nw
+    Xi = np.zeros([6, nw], dtype=np.complex128)
+    st = np.zeros(3, dtype=np.int32)
+    Z = np.zeros([nw, 6, 6], dtype=np.complex128) if want_Z else None
+    Bd = np.zeros([6, 6]) if want_Z else None
+    rc = lib().ro_solve_dynamics(C.byref(od.c), C.c_int(spec), C.c_double(Hs), C.c_double(Tp), C.c_double(gamma),
+                                 C.c_double(beta_deg), C.c_int(nIter), C.c_double(tol), C.c_double(XiStart),
+                                 Xi.ctypes.data_as(C.c_void_p), _ip(st),
+                                 Z.ctypes.data_as(C.c_void_p) if want_Z else None, _dp(Bd) if want_Z else None)
+    if rc:
+        raise ValueError("Wave spectrum input not recognized.")
+    return (Xi, st, Z, Bd) if want_Z else (Xi, st)
+
+
+def solve_cases(od, cases, nIter=10, tol=0.01, XiStart=0.0, nthreads=0):
+    """Batched over a packed case table (raft_b200.packer.pack_cases) -> Xi[nC,6,nw], status[nC,3], threads."""
+    nC = len(cases["Hs"])
+    Xi = np.zeros([nC, 6, od.nw], dtype=np.complex128)
+    st = np.zeros([nC, 3], dtype=np.int32)
+    spec = np.ascontiguousarray(cases["spec"], dtype=np.int32)
+    Hs, Tp, gam, beta = (np.ascontiguousarray(cases[k], dtype=np.float64) for k in ("Hs", "Tp", "gamma", "beta_deg"))
+    used = lib().ro_solve_cases(C.byref(od.c), C.c_int(nC), _ip(spec), _dp(Hs), _dp(Tp), _dp(gam), _dp(beta),
+                                C.c_int(nIter), C.c_double(tol), C.c_double(XiStart),
+                                Xi.ctypes.data_as(C.c_void_p), _ip(st), C.c_int(nthreads))
+    return Xi, st, used
+
+
+def system_response(Z_sys, F):
+    """Z_sys[nw,n,n], F[nw,n] -> Xi[nw,n] through the explicit inverse (raft_model.py:1189-1216)."""
+    Z_sys = np.ascontiguousarray(Z_sys, dtype=np.complex128)
+    F = np.ascontiguousarray(F, dtype=np.complex128)
+    nw, n = F.shape
+    Xi = np.zeros([nw, n], dtype=np.complex128)
+    bad = lib().ro_system_response(C.c_int(n), C.c_int(nw), Z_sys.ctypes.data_as(C.c_void_p),
+                                   F.ctypes.data_as(C.c_void_p), Xi.ctypes.data_as(C.c_void_p))
+    if bad:
+        raise np.linalg.LinAlgError("singular system matrix at %d frequencies" % bad)
+    return Xi

@@ -1,0 +1,208 @@
+"""Packer: RAFT object graph (Model -> FOWT -> Member) -> flat SoA tables for the C-ABI.
+
+This is the host half of the drop-in boundary.  It is duck-typed: it reads the
+attribute names the reference's objects carry (``fowt.memberList``, ``mem.r``, ``mem.q`` ...), so
+the same function packs (a) live reference objects, when ``raft_b200`` is dropped into a RAFT
+install, and (b) the objects built by ``raft_b200.member`` / ``raft_b200.fowt``.
+
+Scope: rigid 6-DOF FOWTs (every member has one structural node that is rigidly tied to the FOWT's
+reference node), no MacCamy-Fuchs, no underwater rotors -- exactly the BASELINE.json configs.
+Anything else raises ``NotImplementedError`` (the caller falls back to the reference path; see
+SURVEY.md section 8f row 4).
+
+Reference formulas restated here (they live inside the reference's per-iteration loops, but are
+iteration-invariant, so the packer hoists them):
+  * drag areas               raft_member.py:2070-2072, 2105-2108
+  * coefficient interpolation raft_member.py:2061-2064  (np.interp over stations)
+  * linearisation prefactor   raft_member.py:2093-2095, 2110   sqrt(8/pi) * 1/2 rho a Cd
+"""
+import numpy as np
+
+SQRT_8_OVER_PI = np.sqrt(8.0 / np.pi)
+
+
+def _member_is_supported(mem):
+    if getattr(mem, "type", "rigid") != "rigid":
+        raise NotImplementedError("member %r: only rigid members are supported by the B200 path" % mem.name)
+    # MCF only alters Imat, which is computed for strip-theory (potMod False) members only
+    # (raft_member.py:1393, 1415); a potMod member with the MCF flag set is unaffected.
+    if getattr(mem, "MCF", False) and not getattr(mem, "potMod", False):
+        raise NotImplementedError("member %r: MacCamy-Fuchs (complex Imat) not supported" % mem.name)
+
+
+def pack_members(fowt, rho=None, g=None):
+    """Flatten the submerged strip nodes of ``fowt.memberList`` into node + member tables.
+
+    Only nodes with ``r_z < 0`` are kept (raft_member.py:1935, 1979, 2058, 2135); members with no
+    submerged node are dropped.  Returns a dict of numpy arrays (float64 unless noted).
+    """
+    rho = float(fowt.rho_water if rho is None else rho)
+    g = float(fowt.g if g is None else g)
+    ref = getattr(fowt, "rigidBodyNode", None)
+    prp = np.array(ref.r[:3] if ref is not None else fowt.r6[:3], dtype=float)
+
+    mq, mp1, mp2, mrA, mcirc, mstart = [], [], [], [], [], [0]
+    cols = {k: [] for k in ("r", "mem", "ls", "cd_q", "cd_p1", "cd_p2", "in_q", "in_p1", "in_p2", "pa",
+                            "Imat", "a_i", "a_q", "a_p1", "a_p2", "a_End", "Cd_q", "Cd_p1", "Cd_p2", "Cd_End")}
+    for mem in fowt.memberList:
+        _member_is_supported(mem)
+        sub = np.where(mem.r[:, 2] < 0)[0]
+        if len(sub) == 0:
+            continue
+        circ = mem.shape == "circular"
+        q, p1, p2 = (np.asarray(v, dtype=float) for v in (mem.q, mem.p1, mem.p2))
+        im = len(mq)
+        mq.append(q), mp1.append(p1), mp2.append(p2)
+        mrA.append(np.array(mem.rA, dtype=float))
+        mcirc.append(1 if circ else 0)
+        for il in sub:
+            ls = float(mem.ls[il])
+            Cd_q = np.interp(ls, mem.stations, mem.Cd_q)
+            Cd_p1 = np.interp(ls, mem.stations, mem.Cd_p1)
+            Cd_p2 = np.interp(ls, mem.stations, mem.Cd_p2)
+            Cd_End = np.interp(ls, mem.stations, mem.Cd_End)
+            if circ:
+                a_q = np.pi * mem.ds[il] * mem.dls[il]
+                a_p1 = mem.ds[il] * mem.dls[il]
+                a_p2 = mem.ds[il] * mem.dls[il]
+                a_End = np.abs(np.pi * mem.ds[il] * mem.drs[il])
+            else:
+                # sic: ds[il,0] twice, as in raft_member.py:2070
+                a_q = 2 * (mem.ds[il, 0] + mem.ds[il, 0]) * mem.dls[il]
+                a_p1 = mem.ds[il, 0] * mem.dls[il]
+                a_p2 = mem.ds[il, 1] * mem.dls[il]
+                a_End = np.abs((mem.ds[il, 0] + mem.drs[il, 0]) * (mem.ds[il, 1] + mem.drs[il, 1])
+                               - (mem.ds[il, 0] - mem.drs[il, 0]) * (mem.ds[il, 1] - mem.drs[il, 1]))
+            pref = SQRT_8_OVER_PI * 0.5 * rho
+            Imat = np.array(mem.Imat[il], dtype=float)
+            a_i = float(mem.a_i[il])
+            in_q, in_p1, in_p2 = q @ Imat @ q, p1 @ Imat @ p1, p2 @ Imat @ p2
+            resid = Imat - (in_q * np.outer(q, q) + in_p1 * np.outer(p1, p1) + in_p2 * np.outer(p2, p2))
+            if np.abs(resid).max() > 1e-9 * max(1.0, np.abs(Imat).max()):
+                raise NotImplementedError("member %r: Imat is not diagonal in the member frame" % mem.name)
+            cols["r"].append(np.array(mem.r[il], dtype=float))
+            cols["mem"].append(im)
+            cols["ls"].append(ls)
+            cols["cd_q"].append(pref * (a_q * Cd_q + a_End * Cd_End))
+            cols["cd_p1"].append(pref * a_p1 * Cd_p1)
+            cols["cd_p2"].append(pref * a_p2 * Cd_p2)
+            cols["in_q"].append(in_q), cols["in_p1"].append(in_p1), cols["in_p2"].append(in_p2)
+            cols["pa"].append(rho * g * a_i)
+            cols["Imat"].append(Imat), cols["a_i"].append(a_i)
+            cols["a_q"].append(a_q), cols["a_p1"].append(a_p1), cols["a_p2"].append(a_p2), cols["a_End"].append(a_End)
+            cols["Cd_q"].append(Cd_q), cols["Cd_p1"].append(Cd_p1), cols["Cd_p2"].append(Cd_p2), cols["Cd_End"].append(Cd_End)
+        mstart.append(len(cols["ls"]))
+
+    ns = len(cols["ls"])
+    out = dict(
+        prp=prp, rho=np.float64(rho), g=np.float64(g),
+        mem_q=np.array(mq, dtype=float).reshape(-1, 3), mem_p1=np.array(mp1, dtype=float).reshape(-1, 3),
+        mem_p2=np.array(mp2, dtype=float).reshape(-1, 3), mem_rA=np.array(mrA, dtype=float).reshape(-1, 3),
+        mem_circ=np.array(mcirc, dtype=np.int32), mem_start=np.array(mstart, dtype=np.int32),
+        node_r=np.array(cols["r"], dtype=float).reshape(ns, 3), node_mem=np.array(cols["mem"], dtype=np.int32),
+        node_Imat=np.array(cols["Imat"], dtype=float).reshape(ns, 3, 3),
+    )
+    for k in ("ls", "cd_q", "cd_p1", "cd_p2", "in_q", "in_p1", "in_p2", "pa", "a_i",
+              "a_q", "a_p1", "a_p2", "a_End", "Cd_q", "Cd_p1", "Cd_p2", "Cd_End"):
+        out["node_" + k] = np.array(cols[k], dtype=float)
+    return out
+
+
+def pack_matrices(fowt, nw):
+    """Iteration-invariant system matrices of one FOWT (raft_model.py:1045-1047).
+
+    M0 = M_struc + A_hydro_morison (+ sum A_aero is frequency dependent -> A_w)
+    B0 = B_struc + sum B_gyro
+    C0 = C_struc + C_hydro + C_moor + C_elast
+    A_w, B_w [nw,6,6]: frequency-dependent parts (A_BEM + sum A_aero, B_BEM + sum B_aero) or None.
+    moorMod 2 (frequency-independent M/A/B_moor from MoorPy) is folded in by the caller if needed.
+    """
+    n = fowt.nDOF
+    if n != 6:
+        raise NotImplementedError("only 6-DOF rigid FOWTs are supported (nDOF=%d)" % n)
+    M0 = np.array(fowt.M_struc, dtype=float) + np.array(fowt.A_hydro_morison, dtype=float)
+    B0 = np.array(fowt.B_struc, dtype=float)
+    B_gyro = getattr(fowt, "B_gyro", None)
+    if B_gyro is not None and np.size(B_gyro):
+        B0 = B0 + np.sum(B_gyro, axis=2)
+    C0 = (np.array(fowt.C_struc, dtype=float) + np.array(fowt.C_hydro, dtype=float)
+          + np.array(fowt.C_moor, dtype=float) + np.array(fowt.C_elast, dtype=float))
+    A_w = np.zeros([n, n, nw])
+    B_w = np.zeros([n, n, nw])
+    have = False
+    if getattr(fowt, "nrotors", 0) > 0:
+        A_w += np.sum(fowt.A_aero, axis=3)
+        B_w += np.sum(fowt.B_aero, axis=3)
+        have = True
+    A_BEM = getattr(fowt, "A_BEM", None)
+    if A_BEM is not None and np.any(A_BEM):
+        A_w += A_BEM
+        have = True
+    B_BEM = getattr(fowt, "B_BEM", None)
+    if B_BEM is not None and np.any(B_BEM):
+        B_w += B_BEM
+        have = True
+    out = dict(M0=M0, B0=B0, C0=C0)
+    if have:
+        # freq-major [nw,6,6] (the reference keeps [6,6,nw]); contiguous 6x6 per frequency
+        out["A_w"] = np.ascontiguousarray(np.moveaxis(A_w, 2, 0))
+        out["B_w"] = np.ascontiguousarray(np.moveaxis(B_w, 2, 0))
+    return out
+
+
+def pack_bem_excitation(fowt):
+    """BEM excitation coefficient table for heading interpolation (raft_fowt.py:1796-1849).
+
+    Returns ``None`` when the FOWT has no potential-flow excitation, else a dict with
+    X_BEM [nhead, nw, 6] complex128 (freq-major), headings [nhead] (deg), heading_adjust, x_ref, y_ref.
+    """
+    if not (getattr(fowt, "potMod", False) or getattr(fowt, "potModMaster", 0) in (2, 3)):
+        return None
+    X = getattr(fowt, "X_BEM", None)
+    if X is None:
+        return None
+    X = np.asarray(X)
+    return dict(X_BEM=np.ascontiguousarray(np.moveaxis(X[:, :6, :], 2, 1)).astype(np.complex128),
+                bem_headings=np.array(fowt.BEM_headings, dtype=float),
+                heading_adjust=np.float64(fowt.heading_adjust))
+
+
+def pack_fowt(fowt, w=None, k=None):
+    """Everything the kernels need for one FOWT design: node/member tables, matrices, grid."""
+    w = np.array(fowt.w if w is None else w, dtype=float)
+    k = np.array(fowt.k if k is None else k, dtype=float)
+    out = pack_members(fowt)
+    out.update(pack_matrices(fowt, len(w)))
+    bem = pack_bem_excitation(fowt)
+    if bem is not None:
+        out.update(bem)
+    out.update(w=w, k=k, depth=np.float64(fowt.depth), dw=np.float64(w[1] - w[0]),
+               x_ref=np.float64(getattr(fowt, "x_ref", 0.0)), y_ref=np.float64(getattr(fowt, "y_ref", 0.0)))
+    return out
+
+
+SPECTRUM_IDS = {"JONSWAP": 0, "unit": 1, "constant": 2, "none": 3, "still": 3}
+
+
+def pack_cases(cases):
+    """Load cases -> SoA case table (first wave train of each case; raft_fowt.py:1742-1774).
+
+    ``cases`` is a list of dicts with keys wave_spectrum, wave_period, wave_height, wave_heading,
+    wave_gamma (scalars, or length-nWaves lists of which train 0 drives the linearisation).
+    Returns dict(Hs, Tp, gamma, beta_deg [nC] float64, spec [nC] int32).
+    Unknown spectrum -> ValueError, as raft_fowt.py:1774.
+    """
+    def first(v):
+        return v if np.isscalar(v) else v[0]
+    nC = len(cases)
+    Hs, Tp, gam, beta, spec = (np.zeros(nC) for _ in range(4)) + (np.zeros(nC, dtype=np.int32),)
+    for i, c in enumerate(cases):
+        s = str(first(c.get("wave_spectrum", "JONSWAP")))
+        if s not in SPECTRUM_IDS:
+            raise ValueError(f"Wave spectrum input '{s}' not recognized.")
+        spec[i] = SPECTRUM_IDS[s]
+        Hs[i] = float(first(c["wave_height"]))
+        Tp[i] = float(first(c["wave_period"]))
+        gam[i] = float(first(c.get("wave_gamma", 0.0)))
+        beta[i] = float(first(c.get("wave_heading", 0.0)))
+    return dict(Hs=Hs, Tp=Tp, gamma=gam, beta_deg=beta, spec=spec)
