@@ -1,0 +1,196 @@
+/*
+ * raftk.h -- C ABI of the B200-native RAO-solve hot path (libraftk.so, sm_100a).
+ *
+ * The reference (WISDEM/RAFT) has no FFI: its boundary for this path is Python-method level.
+ * Every entry point below therefore cites the reference method(s) it replaces
+ * (paths relative to /root/reference/raft/).  INTEGRATION.md shows the ctypes stub a RAFT
+ * maintainer would add at those call sites.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; all entry points return 0 on success or a
+ *     negative RAFTK_E* code, never throw; raftk_last_error() gives the message (thread-local).
+ *   - all floating point is IEEE float64; complex128 is interleaved (re, im) pairs.
+ *   - array layouts follow the reference's NumPy arrays (frequency is the fastest axis), so a
+ *     live RAFT array can be passed without a transpose.
+ *   - *_dev entry points take DEVICE pointers and a cudaStream_t (as void*); they allocate
+ *     nothing: the caller owns a workspace sized by raftk_workspace_bytes().  They are
+ *     asynchronous w.r.t. the host and re-entrant per stream.
+ *   - *_host entry points take HOST pointers, stage through an internal device arena
+ *     (grown on demand, cached per process), and are synchronous.
+ *
+ * Scope: rigid 6-DOF FOWTs, strip-theory members (+ optional BEM tables), one wave train drives
+ * the drag linearisation (raft_fowt.py:1910).  See DESIGN.md for what is out of scope.
+ */
+#ifndef RAFTK_H
+#define RAFTK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAFTK_VERSION 100 /* 0.1.0 */
+
+enum {
+    RAFTK_OK = 0,
+    RAFTK_EINVAL = -1,    /* bad argument / unsupported size            */
+    RAFTK_ECUDA = -2,     /* CUDA runtime error (see raftk_last_error)  */
+    RAFTK_ENOMEM = -3,    /* workspace too small / allocation failed    */
+    RAFTK_ESPECTRUM = -4  /* unknown wave spectrum id (ValueError at raft_fowt.py:1774) */
+};
+
+/* wave_spectrum ids (raft_fowt.py:1761-1772) */
+enum { RAFTK_SPEC_JONSWAP = 0, RAFTK_SPEC_UNIT = 1, RAFTK_SPEC_CONSTANT = 2, RAFTK_SPEC_NONE = 3 };
+
+/* status word per (design, case): int32[4] = {passes, converged, flags, reserved} */
+enum { RAFTK_FLAG_NAN = 1, RAFTK_FLAG_SINGULAR = 2 };
+
+/*
+ * A batch of nD FOWT designs that share one frequency grid (w, k), water depth and density.
+ * Member / node tables are concatenated over designs (CSR offsets).  Only submerged strip
+ * nodes (r_z < 0; raft_member.py:1935,1979,2058) are listed.  Replaces the per-object state
+ * the reference keeps in Member (raft_member.py:258-309, 368-377) and FOWT (raft_fowt.py:
+ * 1045-1047 sums).  All coefficient columns are iteration invariant.
+ */
+typedef struct raftk_designs {
+    int32_t n_designs;          /* nD                                                          */
+    int32_t nw;                 /* frequency bins                                              */
+    int32_t n_members_total;    /* sum of members with >= 1 submerged node                     */
+    int32_t n_nodes_total;      /* sum of submerged strip nodes (NsTot)                        */
+    int32_t max_nodes;          /* max submerged nodes of any one design (table stride)        */
+    int32_t max_members;        /* max members of any one design                               */
+    double depth, rho, g, dw;   /* site (raft_fowt.py:167-173); dw = w[1]-w[0]                  */
+    const double *w;            /* [nw] rad/s           raft_model.py:57                       */
+    const double *k;            /* [nw] wave numbers    raft_fowt.py:170 (helpers.py:377)      */
+    const int32_t *member_offset; /* [nD+1] into member arrays                                 */
+    /* member table [n_members_total] */
+    const double *mem_frame;    /* [.,9]  q, p1, p2 unit vectors   raft_member.py:368-372      */
+    const double *mem_rA;       /* [.,3]  global position of end A (wave phase / depth)        */
+    const double *mem_arm;      /* [.,3]  rA - reference point of the reduced DOFs (lever arm) */
+    const int32_t *mem_node_start; /* [.+1] first node of each member in the node arrays       */
+    const int32_t *mem_circ;    /* [.]    1 circular, 0 rectangular  raft_member.py:2033       */
+    /* node table [n_nodes_total]; node position = rA + ls*q (raft_member.py:360-362) */
+    const double *node_ls;      /* distance along the member axis                              */
+    const double *node_cd_q;    /* sqrt(8/pi)*rho/2*(a_q*Cd_q + a_End*Cd_End)  member:2093,2110 */
+    const double *node_cd_p1;   /* sqrt(8/pi)*rho/2*a_p1*Cd_p1                member:2094       */
+    const double *node_cd_p2;   /* sqrt(8/pi)*rho/2*a_p2*Cd_p2                member:2095       */
+    const double *node_in_q;    /* Imat = in_q qq' + in_p1 p1p1' + in_p2 p2p2' member:1423,1442 */
+    const double *node_in_p1;
+    const double *node_in_p2;
+    const double *node_pa;      /* rho*g*a_i (signed end area)                 member:1343,1988 */
+    /* optional MacCamy-Fuchs tables: complex [n_nodes_total,nw] transverse inertia coefficients that
+       replace in_p1/in_p2 (Imat_MCF, raft_member.py:1415-1420,1446,1984-1985); both or neither NULL */
+    const double *node_in_p1_w;
+    const double *node_in_p2_w;
+    /* system matrices, row-major 6x6 per design (raft_model.py:1045-1047) */
+    const double *M0;           /* [nD,36] M_struc + A_hydro_morison (+ M_moor + A_moor)        */
+    const double *B0;           /* [nD,36] B_struc + sum B_gyro (+ B_moor)                      */
+    const double *C0;           /* [nD,36] C_struc + C_hydro + C_moor + C_elast                 */
+    const double *A_w;          /* [nD,36,nw] A_BEM + sum A_aero, or NULL                       */
+    const double *B_w;          /* [nD,36,nw] B_BEM + sum B_aero, or NULL                       */
+    /* BEM excitation (raft_fowt.py:1796-1849), or n_bem_head = 0 */
+    int32_t n_bem_head;
+    int32_t _pad0;
+    const double *bem_headings; /* [n_bem_head] deg, ascending (shared by all designs)          */
+    const double *X_BEM;        /* complex [nD, n_bem_head, 6, nw]                              */
+    const double *bem_xyh;      /* [nD,3] x_ref, y_ref, heading_adjust(deg)                     */
+} raftk_designs;
+
+/* Load cases, shared by all designs: units of work are (design, case) pairs.
+ * First wave train of each RAFT case (raft_fowt.py:1742-1774). */
+typedef struct raftk_cases {
+    int32_t n_cases;
+    int32_t _pad0;
+    const double *Hs;        /* [nC] wave_height                                                */
+    const double *Tp;        /* [nC] wave_period                                                */
+    const double *gamma;     /* [nC] wave_gamma (0 -> IEC auto, helpers.py:733-740)             */
+    const double *beta_deg;  /* [nC] wave_heading [deg]                                         */
+    const int32_t *spec;     /* [nC] RAFTK_SPEC_*                                               */
+    const double *zeta;      /* optional [nC,nw] explicit amplitudes (overrides spec) or NULL   */
+} raftk_cases;
+
+/* Fixed-point loop controls (raft_model.py:966 tol, :977 nIter, :978 XiStart, :1133 relaxation) */
+typedef struct raftk_solve_opts {
+    int32_t n_iter;          /* settings.nIter; the loop runs at most n_iter+1 passes           */
+    int32_t cluster_size;    /* CTAs per (design,case): 0 = auto, else 1,2,4,8                  */
+    double tol;              /* 0.01                                                            */
+    double xi_start;         /* settings.XiStart                                                */
+} raftk_solve_opts;
+
+/* Outputs.  Any pointer may be NULL (that output is skipped) except Xi/status where noted. */
+typedef struct raftk_outputs {
+    double *Xi;       /* complex [nD,nC,6,nw]  response amplitudes  (Model.Xi[0], fowt.Xi[0])   */
+    int32_t *status;  /* [nD,nC,4]                                                              */
+    double *B_drag;   /* [nD,nC,36] last linearised drag damping (fowt.B_hydro_drag)            */
+    double *F_drag;   /* complex [nD,nC,6,nw] last drag excitation (fowt.F_hydro_drag)          */
+    double *F_iner;   /* complex [nD,nC,6,nw] strip inertial excitation (fowt.F_hydro_iner[0])  */
+    double *F_BEM;    /* complex [nD,nC,6,nw] BEM excitation (fowt.F_BEM[0])                    */
+    double *zeta;     /* [nC,nw] wave amplitudes (fowt.zeta[0])                                 */
+} raftk_outputs;
+
+int raftk_version(void);
+const char *raftk_last_error(void);
+
+/* Number of CUDA kernel launches issued by this library since load (bench.py "gpu_launches"). */
+long long raftk_launch_count(void);
+
+/* Bytes of device workspace the *_dev entry points need for (designs, n_cases). */
+size_t raftk_workspace_bytes(const raftk_designs *d, int32_t n_cases);
+
+/*
+ * FOWT.calcHydroExcitation (raft_fowt.py:1732-1888) + Member.computeWaveKinematics /
+ * calcHydroExcitation (raft_member.py:1899-1992) + helpers.getWaveKin/JONSWAP for every
+ * (design, case).  Fills out->F_iner / F_BEM / zeta (those that are non-NULL) and leaves the
+ * wave-kinematics tables in the workspace for raftk_hydro_linearization_dev.
+ */
+int raftk_hydro_excitation_dev(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * FOWT.calcHydroLinearization(Xi) + calcDragExcitation(0) (raft_fowt.py:1891-1957,
+ * raft_member.py:1995-2152) for every (design, case), with Xi_in complex [nD,nC,6,nw] given.
+ * Requires raftk_hydro_excitation_dev on the same workspace first (the reference has the same
+ * ordering contract: mem.u must exist).  Fills out->B_drag, out->F_drag.
+ */
+int raftk_hydro_linearization_dev(const raftk_designs *d, const raftk_cases *c, const double *Xi_in,
+                                  const raftk_outputs *out, void *workspace, size_t workspace_bytes,
+                                  void *stream);
+
+/*
+ * Model.solveDynamics (raft_model.py:966-1302) for one FOWT per design and every case:
+ * excitation, drag-linearisation fixed-point loop with the 6x6 complex impedance solve at
+ * every frequency, convergence test and relaxation.  out->Xi and out->status are required.
+ */
+int raftk_solve_dynamics_dev(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o,
+                             const raftk_outputs *out, void *workspace, size_t workspace_bytes,
+                             void *stream);
+
+/* Same three operations with HOST pointers everywhere (tables, cases, outputs). */
+int raftk_hydro_excitation_host(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out);
+int raftk_hydro_linearization_host(const raftk_designs *d, const raftk_cases *c, const double *Xi_in,
+                                   const raftk_outputs *out);
+int raftk_solve_dynamics_host(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o,
+                              const raftk_outputs *out);
+
+/*
+ * System (farm) response, raft_model.py:1164-1216: for every frequency solve the dense
+ * n x n complex system Z_sys(w) Xi = F for nrhs right-hand sides (n = 6N).
+ * Z complex [nw,n,n] row-major (destroyed), F complex [nw,n,nrhs] (overwritten with Xi).
+ */
+int raftk_system_solve_dev(int32_t n, int32_t nw, int32_t nrhs, double *Z, double *F, int32_t *info,
+                           void *stream);
+int raftk_system_solve_host(int32_t n, int32_t nw, int32_t nrhs, double *Z, double *F, int32_t *info);
+
+/* Pinned host memory for the *_host paths and the e2e benchmark (cudaHostAlloc / cudaFreeHost). */
+void *raftk_host_alloc(size_t bytes);
+void raftk_host_free(void *p);
+
+/* FP64 FMA micro-benchmark: returns achieved GFLOP/s on the current device (roofline denominator). */
+double raftk_fp64_peak_gflops(int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAFTK_H */

@@ -30,7 +30,7 @@ class RoDesign(C.Structure):
         ("Cd_q", c_double_p), ("Cd_p1", c_double_p), ("Cd_p2", c_double_p), ("Cd_End", c_double_p),
         ("M0", c_double_p), ("B0", c_double_p), ("C0", c_double_p),
         ("A_w", c_double_p), ("B_w", c_double_p),
-        ("X_BEM", C.c_void_p), ("bem_headings", c_double_p),
+        ("X_BEM", C.c_void_p), ("bem_headings", c_double_p), ("node_Imat_w", C.c_void_p),
     ]
 
 
@@ -99,11 +99,51 @@ class OracleDesign:
             d.X_BEM = k["X_BEM"].ctypes.data_as(C.c_void_p)
             d.bem_headings = _dp(k["bem_headings"])
             d.n_bem_head = len(k["bem_headings"])
+        if "node_Imat_w" in P and P["node_Imat_w"] is not None:
+            k["node_Imat_w"] = np.ascontiguousarray(P["node_Imat_w"], dtype=np.complex128)
+            d.node_Imat_w = k["node_Imat_w"].ctypes.data_as(C.c_void_p)
         self.c = d
 
 
 def wave_number(omega, h):
     return lib().ro_wave_number(float(omega), float(h))
+
+
+def wave_kin(zeta0, beta, w, k, h, r, rho=1025.0, g=9.81):
+    """helpers.getWaveKin -> u[3,nw], ud[3,nw], pDyn[nw]."""
+    zeta0, w, k, r = (np.ascontiguousarray(x, dtype=np.float64) for x in (zeta0, w, k, r))
+    nw = len(w)
+    u, ud, p = np.zeros([3, nw], complex), np.zeros([3, nw], complex), np.zeros(nw, complex)
+    lib().ro_wave_kin(_dp(zeta0), C.c_double(beta), _dp(w), _dp(k), C.c_double(h), _dp(r), C.c_int(nw),
+                      C.c_double(rho), C.c_double(g), u.ctypes.data_as(C.c_void_p), ud.ctypes.data_as(C.c_void_p),
+                      p.ctypes.data_as(C.c_void_p))
+    return u, ud, p
+
+
+def get_kinematics(r, Xi, ws):
+    r, ws = np.ascontiguousarray(r, dtype=np.float64), np.ascontiguousarray(ws, dtype=np.float64)
+    Xi = np.ascontiguousarray(Xi, dtype=np.complex128)
+    nw = len(ws)
+    dr, v, a = (np.zeros([3, nw], complex) for _ in range(3))
+    lib().ro_get_kinematics(_dp(r), Xi.ctypes.data_as(C.c_void_p), _dp(ws), C.c_int(nw), dr.ctypes.data_as(C.c_void_p),
+                            v.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p))
+    return dr, v, a
+
+
+def translate_force(f, r):
+    f = np.ascontiguousarray(f, dtype=np.complex128)
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    out = np.zeros(6, complex)
+    lib().ro_translate_force(f.ctypes.data_as(C.c_void_p), _dp(r), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def translate_matrix(M, r):
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    out = np.zeros([6, 6])
+    lib().ro_translate_matrix(_dp(M), _dp(r), _dp(out))
+    return out
 
 
 def jonswap(w, Hs, Tp, gamma=0.0):
@@ -120,8 +160,8 @@ def calc_hydro_excitation(od, spec, Hs, Tp, gamma, beta_deg):
     F_BEM = np.zeros([6, nw], dtype=np.complex128)
     F_iner = np.zeros([6, nw], dtype=np.complex128)
     u = np.zeros([max(Ns, 1), 3, nw], dtype=np.complex128)
-    rc = lib().ro_calc_hydro_excitation(C.byref(od.c), C.c_int(spec), C.c_double(Hs), C.c_double(Tp), C.c_double(gamma),
-                                        C.c_double(beta_deg), _dp(zeta), F_BEM.ctypes.data_as(C.c_void_p),
+    rc = lib().ro_calc_hydro_excitation(C.byref(od.c), C.c_int(spec), C.c_double(float(Hs)), C.c_double(float(Tp)), C.c_double(float(gamma)),
+                                        C.c_double(float(beta_deg)), _dp(zeta), F_BEM.ctypes.data_as(C.c_void_p),
                                         F_iner.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p))
     if rc:
         raise ValueError("Wave spectrum input not recognized.")
@@ -148,8 +188,8 @@ def solve_dynamics(od, spec, Hs, Tp, gamma, beta_deg, nIter=10, tol=0.01, XiStar
     st = np.zeros(3, dtype=np.int32)
     Z = np.zeros([nw, 6, 6], dtype=np.complex128) if want_Z else None
     Bd = np.zeros([6, 6]) if want_Z else None
-    rc = lib().ro_solve_dynamics(C.byref(od.c), C.c_int(spec), C.c_double(Hs), C.c_double(Tp), C.c_double(gamma),
-                                 C.c_double(beta_deg), C.c_int(nIter), C.c_double(tol), C.c_double(XiStart),
+    rc = lib().ro_solve_dynamics(C.byref(od.c), C.c_int(spec), C.c_double(float(Hs)), C.c_double(float(Tp)), C.c_double(float(gamma)),
+                                 C.c_double(float(beta_deg)), C.c_int(nIter), C.c_double(tol), C.c_double(XiStart),
                                  Xi.ctypes.data_as(C.c_void_p), _ip(st),
                                  Z.ctypes.data_as(C.c_void_p) if want_Z else None, _dp(Bd) if want_Z else None)
     if rc:

@@ -16,7 +16,7 @@
  * The loop structure, operation order and two-step (member node -> reduced DOF) translation of
  * the reference are kept on purpose: this is the checker for the restructured CUDA kernels.
  *
- * Scope: rigid 6-DOF FOWT, no MacCamy-Fuchs, no underwater rotor, no second-order forces
+ * Scope: rigid 6-DOF FOWT (MacCamy-Fuchs Imat as an input table), no underwater rotor, no second-order forces
  * (BASELINE.json configs 1-4).
  */
 #include <complex.h>
@@ -44,9 +44,10 @@ typedef struct {
     const double *a_q, *a_p1, *a_p2, *a_End;       /* [Ns] drag areas                         */
     const double *Cd_q, *Cd_p1, *Cd_p2, *Cd_End;   /* [Ns] interpolated coefficients          */
     const double *M0, *B0, *C0;                    /* [6,6] row-major                         */
-    const double *A_w, *B_w;                       /* [nw,6,6] or NULL                        */
-    const cplx *X_BEM;                             /* [nhead,nw,6] or NULL                    */
+    const double *A_w, *B_w;                       /* [6,6,nw] or NULL (reference layout)     */
+    const cplx *X_BEM;                             /* [nhead,6,nw] or NULL (reference layout) */
     const double *bem_headings;                    /* [nhead] deg                             */
+    const cplx *node_Imat_w;                       /* [Ns,3,3,nw] MacCamy-Fuchs Imat_MCF or NULL */
 } ro_design;
 
 /* helpers.py:377-392 waveNumber(omega, h, e=0.001) */
@@ -171,6 +172,26 @@ static void node_T(const double *d, double T[6][6])
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) T[i][3 + j] = H[i][j];
 }
 
+/* exported wrappers so the helper-level known answers of the reference's tests/test_helpers.py
+ * (getKinematics :26-38, translateForce3to6DOF :88-94, translateMatrix3to6DOF :123-136) can be
+ * checked against this file's building blocks */
+void ro_translate_force(const cplx *f, const double *r, cplx *out) { translate_force(f, r, out); }
+void ro_translate_matrix(const double *Min, const double *r, double *Mout)
+{
+    translate_matrix((const double (*)[3])Min, r, (double (*)[6])Mout);
+}
+/* helpers.py:149-184 getKinematics(r, Xi, ws): Xi [6][nw] -> dr, v, a [3][nw] */
+void ro_get_kinematics(const double *r, const cplx *Xi, const double *ws, int nw, cplx *dr, cplx *v, cplx *a)
+{
+    for (int i = 0; i < nw; i++) {
+        const cplx th0 = Xi[3 * nw + i], th1 = Xi[4 * nw + i], th2 = Xi[5 * nw + i];
+        dr[0 * nw + i] = Xi[0 * nw + i] + (-th2 * r[1] + th1 * r[2]);
+        dr[1 * nw + i] = Xi[1 * nw + i] + ( th2 * r[0] - th0 * r[2]);
+        dr[2 * nw + i] = Xi[2 * nw + i] + (-th1 * r[0] + th0 * r[1]);
+        for (int c = 0; c < 3; c++) { v[c * nw + i] = I * ws[i] * dr[c * nw + i]; a[c * nw + i] = I * ws[i] * v[c * nw + i]; }
+    }
+}
+
 /* ---- excitation -------------------------------------------------------------------- */
 
 /* raft_fowt.py:1796-1849 BEM excitation for one wave train: F_BEM[6][nw] */
@@ -199,7 +220,7 @@ static void bem_excitation(const ro_design *d, const double *zeta, double beta_d
     for (int iw = 0; iw < nw; iw++) {
         cplx Xp[6], X[6];
         for (int j = 0; j < 6; j++)
-            Xp[j] = d->X_BEM[((size_t)i1 * nw + iw) * 6 + j] * f1 + d->X_BEM[((size_t)i2 * nw + iw) * 6 + j] * f2;
+            Xp[j] = d->X_BEM[((size_t)i1 * 6 + j) * nw + iw] * f1 + d->X_BEM[((size_t)i2 * 6 + j) * nw + iw] * f2;
         X[0] = Xp[0] * cb - Xp[1] * sb;  X[1] = Xp[0] * sb + Xp[1] * cb;  X[2] = Xp[2];
         X[3] = Xp[3] * cb - Xp[4] * sb;  X[4] = Xp[3] * sb + Xp[4] * cb;  X[5] = Xp[5];
         cplx ph = cexp(-I * d->k[iw] * (d->x_ref * cos(beta_rad) + d->y_ref * sin(beta_rad)));
@@ -227,9 +248,15 @@ static void hydro_excitation(const ro_design *d, const double *zeta, double beta
             double rr[3] = { r[0] - rn[0], r[1] - rn[1], r[2] - rn[2] };
             for (int i = 0; i < nw; i++) {
                 cplx f[3], f6[6];
-                for (int a = 0; a < 3; a++)
+                for (int a = 0; a < 3; a++) {
+                    if (d->node_Imat_w) {                             /* member:1984-1985 Imat_MCF[il,:,:,i] */
+                        const cplx *Iw = d->node_Imat_w + (size_t)il * 9 * nw;
+                        f[a] = Iw[(3 * a) * nw + i] * ud[i] + Iw[(3 * a + 1) * nw + i] * ud[nw + i]
+                             + Iw[(3 * a + 2) * nw + i] * ud[2 * nw + i] + pD[i] * d->node_a_i[il] * q[a];
+                    } else
                     f[a] = Im[3 * a] * ud[i] + Im[3 * a + 1] * ud[nw + i] + Im[3 * a + 2] * ud[2 * nw + i]
                          + pD[i] * d->node_a_i[il] * q[a];            /* member:1988 */
+                }
                 translate_force(f, rr, f6);
                 for (int a = 0; a < 6; a++) Fm[a * nw + i] += f6[a];
             }
@@ -443,8 +470,8 @@ int ro_solve_dynamics(const ro_design *d, int spec, double Hs, double Tp, double
             for (int a = 0; a < 6; a++) {
                 for (int c = 0; c < 6; c++) {
                     double M = d->M0[6 * a + c], B = d->B0[6 * a + c];
-                    if (d->A_w) M += d->A_w[(size_t)ii * 36 + 6 * a + c];
-                    if (d->B_w) B += d->B_w[(size_t)ii * 36 + 6 * a + c];
+                    if (d->A_w) M += d->A_w[(size_t)(6 * a + c) * nw + ii];
+                    if (d->B_w) B += d->B_w[(size_t)(6 * a + c) * nw + ii];
                     B += B_drag[a][c];
                     A[6 * a + c] = -wv * wv * M + I * wv * B + d->C0[6 * a + c];   /* :1086 */
                 }

@@ -1,0 +1,102 @@
+"""ctypes binding of libraftk.so (include/raftk.h).  No CPU fallback: if the CUDA library is not
+built, importing this module raises -- the product path must fail loudly, never degrade."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libraftk.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class RaftkDesigns(C.Structure):
+    _fields_ = [
+        ("n_designs", C.c_int32), ("nw", C.c_int32), ("n_members_total", C.c_int32), ("n_nodes_total", C.c_int32),
+        ("max_nodes", C.c_int32), ("max_members", C.c_int32),
+        ("depth", C.c_double), ("rho", C.c_double), ("g", C.c_double), ("dw", C.c_double),
+        ("w", C.c_void_p), ("k", C.c_void_p), ("member_offset", C.c_void_p),
+        ("mem_frame", C.c_void_p), ("mem_rA", C.c_void_p), ("mem_arm", C.c_void_p),
+        ("mem_node_start", C.c_void_p), ("mem_circ", C.c_void_p),
+        ("node_ls", C.c_void_p), ("node_cd_q", C.c_void_p), ("node_cd_p1", C.c_void_p), ("node_cd_p2", C.c_void_p),
+        ("node_in_q", C.c_void_p), ("node_in_p1", C.c_void_p), ("node_in_p2", C.c_void_p), ("node_pa", C.c_void_p),
+        ("node_in_p1_w", C.c_void_p), ("node_in_p2_w", C.c_void_p),
+        ("M0", C.c_void_p), ("B0", C.c_void_p), ("C0", C.c_void_p), ("A_w", C.c_void_p), ("B_w", C.c_void_p),
+        ("n_bem_head", C.c_int32), ("_pad0", C.c_int32),
+        ("bem_headings", C.c_void_p), ("X_BEM", C.c_void_p), ("bem_xyh", C.c_void_p),
+    ]
+
+
+class RaftkCases(C.Structure):
+    _fields_ = [
+        ("n_cases", C.c_int32), ("_pad0", C.c_int32),
+        ("Hs", C.c_void_p), ("Tp", C.c_void_p), ("gamma", C.c_void_p), ("beta_deg", C.c_void_p),
+        ("spec", C.c_void_p), ("zeta", C.c_void_p),
+    ]
+
+
+class RaftkSolveOpts(C.Structure):
+    _fields_ = [("n_iter", C.c_int32), ("cluster_size", C.c_int32), ("tol", C.c_double), ("xi_start", C.c_double)]
+
+
+class RaftkOutputs(C.Structure):
+    _fields_ = [("Xi", C.c_void_p), ("status", C.c_void_p), ("B_drag", C.c_void_p), ("F_drag", C.c_void_p),
+                ("F_iner", C.c_void_p), ("F_BEM", C.c_void_p), ("zeta", C.c_void_p)]
+
+
+# every symbol include/raftk.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "raftk_version", "raftk_last_error", "raftk_launch_count", "raftk_workspace_bytes",
+    "raftk_hydro_excitation_dev", "raftk_hydro_linearization_dev", "raftk_solve_dynamics_dev",
+    "raftk_hydro_excitation_host", "raftk_hydro_linearization_host", "raftk_solve_dynamics_host",
+    "raftk_system_solve_dev", "raftk_system_solve_host", "raftk_host_alloc", "raftk_host_free",
+    "raftk_fp64_peak_gflops",
+]
+
+
+class RaftkError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "raft_b200: CUDA library %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    lib.raftk_version.restype = C.c_int
+    lib.raftk_last_error.restype = C.c_char_p
+    lib.raftk_launch_count.restype = C.c_longlong
+    lib.raftk_workspace_bytes.restype = C.c_size_t
+    lib.raftk_workspace_bytes.argtypes = [P(RaftkDesigns), C.c_int32]
+    lib.raftk_hydro_excitation_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.raftk_hydro_linearization_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), C.c_void_p, P(RaftkOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.raftk_solve_dynamics_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkSolveOpts), P(RaftkOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.raftk_hydro_excitation_host.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkOutputs)]
+    lib.raftk_hydro_linearization_host.argtypes = [P(RaftkDesigns), P(RaftkCases), C.c_void_p, P(RaftkOutputs)]
+    lib.raftk_solve_dynamics_host.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkSolveOpts), P(RaftkOutputs)]
+    lib.raftk_system_solve_dev.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.raftk_system_solve_host.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.raftk_host_alloc.restype = C.c_void_p
+    lib.raftk_host_alloc.argtypes = [C.c_size_t]
+    lib.raftk_host_free.argtypes = [C.c_void_p]
+    lib.raftk_fp64_peak_gflops.restype = C.c_double
+    lib.raftk_fp64_peak_gflops.argtypes = [C.c_int]
+    for fn in ("raftk_hydro_excitation_dev", "raftk_hydro_linearization_dev", "raftk_solve_dynamics_dev",
+               "raftk_hydro_excitation_host", "raftk_hydro_linearization_host", "raftk_solve_dynamics_host",
+               "raftk_system_solve_dev", "raftk_system_solve_host"):
+        getattr(lib, fn).restype = C.c_int
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    """Translate a negative return code into an exception carrying raftk_last_error()."""
+    if rc != 0:
+        msg = lib.raftk_last_error().decode("utf-8", "replace")
+        if rc == -4:
+            raise ValueError("Wave spectrum input not recognized. (%s)" % msg)
+        raise RaftkError("raftk error %d: %s" % (rc, msg))

@@ -1,0 +1,45 @@
+"""Frequency grid and dispersion relation of the model (host pre-pass, once per Model).
+
+Restates raft_model.py:57 (grid) and helpers.py:377-392 (waveNumber).  The wave number is NOT the
+exact dispersion root: the reference stops its fixed-point iteration at a 1e-3 relative change, and
+parity requires reproducing that, so the same iteration is run here (vectorised over frequency,
+each bin keeps iterating only while its own criterion is unmet, exactly like the scalar loop).
+"""
+import numpy as np
+
+
+def make_w(min_freq, max_freq):
+    """w [rad/s]: np.arange(min_freq, max_freq + 0.5*min_freq, min_freq) * 2 pi  (raft_model.py:57)."""
+    return np.arange(min_freq, max_freq + 0.5 * min_freq, min_freq) * 2 * np.pi
+
+
+def wave_number(w, depth, e=0.001, g=9.81):
+    """k(w) by the reference's fixed-point iteration k <- w^2 / (g tanh(k h))  (helpers.py:377-392)."""
+    w = np.atleast_1d(np.asarray(w, dtype=float))
+    k1 = w * w / g
+    k2 = w * w / (np.tanh(k1 * depth) * g)
+    active = np.abs(k2 - k1) / k1 > e
+    while np.any(active):
+        k1 = np.where(active, k2, k1)
+        k2n = w * w / (np.tanh(k1 * depth) * g)
+        k2 = np.where(active, k2n, k2)
+        active = active & (np.abs(k2 - k1) / k1 > e)
+    return k2
+
+
+def regrid(P, nw, max_freq):
+    """Copy of a packed design on a new grid of ``nw`` bins up to ``max_freq`` Hz (min_freq = max_freq/nw).
+
+    Only for designs without frequency tables (A_w/B_w/X_BEM/MCF) -- those must be re-interpolated
+    by their producer."""
+    for key in ("A_w", "B_w", "X_BEM", "node_in_p1_w"):
+        if key in P and P[key] is not None:
+            raise ValueError("regrid: design carries the frequency table %r" % key)
+    Q = dict(P)
+    w = make_w(max_freq / nw, max_freq)
+    if len(w) != nw:
+        raise ValueError("grid recipe produced %d bins, wanted %d" % (len(w), nw))
+    Q["w"] = w
+    Q["k"] = wave_number(w, float(P["depth"]))
+    Q["dw"] = np.float64(w[1] - w[0])
+    return Q

@@ -6,7 +6,7 @@ the same function packs (a) live reference objects, when ``raft_b200`` is droppe
 install, and (b) the objects built by ``raft_b200.member`` / ``raft_b200.fowt``.
 
 Scope: rigid 6-DOF FOWTs (every member has one structural node that is rigidly tied to the FOWT's
-reference node), no MacCamy-Fuchs, no underwater rotors -- exactly the BASELINE.json configs.
+reference node), no underwater rotors -- the BASELINE.json configs plus MacCamy-Fuchs members.
 Anything else raises ``NotImplementedError`` (the caller falls back to the reference path; see
 SURVEY.md section 8f row 4).
 
@@ -24,10 +24,12 @@ SQRT_8_OVER_PI = np.sqrt(8.0 / np.pi)
 def _member_is_supported(mem):
     if getattr(mem, "type", "rigid") != "rigid":
         raise NotImplementedError("member %r: only rigid members are supported by the B200 path" % mem.name)
-    # MCF only alters Imat, which is computed for strip-theory (potMod False) members only
-    # (raft_member.py:1393, 1415); a potMod member with the MCF flag set is unaffected.
-    if getattr(mem, "MCF", False) and not getattr(mem, "potMod", False):
-        raise NotImplementedError("member %r: MacCamy-Fuchs (complex Imat) not supported" % mem.name)
+
+
+def _uses_mcf(mem):
+    """MacCamy-Fuchs only alters Imat, which is computed for strip-theory (potMod False) members
+    only (raft_member.py:1393, 1415); a potMod member with the MCF flag set is unaffected."""
+    return bool(getattr(mem, "MCF", False)) and not bool(getattr(mem, "potMod", False))
 
 
 def pack_members(fowt, rho=None, g=None):
@@ -42,6 +44,9 @@ def pack_members(fowt, rho=None, g=None):
     prp = np.array(ref.r[:3] if ref is not None else fowt.r6[:3], dtype=float)
 
     mq, mp1, mp2, mrA, mcirc, mstart = [], [], [], [], [], [0]
+    any_mcf = any(_uses_mcf(m) for m in fowt.memberList)
+    nw = len(fowt.w) if any_mcf else 0
+    in_p1_w, in_p2_w, Imat_w, mcf_flag = [], [], [], []
     cols = {k: [] for k in ("r", "mem", "ls", "cd_q", "cd_p1", "cd_p2", "in_q", "in_p1", "in_p2", "pa",
                             "Imat", "a_i", "a_q", "a_p1", "a_p2", "a_End", "Cd_q", "Cd_p1", "Cd_p2", "Cd_End")}
     for mem in fowt.memberList:
@@ -74,12 +79,30 @@ def pack_members(fowt, rho=None, g=None):
                 a_End = np.abs((mem.ds[il, 0] + mem.drs[il, 0]) * (mem.ds[il, 1] + mem.drs[il, 1])
                                - (mem.ds[il, 0] - mem.drs[il, 0]) * (mem.ds[il, 1] - mem.drs[il, 1]))
             pref = SQRT_8_OVER_PI * 0.5 * rho
-            Imat = np.array(mem.Imat[il], dtype=float)
             a_i = float(mem.a_i[il])
-            in_q, in_p1, in_p2 = q @ Imat @ q, p1 @ Imat @ p1, p2 @ Imat @ p2
-            resid = Imat - (in_q * np.outer(q, q) + in_p1 * np.outer(p1, p1) + in_p2 * np.outer(p2, p2))
+            if _uses_mcf(mem):
+                # complex, frequency dependent transverse coefficient (raft_member.py:1415-1420, 1446);
+                # the axial (end) term stays real.  Imat holds the k -> 0 values for reference only.
+                Iw = np.array(mem.Imat_MCF[il], dtype=complex)            # [3,3,nw]
+                Imat = np.real(Iw[:, :, 0])
+                in_q = np.real(np.einsum("a,abw,b->w", q, Iw, q))[0]
+                w1 = np.einsum("a,abw,b->w", p1, Iw, p1)
+                w2 = np.einsum("a,abw,b->w", p2, Iw, p2)
+                in_p1, in_p2 = np.real(w1[0]), np.real(w2[0])
+                resid = Iw - (in_q * np.outer(q, q)[:, :, None] + np.outer(p1, p1)[:, :, None] * w1 + np.outer(p2, p2)[:, :, None] * w2)
+                mcf_flag.append(1)
+            else:
+                Imat = np.array(mem.Imat[il], dtype=float)
+                in_q, in_p1, in_p2 = q @ Imat @ q, p1 @ Imat @ p1, p2 @ Imat @ p2
+                resid = Imat - (in_q * np.outer(q, q) + in_p1 * np.outer(p1, p1) + in_p2 * np.outer(p2, p2))
+                if any_mcf:
+                    w1, w2 = np.full(nw, in_p1, dtype=complex), np.full(nw, in_p2, dtype=complex)
+                    Iw = np.repeat(Imat[:, :, None], nw, axis=2).astype(complex)
+                mcf_flag.append(0)
             if np.abs(resid).max() > 1e-9 * max(1.0, np.abs(Imat).max()):
                 raise NotImplementedError("member %r: Imat is not diagonal in the member frame" % mem.name)
+            if any_mcf:
+                in_p1_w.append(w1), in_p2_w.append(w2), Imat_w.append(Iw)
             cols["r"].append(np.array(mem.r[il], dtype=float))
             cols["mem"].append(im)
             cols["ls"].append(ls)
@@ -105,6 +128,11 @@ def pack_members(fowt, rho=None, g=None):
     for k in ("ls", "cd_q", "cd_p1", "cd_p2", "in_q", "in_p1", "in_p2", "pa", "a_i",
               "a_q", "a_p1", "a_p2", "a_End", "Cd_q", "Cd_p1", "Cd_p2", "Cd_End"):
         out["node_" + k] = np.array(cols[k], dtype=float)
+    if any_mcf:
+        # MacCamy-Fuchs: per-node, per-frequency complex transverse inertia coefficients [Ns,nw]
+        out["node_in_p1_w"] = np.array(in_p1_w, dtype=complex).reshape(ns, nw)
+        out["node_in_p2_w"] = np.array(in_p2_w, dtype=complex).reshape(ns, nw)
+        out["node_Imat_w"] = np.array(Imat_w, dtype=complex).reshape(ns, 3, 3, nw)   # oracle only
     return out
 
 
@@ -114,7 +142,7 @@ def pack_matrices(fowt, nw):
     M0 = M_struc + A_hydro_morison (+ sum A_aero is frequency dependent -> A_w)
     B0 = B_struc + sum B_gyro
     C0 = C_struc + C_hydro + C_moor + C_elast
-    A_w, B_w [nw,6,6]: frequency-dependent parts (A_BEM + sum A_aero, B_BEM + sum B_aero) or None.
+    A_w, B_w [6,6,nw]: frequency-dependent parts (A_BEM + sum A_aero, B_BEM + sum B_aero) or None.
     moorMod 2 (frequency-independent M/A/B_moor from MoorPy) is folded in by the caller if needed.
     """
     n = fowt.nDOF
@@ -144,9 +172,9 @@ def pack_matrices(fowt, nw):
         have = True
     out = dict(M0=M0, B0=B0, C0=C0)
     if have:
-        # freq-major [nw,6,6] (the reference keeps [6,6,nw]); contiguous 6x6 per frequency
-        out["A_w"] = np.ascontiguousarray(np.moveaxis(A_w, 2, 0))
-        out["B_w"] = np.ascontiguousarray(np.moveaxis(B_w, 2, 0))
+        # the reference's own layout [6,6,nw] (frequency fastest) -> coalesced per-frequency reads
+        out["A_w"] = np.ascontiguousarray(A_w)
+        out["B_w"] = np.ascontiguousarray(B_w)
     return out
 
 
@@ -154,7 +182,7 @@ def pack_bem_excitation(fowt):
     """BEM excitation coefficient table for heading interpolation (raft_fowt.py:1796-1849).
 
     Returns ``None`` when the FOWT has no potential-flow excitation, else a dict with
-    X_BEM [nhead, nw, 6] complex128 (freq-major), headings [nhead] (deg), heading_adjust, x_ref, y_ref.
+    X_BEM [nhead, 6, nw] complex128 (the reference's layout), headings [nhead] (deg), heading_adjust.
     """
     if not (getattr(fowt, "potMod", False) or getattr(fowt, "potModMaster", 0) in (2, 3)):
         return None
@@ -162,7 +190,7 @@ def pack_bem_excitation(fowt):
     if X is None:
         return None
     X = np.asarray(X)
-    return dict(X_BEM=np.ascontiguousarray(np.moveaxis(X[:, :6, :], 2, 1)).astype(np.complex128),
+    return dict(X_BEM=np.ascontiguousarray(X[:, :6, :]).astype(np.complex128),
                 bem_headings=np.array(fowt.BEM_headings, dtype=float),
                 heading_adjust=np.float64(fowt.heading_adjust))
 
@@ -195,7 +223,8 @@ def pack_cases(cases):
     def first(v):
         return v if np.isscalar(v) else v[0]
     nC = len(cases)
-    Hs, Tp, gam, beta, spec = (np.zeros(nC) for _ in range(4)) + (np.zeros(nC, dtype=np.int32),)
+    Hs, Tp, gam, beta = (np.zeros(nC) for _ in range(4))
+    spec = np.zeros(nC, dtype=np.int32)
     for i, c in enumerate(cases):
         s = str(first(c.get("wave_spectrum", "JONSWAP")))
         if s not in SPECTRUM_IDS:

@@ -1,0 +1,297 @@
+"""Host-side driver of the C ABI: packed designs + case table -> libraftk.so -> NumPy / torch results.
+
+Two routes, both straight through the C ABI (no CPU fallback anywhere):
+
+* ``solve_dynamics`` / ``hydro_excitation`` / ``hydro_linearization``: HOST buffers in and out
+  (``raftk_*_host``).  This is the reference-facing call: what ``Model.solveDynamics`` would invoke
+  when ``raft_b200`` is dropped into RAFT, and what ``bench.py`` times as ``e2e``.
+* ``DeviceSession``: tables, workspace and outputs resident in HBM as torch tensors
+  (``raftk_*_dev`` on torch's current stream).  ``bench.py`` times this as ``value``; the sweep
+  driver (``raft_b200.sweep``) all-gathers its output tensor over NCCL.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import RaftkCases, RaftkDesigns, RaftkOutputs, RaftkSolveOpts, check, lib
+
+_F8 = np.float64
+_I4 = np.int32
+
+
+class DesignBatch:
+    """CSR concatenation of packed designs (``packer.pack_fowt`` dicts) sharing one frequency grid."""
+
+    NODE_COLS = ("ls", "cd_q", "cd_p1", "cd_p2", "in_q", "in_p1", "in_p2", "pa")
+
+    def __init__(self, packed):
+        if isinstance(packed, dict):
+            packed = [packed]
+        if len(packed) == 0:
+            raise ValueError("DesignBatch needs at least one design")
+        P0 = packed[0]
+        self.n_designs = len(packed)
+        self.w = np.ascontiguousarray(P0["w"], dtype=_F8)
+        self.k = np.ascontiguousarray(P0["k"], dtype=_F8)
+        self.nw = len(self.w)
+        self.depth, self.rho, self.g = float(P0["depth"]), float(P0["rho"]), float(P0["g"])
+        self.dw = float(P0["dw"]) if "dw" in P0 else float(self.w[1] - self.w[0])
+        a = self.arrays = {}
+        member_offset, mem_node_start = [0], [0]
+        frames, rAs, arms, circs = [], [], [], []
+        cols = {c: [] for c in self.NODE_COLS}
+        max_nodes = max_members = 0
+        for P in packed:
+            if len(P["w"]) != self.nw or float(P["depth"]) != self.depth:
+                raise ValueError("all designs of a batch must share the frequency grid and water depth")
+            nm = len(P["mem_circ"])
+            frames.append(np.concatenate([P["mem_q"], P["mem_p1"], P["mem_p2"]], axis=1).reshape(nm, 9))
+            rAs.append(np.asarray(P["mem_rA"], dtype=_F8).reshape(nm, 3))
+            arms.append(np.asarray(P["mem_rA"], dtype=_F8).reshape(nm, 3) - np.asarray(P["prp"], dtype=_F8)[None, :])
+            circs.append(np.asarray(P["mem_circ"], dtype=_I4))
+            base = mem_node_start[-1]
+            ms = np.asarray(P["mem_start"], dtype=np.int64)
+            mem_node_start.extend((base + ms[1:]).tolist())
+            member_offset.append(member_offset[-1] + nm)
+            for c in self.NODE_COLS:
+                cols[c].append(np.asarray(P["node_" + c], dtype=_F8))
+            max_nodes = max(max_nodes, int(ms[-1]))
+            max_members = max(max_members, nm)
+        a["member_offset"] = np.array(member_offset, dtype=_I4)
+        a["mem_frame"] = np.ascontiguousarray(np.concatenate(frames, axis=0), dtype=_F8)
+        a["mem_rA"] = np.ascontiguousarray(np.concatenate(rAs, axis=0), dtype=_F8)
+        a["mem_arm"] = np.ascontiguousarray(np.concatenate(arms, axis=0), dtype=_F8)
+        a["mem_node_start"] = np.array(mem_node_start, dtype=_I4)
+        a["mem_circ"] = np.ascontiguousarray(np.concatenate(circs), dtype=_I4)
+        for c in self.NODE_COLS:
+            a["node_" + c] = np.ascontiguousarray(np.concatenate(cols[c]), dtype=_F8)
+        have_mcf = ["node_in_p1_w" in P and P["node_in_p1_w"] is not None for P in packed]
+        if any(have_mcf):
+            for c in ("in_p1", "in_p2"):
+                a["node_%s_w" % c] = np.ascontiguousarray(np.concatenate([
+                    np.asarray(P["node_%s_w" % c], dtype=np.complex128) if h
+                    else np.repeat(np.asarray(P["node_" + c], dtype=np.complex128)[:, None], self.nw, axis=1)
+                    for P, h in zip(packed, have_mcf)], axis=0))
+        for mname in ("M0", "B0", "C0"):
+            a[mname] = np.ascontiguousarray(np.stack([np.asarray(P[mname], dtype=_F8).reshape(36) for P in packed]))
+        have_w = ["A_w" in P and P["A_w"] is not None for P in packed]
+        if any(have_w):
+            z = np.zeros([36, self.nw])
+            a["A_w"] = np.ascontiguousarray(np.stack([np.asarray(P["A_w"], dtype=_F8).reshape(36, self.nw) if h else z
+                                                      for P, h in zip(packed, have_w)]))
+            a["B_w"] = np.ascontiguousarray(np.stack([np.asarray(P["B_w"], dtype=_F8).reshape(36, self.nw) if h else z
+                                                      for P, h in zip(packed, have_w)]))
+        self.n_bem_head = 0
+        if "X_BEM" in P0 and P0["X_BEM"] is not None:
+            heads = np.ascontiguousarray(P0["bem_headings"], dtype=_F8)
+            self.n_bem_head = len(heads)
+            for P in packed:
+                if "X_BEM" not in P or len(P["bem_headings"]) != self.n_bem_head:
+                    raise ValueError("all designs of a batch must share the BEM heading list")
+            a["bem_headings"] = heads
+            a["X_BEM"] = np.ascontiguousarray(np.stack([np.asarray(P["X_BEM"], dtype=np.complex128) for P in packed]))
+            a["bem_xyh"] = np.ascontiguousarray(np.array(
+                [[float(P.get("x_ref", 0.0)), float(P.get("y_ref", 0.0)), float(P.get("heading_adjust", 0.0))] for P in packed],
+                dtype=_F8))
+        a["w"], a["k"] = self.w, self.k
+        self.n_members_total = int(member_offset[-1])
+        self.n_nodes_total = int(mem_node_start[-1])
+        self.max_nodes = max(1, max_nodes)
+        self.max_members = max(1, max_members)
+
+    def input_bytes(self):
+        return int(sum(v.nbytes for v in self.arrays.values()))
+
+    def struct(self, ptr):
+        """Build the C struct; ``ptr(name)`` returns the address (host or device) of array ``name`` or None."""
+        s = RaftkDesigns()
+        s.n_designs, s.nw = self.n_designs, self.nw
+        s.n_members_total, s.n_nodes_total = self.n_members_total, self.n_nodes_total
+        s.max_nodes, s.max_members = self.max_nodes, self.max_members
+        s.depth, s.rho, s.g, s.dw = self.depth, self.rho, self.g, self.dw
+        for name in ("w", "k", "member_offset", "mem_frame", "mem_rA", "mem_arm", "mem_node_start", "mem_circ",
+                     "node_ls", "node_cd_q", "node_cd_p1", "node_cd_p2", "node_in_q", "node_in_p1", "node_in_p2",
+                     "node_pa", "node_in_p1_w", "node_in_p2_w", "M0", "B0", "C0", "A_w", "B_w",
+                     "bem_headings", "X_BEM", "bem_xyh"):
+            setattr(s, name, ptr(name) if name in self.arrays else None)
+        s.n_bem_head = self.n_bem_head
+        return s
+
+
+class CaseTable:
+    """SoA case table (``packer.pack_cases`` dict, or keyword arrays)."""
+
+    def __init__(self, cases, zeta=None):
+        self.arrays = a = {}
+        for kname in ("Hs", "Tp", "gamma", "beta_deg"):
+            a[kname] = np.ascontiguousarray(cases[kname], dtype=_F8)
+        a["spec"] = np.ascontiguousarray(cases["spec"], dtype=_I4)
+        if np.any((a["spec"] < 0) | (a["spec"] > 3)):
+            raise ValueError("Wave spectrum input not recognized.")       # raft_fowt.py:1774
+        self.n_cases = len(a["Hs"])
+        if zeta is not None:
+            a["zeta"] = np.ascontiguousarray(zeta, dtype=_F8)
+
+    def input_bytes(self):
+        return int(sum(v.nbytes for v in self.arrays.values()))
+
+    def struct(self, ptr):
+        s = RaftkCases()
+        s.n_cases = self.n_cases
+        for name in ("Hs", "Tp", "gamma", "beta_deg", "spec", "zeta"):
+            setattr(s, name, ptr(name) if name in self.arrays else None)
+        return s
+
+
+def _host_ptr(arrays):
+    return lambda name: arrays[name].ctypes.data
+
+
+def _alloc_outputs(nD, nC, nw, want, alloc=np.zeros):
+    shapes = dict(Xi=([nD, nC, 6, nw], np.complex128), status=([nD, nC, 4], _I4), B_drag=([nD, nC, 6, 6], _F8),
+                  F_drag=([nD, nC, 6, nw], np.complex128), F_iner=([nD, nC, 6, nw], np.complex128),
+                  F_BEM=([nD, nC, 6, nw], np.complex128), zeta=([nC, nw], _F8))
+    return {k: alloc(shapes[k][0], dtype=shapes[k][1]) for k in want}
+
+
+def _out_struct(outs, ptr):
+    o = RaftkOutputs()
+    for k in ("Xi", "status", "B_drag", "F_drag", "F_iner", "F_BEM", "zeta"):
+        setattr(o, k, ptr(outs[k]) if k in outs else None)
+    return o
+
+
+def solve_dynamics(batch, cases, n_iter=10, tol=0.01, xi_start=0.0, cluster_size=0,
+                   want=("Xi", "status", "B_drag"), out=None):
+    """Model.solveDynamics for every (design, case), host buffers in/out (raft_model.py:966-1302).
+
+    Returns a dict of NumPy arrays: Xi [nD,nC,6,nw] complex128, status [nD,nC,4] int32
+    (passes, converged, flags, 0), B_drag [nD,nC,6,6], and optionally F_drag / F_iner / F_BEM / zeta.
+    """
+    want = tuple(dict.fromkeys(tuple(want) + ("Xi", "status")))
+    outs = out if out is not None else _alloc_outputs(batch.n_designs, cases.n_cases, batch.nw, want)
+    d = batch.struct(_host_ptr(batch.arrays))
+    c = cases.struct(_host_ptr(cases.arrays))
+    o = RaftkSolveOpts(int(n_iter), int(cluster_size), float(tol), float(xi_start))
+    os_ = _out_struct(outs, lambda a: a.ctypes.data)
+    check(lib.raftk_solve_dynamics_host(C.byref(d), C.byref(c), C.byref(o), C.byref(os_)))
+    return outs
+
+
+def hydro_excitation(batch, cases, want=("F_iner", "F_BEM", "zeta")):
+    """FOWT.calcHydroExcitation for every (design, case) (raft_fowt.py:1732-1888), host buffers."""
+    outs = _alloc_outputs(batch.n_designs, cases.n_cases, batch.nw, want)
+    d = batch.struct(_host_ptr(batch.arrays))
+    c = cases.struct(_host_ptr(cases.arrays))
+    os_ = _out_struct(outs, lambda a: a.ctypes.data)
+    check(lib.raftk_hydro_excitation_host(C.byref(d), C.byref(c), C.byref(os_)))
+    return outs
+
+
+def hydro_linearization(batch, cases, Xi, want=("B_drag", "F_drag")):
+    """FOWT.calcHydroLinearization(Xi) + calcDragExcitation(0) (raft_fowt.py:1891-1957), host buffers.
+
+    ``Xi`` complex [nD,nC,6,nw] (or [6,nw], broadcast to every unit)."""
+    nD, nC, nw = batch.n_designs, cases.n_cases, batch.nw
+    Xi = np.asarray(Xi, dtype=np.complex128)
+    if Xi.shape == (6, nw):
+        Xi = np.broadcast_to(Xi, (nD, nC, 6, nw))
+    Xi = np.ascontiguousarray(Xi)
+    if Xi.shape != (nD, nC, 6, nw):
+        raise ValueError("Xi must have shape [nD,nC,6,nw] or [6,nw]")
+    outs = _alloc_outputs(nD, nC, nw, want)
+    d = batch.struct(_host_ptr(batch.arrays))
+    c = cases.struct(_host_ptr(cases.arrays))
+    os_ = _out_struct(outs, lambda a: a.ctypes.data)
+    check(lib.raftk_hydro_linearization_host(C.byref(d), C.byref(c), Xi.ctypes.data, C.byref(os_)))
+    return outs
+
+
+def system_solve(Z, F):
+    """Farm system response (raft_model.py:1164-1216): Z [nw,n,n], F [nw,n] or [nw,n,nrhs] -> Xi, info."""
+    Z = np.array(Z, dtype=np.complex128, order="C")
+    F = np.array(F, dtype=np.complex128, order="C")
+    squeeze = F.ndim == 2
+    if squeeze:
+        F = np.ascontiguousarray(F[:, :, None])
+    nw, n, nrhs = F.shape
+    if Z.shape != (nw, n, n):
+        raise ValueError("Z must be [nw,n,n] matching F")
+    info = np.zeros(nw, dtype=_I4)
+    check(lib.raftk_system_solve_host(n, nw, nrhs, Z.ctypes.data, F.ctypes.data, info.ctypes.data))
+    return (F[:, :, 0] if squeeze else F), info
+
+
+def pinned_empty(shape, dtype):
+    """NumPy array backed by page-locked host memory (cudaHostAlloc) for the e2e path."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib.raftk_host_alloc(max(n, 1))
+    if not p:
+        raise MemoryError("cudaHostAlloc failed")
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    arr._raftk_pinned = (buf, p)    # keep alive; freed at process exit
+    return arr
+
+
+class DeviceSession:
+    """Tables, workspace and outputs resident in HBM (torch tensors); kernels on torch's current stream."""
+
+    def __init__(self, batch, cases, device=None, want=("Xi", "status", "B_drag"), workspace_bytes=None):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.batch, self.cases = batch, cases
+        with torch.cuda.device(self.device):
+            self.dt = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.float64) if v.dtype == np.complex128 else v).to(self.device)
+                       for k, v in batch.arrays.items()}
+            self.ct = {k: torch.from_numpy(v).to(self.device) for k, v in cases.arrays.items()}
+            self.d_struct = batch.struct(lambda name: self.dt[name].data_ptr())
+            self.c_struct = cases.struct(lambda name: self.ct[name].data_ptr())
+            need = lib.raftk_workspace_bytes(C.byref(self.d_struct), cases.n_cases)
+            self.workspace_bytes = int(need if workspace_bytes is None else workspace_bytes)
+            self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+            nD, nC, nw = batch.n_designs, cases.n_cases, batch.nw
+            want = tuple(dict.fromkeys(tuple(want) + ("Xi", "status")))
+            shapes = dict(Xi=([nD, nC, 6, nw], torch.complex128), status=([nD, nC, 4], torch.int32),
+                          B_drag=([nD, nC, 6, 6], torch.float64), F_drag=([nD, nC, 6, nw], torch.complex128),
+                          F_iner=([nD, nC, 6, nw], torch.complex128), F_BEM=([nD, nC, 6, nw], torch.complex128),
+                          zeta=([nC, nw], torch.float64))
+            self.out = {k: torch.zeros(shapes[k][0], dtype=shapes[k][1], device=self.device) for k in want}
+            self.o_struct = _out_struct(self.out, lambda t: t.data_ptr())
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def solve(self, n_iter=10, tol=0.01, xi_start=0.0, cluster_size=0):
+        """Enqueue Model.solveDynamics for all units on the current stream; returns the output dict (async)."""
+        o = RaftkSolveOpts(int(n_iter), int(cluster_size), float(tol), float(xi_start))
+        with self.torch.cuda.device(self.device):
+            check(lib.raftk_solve_dynamics_dev(C.byref(self.d_struct), C.byref(self.c_struct), C.byref(o),
+                                               C.byref(self.o_struct), self.workspace.data_ptr(), self.workspace_bytes,
+                                               self._stream()))
+        return self.out
+
+    def excitation(self):
+        with self.torch.cuda.device(self.device):
+            check(lib.raftk_hydro_excitation_dev(C.byref(self.d_struct), C.byref(self.c_struct), C.byref(self.o_struct),
+                                                 self.workspace.data_ptr(), self.workspace_bytes, self._stream()))
+        return self.out
+
+    def linearization(self, Xi):
+        """Xi: complex128 torch tensor [nD,nC,6,nw] on the session's device (after ``excitation``)."""
+        with self.torch.cuda.device(self.device):
+            check(lib.raftk_hydro_linearization_dev(C.byref(self.d_struct), C.byref(self.c_struct), Xi.data_ptr(),
+                                                    C.byref(self.o_struct), self.workspace.data_ptr(),
+                                                    self.workspace_bytes, self._stream()))
+        return self.out
+
+
+def launch_count():
+    return int(lib.raftk_launch_count())
+
+
+def fp64_peak_gflops(iters=20000):
+    return float(lib.raftk_fp64_peak_gflops(int(iters)))

@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ (run in the BUILD CONTAINER only).
+
+Needs the read-only reference tree at /root/reference; nothing here travels to the GPU box except
+the .npz files it writes.  Two sources of truth go into every fixture:
+
+  ref_pickle_*  : arrays copied out of the reference's OWN golden pickles
+                  (/root/reference/tests/test_data/<design>_true_hydroExcitation.pkl, ..._hydroLinearization.pkl;
+                  produced by tests/test_fowt.py:111-175 of the reference with the full turbine+mooring design)
+  ref_run_*     : outputs of the UNMODIFIED reference executed here under the stub harness
+                  (oracle/ref_harness.py: moorpy/ccblade/matplotlib stubbed, turbine+mooring stripped,
+                  synthetic C_moor) -- FOWT.calcHydroExcitation / calcHydroLinearization / Model.solveDynamics
+  P_*           : the packed input tables (raft_b200.packer.pack_fowt on the live reference objects)
+
+Usage:  python tests/golden/make_golden.py [--only NAME]
+"""
+import argparse
+import os
+import pickle
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as rh  # noqa: E402
+from raft_b200 import packer  # noqa: E402
+
+REF = rh.REF_ROOT
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def seeded_cases(seed, n):
+    """SURVEY.md 8d sea-state distribution: Hs~U[1,10], Tp~U[5,18], gamma=0 (IEC auto), beta~U[-180,180)."""
+    rng = np.random.default_rng(seed)
+    Hs = rng.uniform(1, 10, n)
+    Tp = rng.uniform(5, 18, n)
+    beta = rng.uniform(-180, 180, n)
+    return Hs, Tp, beta
+
+
+def count_passes(fowt):
+    """Wrap calcHydroLinearization to count the passes of the drag loop (raft_model.py:1063)."""
+    cnt = [0]
+    orig = fowt.calcHydroLinearization
+
+    def wrapped(Xi):
+        cnt[0] += 1
+        return orig(Xi)
+    fowt.calcHydroLinearization = wrapped
+    return cnt, orig
+
+
+def run_solves(model, cases):
+    fowt = model.fowtList[0]
+    cnt, orig = count_passes(fowt)
+    Xi, passes = [], []
+    for (Hs, Tp, beta) in cases:
+        cnt[0] = 0
+        x = rh.solve_dynamics(model, rh.make_case(Hs, Tp, beta))
+        Xi.append(np.array(x[0]))
+        passes.append(cnt[0])
+    fowt.calcHydroLinearization = orig
+    return np.array(Xi), np.array(passes, dtype=np.int32)
+
+
+def fixture(name, yaml_path, nw=None, max_freq=None, solve_cases=(), pickles=None, lin_check=True):
+    t0 = time.time()
+    design = rh.load_design(yaml_path, nw=nw, max_freq=max_freq)
+    model = rh.build_model(design)
+    fowt = model.fowtList[0]
+    P = packer.pack_fowt(fowt)
+    out = {"P_" + k: np.asarray(v) for k, v in P.items()}
+    out["n_iter"] = np.int32(int(model.nIter))
+    out["xi_start"] = np.float64(model.XiStart)
+    out["C_moor"] = np.array(fowt.C_moor)
+    out["A_hydro_morison"] = np.array(fowt.A_hydro_morison)
+
+    if pickles:
+        with open(pickles + "_true_hydroExcitation.pkl", "rb") as f:
+            tv = pickle.load(f)
+        out["ref_pickle_exc_heading"] = np.array([t["case"]["wave_heading"] for t in tv], dtype=float)
+        out["ref_pickle_exc_period"] = np.array([t["case"]["wave_period"] for t in tv], dtype=float)
+        out["ref_pickle_exc_height"] = np.array([t["case"]["wave_height"] for t in tv], dtype=float)
+        out["ref_pickle_exc_F_hydro_iner"] = np.array([t["F_hydro_iner"][0] for t in tv])
+        assert np.allclose(tv[0]["w"], P["w"])
+        with open(pickles + "_true_hydroLinearization.pkl", "rb") as f:
+            tv = pickle.load(f)
+        out["ref_pickle_lin_B_hydro_drag"] = np.array(tv["B_hydro_drag"])
+        out["ref_pickle_lin_F_hydro_drag"] = np.array(tv["F_hydro_drag"])
+        with open(pickles + "_true_hydroConstants.pkl", "rb") as f:
+            tv = pickle.load(f)
+        out["ref_pickle_A_hydro_morison"] = np.array(tv["A_hydro_morison"])
+
+    if lin_check:
+        # the reference's own linearisation test recipe (tests/test_fowt.py:150-175), run live
+        case = dict(rh.make_case(2, 10, 0), wave_spectrum="unit")
+        fowt.calcHydroExcitation(case, memberList=fowt.memberList)
+        phase = np.linspace(0, 2 * np.pi, fowt.nw * fowt.nDOF).reshape(fowt.nDOF, fowt.nw)
+        Xi = 0.1 * np.exp(1j * phase)
+        out["ref_run_lin_Xi"] = Xi
+        out["ref_run_lin_B_hydro_drag"] = np.array(fowt.calcHydroLinearization(Xi))
+        out["ref_run_lin_F_hydro_drag"] = np.array(fowt.calcDragExcitation(0))
+        out["ref_run_lin_F_hydro_iner"] = np.array(fowt.F_hydro_iner[0])
+        out["ref_run_lin_F_BEM"] = np.array(fowt.F_BEM[0])
+        out["ref_run_lin_zeta"] = np.array(fowt.zeta[0])
+
+    if len(solve_cases):
+        Xi, passes = run_solves(model, solve_cases)
+        out["ref_run_solve_cases"] = np.array(solve_cases, dtype=float)      # rows (Hs, Tp, heading_deg)
+        out["ref_run_solve_Xi"] = Xi
+        out["ref_run_solve_passes"] = passes
+
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-28s nw=%4d Ns=%3d cases=%2d  %.1f s  %.0f KB" % (name, len(P["w"]), len(P["node_ls"]), len(solve_cases),
+                                                             time.time() - t0, os.path.getsize(path) / 1024))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    td = os.path.join(REF, "tests", "test_data")
+    jobs = []
+    # the reference's own test designs / grids (nw = 40) + its golden pickles
+    for nm in ("OC3spar", "VolturnUS-S", "OC4semi-WAMIT_Coefs"):
+        cases = [(2.0, 8.0, 0.0), (6.0, 12.0, 30.0), (9.5, 15.0, -135.0), (1.2, 5.5, 90.0)]
+        jobs.append(dict(name="test_" + nm, yaml_path=os.path.join(td, nm + ".yaml"), solve_cases=cases,
+                         pickles=os.path.join(td, nm)))
+    # BASELINE.json configs at reduced size (same recipes as SURVEY.md 8d, fewer bins/cases)
+    Hs, Tp, beta = seeded_cases(2, 6)
+    jobs.append(dict(name="cfg1_OC3spar", yaml_path=os.path.join(REF, "designs", "OC3spar.yaml"),
+                     solve_cases=[(2.0, 8.0, 0.0)]))
+    jobs.append(dict(name="cfg2_VolturnUS-S_nw64", yaml_path=os.path.join(REF, "designs", "VolturnUS-S.yaml"),
+                     nw=64, max_freq=0.512, solve_cases=list(zip(Hs, Tp, beta))))
+    Hs, Tp, beta = seeded_cases(3, 4)
+    jobs.append(dict(name="cfg3_OC4semi-WAMIT_nw128", yaml_path=os.path.join(REF, "examples", "OC4semi-WAMIT_Coefs.yaml"),
+                     nw=128, max_freq=0.256, solve_cases=list(zip(Hs, Tp, beta))))
+    for j in jobs:
+        if args.only and args.only not in j["name"]:
+            continue
+        fixture(**j)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI, against
+(a) the golden fixtures (reference pickles + reference runs) and (b) the C oracle on larger seeded inputs.
+
+Tolerance: BASELINE.json north_star states fp64 rtol 1e-10 on the RAOs; the metric is
+conftest.response_err (per frequency, relative to the largest amplitude in the DOF's unit group).
+Pass counts of the drag-linearisation loop must match exactly."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, relerr, response_err
+
+pytestmark = pytest.mark.gpu
+NAMES = golden_names()
+PICKLED = [n for n in NAMES if n.startswith("test_")]
+RTOL = 1e-10
+
+
+def sea_states(seed, n):
+    rng = np.random.default_rng(seed)
+    return dict(Hs=rng.uniform(1, 10, n), Tp=rng.uniform(5, 18, n), gamma=np.zeros(n), beta_deg=rng.uniform(-180, 180, n),
+                spec=np.zeros(n, dtype=np.int32))
+
+
+@pytest.fixture(scope="module")
+def solver():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from raft_b200 import solver as s
+    return s
+
+
+@pytest.mark.parametrize("name", PICKLED)
+def test_excitation_vs_reference_pickle(name, solver):
+    """FOWT.calcHydroExcitation vs the reference's 72-case golden pickle, all cases in one launch."""
+    G, P = load_golden(name)
+    n = len(G["ref_pickle_exc_F_hydro_iner"])
+    cases = solver.CaseTable(dict(Hs=G["ref_pickle_exc_height"].reshape(n), Tp=G["ref_pickle_exc_period"].reshape(n),
+                                  gamma=np.zeros(n), beta_deg=G["ref_pickle_exc_heading"].reshape(n), spec=np.zeros(n, dtype=np.int32)))
+    out = solver.hydro_excitation(solver.DesignBatch(P), cases)
+    ref = G["ref_pickle_exc_F_hydro_iner"]
+    if np.abs(ref).max() > 0:
+        assert relerr(out["F_iner"][0], ref) < RTOL
+    else:
+        assert np.abs(out["F_iner"]).max() == 0
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_excitation_and_linearization_vs_reference_run(name, solver):
+    """calcHydroExcitation + calcHydroLinearization(Xi) + calcDragExcitation(0) vs the reference run (unit spectrum)."""
+    G, P = load_golden(name)
+    cases = solver.CaseTable(dict(Hs=[2.0], Tp=[10.0], gamma=[0.0], beta_deg=[0.0], spec=np.array([1], dtype=np.int32)))
+    b = solver.DesignBatch(P)
+    exc = solver.hydro_excitation(b, cases)
+    assert relerr(exc["zeta"][0], G["ref_run_lin_zeta"]) < 1e-14
+    for mine, key in ((exc["F_iner"][0, 0], "ref_run_lin_F_hydro_iner"), (exc["F_BEM"][0, 0], "ref_run_lin_F_BEM")):
+        if np.abs(G[key]).max() > 0:
+            assert relerr(mine, G[key]) < RTOL
+        else:
+            assert np.abs(mine).max() == 0
+    lin = solver.hydro_linearization(b, cases, G["ref_run_lin_Xi"])
+    assert relerr(lin["B_drag"][0, 0], G["ref_run_lin_B_hydro_drag"]) < RTOL
+    assert relerr(lin["F_drag"][0, 0], G["ref_run_lin_F_hydro_drag"]) < RTOL
+    if "ref_pickle_lin_B_hydro_drag" in G:
+        assert relerr(lin["B_drag"][0, 0], G["ref_pickle_lin_B_hydro_drag"]) < RTOL
+        assert relerr(lin["F_drag"][0, 0], G["ref_pickle_lin_F_hydro_drag"]) < RTOL
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("cluster", [0, 1, 2])
+def test_solve_dynamics_vs_reference_run(name, cluster, solver):
+    """Model.solveDynamics vs the unmodified reference: responses within 1e-10, identical pass counts."""
+    G, P = load_golden(name)
+    sc = G["ref_run_solve_cases"]
+    cases = solver.CaseTable(dict(Hs=sc[:, 0], Tp=sc[:, 1], gamma=np.zeros(len(sc)), beta_deg=sc[:, 2],
+                                  spec=np.zeros(len(sc), dtype=np.int32)))
+    out = solver.solve_dynamics(solver.DesignBatch(P), cases, n_iter=int(G["n_iter"]), xi_start=float(G["xi_start"]),
+                                cluster_size=cluster)
+    assert np.array_equal(out["status"][0, :, 0], G["ref_run_solve_passes"])
+    assert np.all(out["status"][0, :, 1] == 1) and np.all(out["status"][0, :, 2] == 0)
+    assert response_err(out["Xi"][0], G["ref_run_solve_Xi"]) < RTOL
+
+
+@pytest.mark.parametrize("name,nw,max_freq,nC", [("cfg2_VolturnUS-S_nw64", 256, 0.512, 12), ("cfg1_OC3spar", 333, 0.40, 5)])
+@pytest.mark.parametrize("cluster", [1, 4, 8])
+def test_solve_dynamics_vs_oracle_seeded(name, nw, max_freq, nC, cluster, solver, oracle):
+    """Larger seeded sweeps against the C oracle (which is pinned to the reference), incl. ragged nw and clusters."""
+    from raft_b200 import grid
+    _, P = load_golden(name)
+    Q = grid.regrid(P, nw, max_freq)
+    cs = sea_states(7, nC)
+    out = solver.solve_dynamics(solver.DesignBatch(Q), solver.CaseTable(cs), n_iter=10, cluster_size=cluster)
+    Xi_o, st_o, _ = oracle.solve_cases(oracle.OracleDesign(Q), cs, nIter=10)
+    assert np.array_equal(out["status"][0, :, 0], st_o[:, 0])
+    assert np.array_equal(out["status"][0, :, 1], st_o[:, 1])
+    assert response_err(out["Xi"][0], Xi_o) < RTOL
+
+
+def test_bem_design_vs_oracle_seeded(solver, oracle):
+    _, P = load_golden("cfg3_OC4semi-WAMIT_nw128")
+    cs = sea_states(3, 9)
+    cs["beta_deg"][:3] = [0.0, 360.0, -180.0]          # heading-bracket edge cases (raft_fowt.py:1810-1828)
+    out = solver.solve_dynamics(solver.DesignBatch(P), solver.CaseTable(cs), n_iter=10, want=("Xi", "status", "F_BEM"))
+    od = oracle.OracleDesign(P)
+    Xi_o, st_o, _ = oracle.solve_cases(od, cs, nIter=10)
+    assert np.array_equal(out["status"][0, :, 0], st_o[:, 0])
+    assert response_err(out["Xi"][0], Xi_o) < RTOL
+    for c in range(3):
+        _, F_BEM, _, _ = oracle.calc_hydro_excitation(od, 0, cs["Hs"][c], cs["Tp"][c], 0.0, cs["beta_deg"][c])
+        assert relerr(out["F_BEM"][0, c], F_BEM) < RTOL
+
+
+def test_design_batch_and_device_session(solver, oracle):
+    """Several designs x cases in one batch; device-resident path equals the host path bit for bit."""
+    import torch
+    from raft_b200 import grid
+    _, Pa = load_golden("cfg2_VolturnUS-S_nw64")
+    _, Pb = load_golden("cfg1_OC3spar")
+    Qa, Qb = grid.regrid(Pa, 96, 0.384), grid.regrid(Pb, 96, 0.384)
+    Qb["depth"] = Qa["depth"]; Qb["k"] = Qa["k"]            # one batch shares the site
+    Qc = dict(Qa); Qc["C0"] = Qa["C0"] * 1.3
+    batch = solver.DesignBatch([Qa, Qb, Qc])
+    cs = sea_states(11, 5)
+    host = solver.solve_dynamics(batch, solver.CaseTable(cs), n_iter=10)
+    for d, Q in enumerate((Qa, Qb, Qc)):
+        Xi_o, st_o, _ = oracle.solve_cases(oracle.OracleDesign(Q), cs, nIter=10)
+        assert np.array_equal(host["status"][d, :, 0], st_o[:, 0])
+        assert response_err(host["Xi"][d], Xi_o) < RTOL
+    sess = solver.DeviceSession(batch, solver.CaseTable(cs))
+    dev = sess.solve(n_iter=10)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev["Xi"].cpu().numpy(), host["Xi"])
+    assert np.array_equal(dev["status"].cpu().numpy(), host["status"])
+    # a workspace smaller than the batch forces design chunking: same answer
+    small = solver.DeviceSession(batch, solver.CaseTable(cs), workspace_bytes=sess.workspace_bytes // 2)
+    dev2 = small.solve(n_iter=10)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev2["Xi"].cpu().numpy(), host["Xi"])
+
+
+def test_edge_cases(solver, oracle):
+    """Still water, unit/constant spectra, non-converging loop (n_iter=0,1), XiStart != 0, explicit zeta."""
+    _, P = load_golden("cfg1_OC3spar")
+    b = solver.DesignBatch(P)
+    od = oracle.OracleDesign(P)
+    cs = dict(Hs=np.array([3.0, 3.0, 3.0, 3.0]), Tp=np.array([9.0] * 4), gamma=np.array([0.0, 3.3, 0.0, 0.0]),
+              beta_deg=np.array([15.0, 15.0, 15.0, 15.0]), spec=np.array([3, 0, 1, 2], dtype=np.int32))
+    for n_iter, xi0 in ((0, 0.0), (1, 0.0), (10, 0.1)):
+        out = solver.solve_dynamics(b, solver.CaseTable(cs), n_iter=n_iter, xi_start=xi0)
+        Xi_o, st_o, _ = oracle.solve_cases(od, cs, nIter=n_iter, XiStart=xi0)
+        assert np.array_equal(out["status"][0, :, :2], st_o[:, :2])
+        assert response_err(out["Xi"][0, 1:], Xi_o[1:]) < RTOL
+        assert np.abs(out["Xi"][0, 0] - Xi_o[0]).max() <= 1e-10 * max(1e-300, np.abs(Xi_o[0]).max()) or np.abs(Xi_o[0]).max() == 0
+    zeta = np.abs(np.sin(np.arange(b.nw) * 0.1))[None, :] * 0.3
+    out = solver.solve_dynamics(b, solver.CaseTable({k: v[:1] for k, v in cs.items()}, zeta=zeta), n_iter=10, want=("Xi", "status", "zeta"))
+    assert np.array_equal(out["zeta"], zeta)
+    assert out["status"][0, 0, 1] == 1 and np.isfinite(out["Xi"]).all()
+    with pytest.raises(ValueError):
+        solver.CaseTable(dict(cs, spec=np.array([0, 1, 2, 7], dtype=np.int32)))
+
+
+def test_system_solve_vs_oracle(solver, oracle):
+    """Farm 6N x 6N system response (raft_model.py:1164-1216) vs the oracle's inverse-based response."""
+    rng = np.random.default_rng(5)
+    for n, nw, nrhs in ((12, 64, 1), (48, 33, 3), (96, 16, 2)):
+        A = rng.normal(size=(nw, n, n)) + 1j * rng.normal(size=(nw, n, n)) + 4 * np.eye(n)[None]
+        F = rng.normal(size=(nw, n, nrhs)) + 1j * rng.normal(size=(nw, n, nrhs))
+        X, info = solver.system_solve(A, F)
+        assert np.all(info == 0)
+        for r in range(nrhs):
+            Xo = oracle.system_response(A, F[:, :, r])
+            assert relerr(X[:, :, r], Xo) < 1e-11
