@@ -67,7 +67,7 @@ def test_excitation_and_linearization_vs_reference_run(name, solver):
 
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("cluster", [0, 1, 2])
-def test_solve_dynamics_vs_reference_run(name, cluster, solver):
+def test_solve_dynamics_vs_reference_run(name, cluster, solver, oracle):
     """Model.solveDynamics vs the unmodified reference: responses within 1e-10, identical pass counts."""
     G, P = load_golden(name)
     sc = G["ref_run_solve_cases"]
@@ -76,7 +76,10 @@ def test_solve_dynamics_vs_reference_run(name, cluster, solver):
     out = solver.solve_dynamics(solver.DesignBatch(P), cases, n_iter=int(G["n_iter"]), xi_start=float(G["xi_start"]),
                                 cluster_size=cluster)
     assert np.array_equal(out["status"][0, :, 0], G["ref_run_solve_passes"])
-    assert np.all(out["status"][0, :, 1] == 1) and np.all(out["status"][0, :, 2] == 0)
+    # converged flag: the reference only prints a warning when the loop runs out (raft_model.py:1138-1140);
+    # the pinned oracle carries the flag
+    _, st_o, _ = oracle.solve_cases(oracle.OracleDesign(P), cases.arrays, nIter=int(G["n_iter"]), XiStart=float(G["xi_start"]))
+    assert np.array_equal(out["status"][0, :, 1], st_o[:, 1]) and np.all(out["status"][0, :, 2] == 0)
     assert response_err(out["Xi"][0], G["ref_run_solve_Xi"]) < RTOL
 
 
