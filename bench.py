@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- RAO solves/s of the B200-native hot path (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|sweep]
+
+A "step" is one pass of the hot path (Model.solveDynamics for every (design, case) unit of the batch:
+excitation tables, drag-linearisation fixed-point loop, 6x6 complex impedance solve per frequency).
+
+workload cfg2 (default; BASELINE.json configs[1]): VolturnUS-S strip-theory platform, 1024 bins
+    (max_freq 0.512 Hz), 64 JONSWAP sea states (seed 2: Hs~U[1,10], Tp~U[5,18], IEC gamma,
+    heading~U[-180,180)), nIter 10, tol 0.01, fp64.  65536 RAO solves per step per GPU.
+    N > 1: weak scaling -- every rank gets its own 64 sea states (slice r of the seed-2 stream of 64N)
+    and the step ends with ONE all-gather of the RAO block over NCCL (the path's only collective).
+workload sweep (BASELINE.json configs[3] shard): 1250 VolturnUS-S geometry variants x 16 sea states x
+    512 bins per GPU (10000 designs at N = 8), all-gather of the RAOs at the end of the step.
+
+value = units of all ranks / max-over-ranks device time (CUDA events, inputs resident in HBM).
+e2e   = same metric through the host-buffer C-ABI call (pinned host inputs -> H2D -> kernels -> D2H).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RAO solves/sec (freq-bins x cases x designs)"
+UNIT = "solves/s"
+
+
+def sea_states(seed, n):
+    rng = np.random.default_rng(seed)
+    return dict(Hs=rng.uniform(1, 10, n), Tp=rng.uniform(5, 18, n), gamma=np.zeros(n),
+                beta_deg=rng.uniform(-180, 180, n), spec=np.zeros(n, dtype=np.int32))
+
+
+def load_packed(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    return {k[2:]: z[k] for k in z.files if k.startswith("P_")}
+
+
+def build_workload(args, rank, world):
+    """-> (list of packed designs, case dict, config dict) for this rank."""
+    from raft_b200 import grid
+    if args.workload == "cfg2":
+        P = grid.regrid(load_packed("cfg2_VolturnUS-S_nw64"), args.nw or 1024, 0.512)
+        nC = args.cases or 64
+        cs_all = sea_states(2, nC * world)
+        cs = {k: v[rank * nC:(rank + 1) * nC] for k, v in cs_all.items()}
+        cfg = dict(workload="cfg2: designs/VolturnUS-S.yaml (strip theory, turbine+mooring stripped, C_moor=diag(7e4,7e4,0,0,0,1.2e8)), "
+                            "%d freq bins x %d sea states per GPU, fp64, nIter=10, tol=0.01" % (len(P["w"]), nC),
+                   designs_per_gpu=1, cases_per_gpu=nC, nw=len(P["w"]), submerged_nodes=int(len(P["node_ls"])))
+        return [P], cs, cfg
+    else:
+        from raft_b200 import sweep
+        nD = args.designs or 1250
+        nC = args.cases or 16
+        designs = sweep.volturnus_variants(nD * world, seed=40, nw=args.nw or 512, max_freq=0.40)[rank * nD:(rank + 1) * nD]
+        cs = sea_states(4, nC)
+        cfg = dict(workload="sweep: %d synthetic VolturnUS-S geometry variants x %d sea states x %d bins per GPU, fp64" % (nD, nC, len(designs[0]["w"])),
+                   designs_per_gpu=nD, cases_per_gpu=nC, nw=len(designs[0]["w"]))
+        return designs, cs, cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(max(mx)) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def algorithmic_bytes_per_solve(Ns, Nm, nC, nw, bem=False):
+    """Xi out (96) + zeta in (8) + per-frequency tables / nC + per-design tables / (nC nw)."""
+    T_f = 784 if bem else 16
+    T_d = 208 * Ns + 72 * Nm + 864
+    return 96 + 8 + T_f / nC + T_d / (nC * nw)
+
+
+def algorithmic_flops_per_solve(Ns, passes):
+    """(250 Ns + 1.7e3) per pass + 150 Ns for the excitation pass (fp64, real flops)."""
+    return (250 * Ns + 1.7e3) * passes + 150 * Ns
+
+
+def cpu_oracle_rate(designs, cs, min_seconds, nthreads=0):
+    """Time the pinned C oracle (kind 'port') on all host threads over a bounded sample of the workload."""
+    from oracle import oracle as orc
+    orc.build()
+    ods = [orc.OracleDesign(P) for P in designs]
+    nw = ods[0].nw
+    orc.solve_cases(ods[0], {k: v[:1] for k, v in cs.items()}, nIter=10)      # warm-up / page-in
+    done, t0, used = 0, time.perf_counter(), 1
+    while True:
+        for od in ods:
+            _, _, used = orc.solve_cases(od, cs, nIter=10, nthreads=nthreads)
+            done += len(cs["Hs"]) * nw
+            if time.perf_counter() - t0 > min_seconds:
+                break
+        if time.perf_counter() - t0 > min_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, used, done, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the pinned oracle port, all host threads."""
+    if rank != 0:
+        return
+    designs, cs, cfg = build_workload(args, 0, 1)
+    if len(designs) > 8:
+        designs = designs[:8]                        # bounded sample of the sweep
+    from oracle import oracle as orc
+    orc.build()
+    ods = [orc.OracleDesign(P) for P in designs]
+    nw = ods[0].nw
+    units = len(designs) * len(cs["Hs"]) * nw
+    used = 1
+    for _ in range(args.warmup):
+        orc.solve_cases(ods[0], cs, nIter=10)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for od in ods:
+            _, _, used = orc.solve_cases(od, cs, nIter=10)
+    dt = time.perf_counter() - t0
+    val = units * args.steps / dt
+    sample = "%d design(s) x %d sea states x %d bins per step, %d steps" % (len(designs), len(cs["Hs"]), nw, args.steps)
+    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", config=cfg, impl="reference",
+                cpu_baseline=dict(value=val, unit=UNIT, cores=int(used), kind="port", sample=sample),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "sweep"])
+    ap.add_argument("--nw", type=int, default=0)
+    ap.add_argument("--cases", type=int, default=0)
+    ap.add_argument("--designs", type=int, default=0)
+    ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from raft_b200 import solver
+
+    designs, cs, cfg = build_workload(args, rank, world)
+    batch, cases = solver.DesignBatch(designs), solver.CaseTable(cs)
+    nD, nC, nw = batch.n_designs, cases.n_cases, batch.nw
+    units = nD * nC * nw
+    sess = solver.DeviceSession(batch, cases, device=dev)
+    Xi = sess.out["Xi"]
+    gathered = torch.empty((world,) + tuple(Xi.shape), dtype=Xi.dtype, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step():
+        sess.solve(n_iter=10, tol=0.01, xi_start=0.0, cluster_size=args.cluster)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, Xi)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = solver.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1)                       # not timed: evicts the previous step's tables/outputs from L2
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = solver.launch_count() - launches0
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = units * world * args.steps / (ms * 1e-3)
+    status = sess.out["status"].cpu().numpy()
+    mean_passes = float(status[..., 0].mean())
+
+    # ---- roofline of the dominant kernel (drag-linearise + solve), timed live with CUDA events ----
+    solver.profile_enable(True)
+    kms, kn = [0.0, 0.0, 0.0], [0, 0, 0]
+    reps = max(3, min(args.steps, 10))
+    for _ in range(reps):
+        flush.fill_(1)
+        sess.solve(n_iter=10, tol=0.01, xi_start=0.0, cluster_size=args.cluster)
+        m, n = solver.profile_read()
+        kms = [x + y for x, y in zip(kms, m)]
+        kn = [x + y for x, y in zip(kn, n)]
+    solver.profile_enable(False)
+    k2_ms = kms[2] / max(kn[2], 1)
+    launches_per_step = kn[2] / reps
+    Ns, Nm = batch.max_nodes, batch.max_members
+    b_alg = algorithmic_bytes_per_solve(Ns, Nm, nC, nw, bem=batch.n_bem_head > 0)
+    units_per_launch = units / launches_per_step
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = b_alg * units_per_launch / (k2_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    roofline = dict(bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak, traffic=traffic,
+                    kernel="k_drag_solve", kernel_ms=k2_ms, share_of_step=kms[2] / max(sum(kms), 1e-30),
+                    algorithmic_bytes_per_solve=b_alg, peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                    other_kernels_ms=dict(depth_table=kms[0] / max(kn[0], 1), excitation=kms[1] / max(kn[1], 1)))
+    fp64_peak = solver.fp64_peak_gflops(20000) if rank == 0 else 0.0
+    f_alg = algorithmic_flops_per_solve(Ns, mean_passes)
+    fp64_ach = f_alg * units_per_launch / (k2_ms * 1e-3) / 1e9
+    roofline_fp64 = dict(bound="fp64", achieved=fp64_ach / 1e3, peak=fp64_peak / 1e3, unit="TFLOP/s",
+                         frac=(fp64_ach / fp64_peak) if fp64_peak > 0 else None, algorithmic_flops_per_solve=f_alg,
+                         mean_passes=mean_passes, peak_source="DFMA micro-kernel measured in this run")
+
+    # ---- e2e: host buffers through the reference-facing C-ABI call, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        for k_, v in list(batch.arrays.items()):
+            p = solver.pinned_empty(v.shape, v.dtype); p[...] = v; batch.arrays[k_] = p
+        for k_, v in list(cases.arrays.items()):
+            p = solver.pinned_empty(v.shape, v.dtype); p[...] = v; cases.arrays[k_] = p
+        outs = dict(Xi=solver.pinned_empty([nD, nC, 6, nw], np.complex128), status=solver.pinned_empty([nD, nC, 4], np.int32),
+                    B_drag=solver.pinned_empty([nD, nC, 6, 6], np.float64))
+        h2d = batch.input_bytes() + cases.input_bytes()
+        d2h = int(sum(v.nbytes for v in outs.values()))
+        for _ in range(args.warmup):
+            solver.solve_dynamics(batch, cases, n_iter=10, cluster_size=args.cluster, out=outs)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            solver.solve_dynamics(batch, cases, n_iter=10, cluster_size=args.cluster, out=outs)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert np.array_equal(outs["status"], status), "e2e and resident paths disagree"
+        e2e = dict(value=units * world * args.steps / float(te.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
+                   d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * float(te.item()) / args.steps)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, used, done, dt = cpu_oracle_rate(designs[:4], cs, min_seconds=8.0)
+        cpu = dict(value=rate, unit=UNIT, cores=int(used), kind="port",
+                   sample="%d RAO solves of the same workload (%.1f s, OpenMP over cases, C oracle pinned to the reference)" % (done, dt))
+
+    if rank == 0:
+        cfg.update(l2="flushed between timed steps (256 MiB write)", cluster_size=args.cluster or "auto",
+                   units_per_step=units * world, mean_passes=mean_passes, wall_s_timed_region=t_wall,
+                   collective=("all_gather_into_tensor of Xi (%d B per rank) per step" % (Xi.numel() * 16)) if world > 1 else "none")
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                    data="synthetic", config=cfg, clocks=clocks, e2e=e2e, gpu_launches=int(launches),
+                    roofline=roofline, roofline_fp64=roofline_fp64, cpu_baseline=cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -136,6 +136,14 @@ const char *raftk_last_error(void);
 /* Number of CUDA kernel launches issued by this library since load (bench.py "gpu_launches"). */
 long long raftk_launch_count(void);
 
+/* Per-kernel device timing for the roofline report.  When enabled, every *_dev / *_host call
+ * brackets each kernel it launches with CUDA events on the launching stream.
+ * raftk_profile_read synchronises those events and returns, for the LAST call, the summed device
+ * milliseconds of ms[0] = depth-table kernel, ms[1] = excitation kernel, ms[2] = drag-linearise +
+ * impedance-solve kernel, and launches[0..2] = how many launches each sum covers. */
+void raftk_profile_enable(int on);
+int raftk_profile_read(double ms[3], int launches[3]);
+
 /* Bytes of device workspace the *_dev entry points need for (designs, n_cases). */
 size_t raftk_workspace_bytes(const raftk_designs *d, int32_t n_cases);
 

@@ -28,6 +28,7 @@
 #include <mutex>
 #include <algorithm>
 #include <type_traits>
+#include <vector>
 
 #include "../../include/raftk.h"
 
@@ -49,6 +50,51 @@ static int set_err(int code, const char *fmt, const char *a = "", const char *b 
         cudaError_t _e = (expr);                                                                \
         if (_e != cudaSuccess) return set_err(RAFTK_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
+
+// ---- optional per-kernel event timing (roofline report) ----------------------------------------------
+struct ProfRec { cudaEvent_t a, b; int kind; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+
+static void prof_begin_call()
+{
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+}
+struct ProfScope {
+    cudaStream_t st; int idx = -1;
+    ProfScope(cudaStream_t s, int kind) : st(s)
+    {
+        if (!g_prof_on) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        ProfRec r; r.kind = kind;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, st);
+        g_prof.push_back(r); idx = (int)g_prof.size() - 1;
+    }
+    ~ProfScope()
+    {
+        if (idx < 0) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        cudaEventRecord(g_prof[idx].b, st);
+    }
+};
+extern "C" void raftk_profile_enable(int on) { g_prof_on = on != 0; }
+extern "C" int raftk_profile_read(double ms[3], int launches[3])
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int t = 0; t < 3; t++) { ms[t] = 0.0; launches[t] = 0; }
+    for (auto &r : g_prof) {
+        if (cudaEventSynchronize(r.b) != cudaSuccess) return RAFTK_ECUDA;
+        float f = 0.f;
+        if (cudaEventElapsedTime(&f, r.a, r.b) != cudaSuccess) return RAFTK_ECUDA;
+        ms[r.kind] += f; launches[r.kind]++;
+    }
+    return RAFTK_OK;
+}
 
 extern "C" int raftk_version(void) { return RAFTK_VERSION; }
 extern "C" const char *raftk_last_error(void) { return g_err; }
@@ -912,6 +958,7 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
     int rc = validate(d, c);
     if (rc) return rc;
     const int nD = d->n_designs, nC = c->n_cases, nw = d->nw;
+    if (do_excitation) prof_begin_call();
     DesignsDev D = to_dev(d, d->max_nodes, d->max_members);
     CasesDev C = to_dev(c);
     const size_t one = chunk_bytes(1, nC, d->max_nodes, nw);
@@ -946,14 +993,20 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
 
         if (do_excitation) {
             dim3 g0((nw + 127) / 128, nDc, 1);
-            k_depth_table<<<g0, 128, 0, st>>>(D, W);
+            {
+                ProfScope ps(st, 0);
+                k_depth_table<<<g0, 128, 0, st>>>(D, W);
+            }
             g_launches++;
             ExcOut EO;
             EO.F_iner = reinterpret_cast<double2 *>(out->F_iner);
             EO.F_BEM = reinterpret_cast<double2 *>(out->F_BEM);
             EO.zeta = out->zeta;
             dim3 g1((nw + 127) / 128, nC, nDc);
-            k_excitation<<<g1, 128, 0, st>>>(D, C, W, EO);
+            {
+                ProfScope ps(st, 1);
+                k_excitation<<<g1, 128, 0, st>>>(D, C, W, EO);
+            }
             g_launches++;
         }
         if (mode != 2) {
@@ -975,7 +1028,10 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = pl.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, k_drag_solve, D, C, W, P));
+            {
+                ProfScope ps(st, 2);
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, k_drag_solve, D, C, W, P));
+            }
             g_launches++;
         }
         CUDA_TRY(cudaGetLastError());

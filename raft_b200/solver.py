@@ -295,3 +295,15 @@ def launch_count():
 
 def fp64_peak_gflops(iters=20000):
     return float(lib.raftk_fp64_peak_gflops(int(iters)))
+
+
+def profile_enable(on=True):
+    lib.raftk_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """-> (ms[3], launches[3]) device time of the depth-table, excitation and drag-solve kernels of the last call."""
+    ms = (C.c_double * 3)()
+    n = (C.c_int * 3)()
+    check(lib.raftk_profile_read(ms, n))
+    return list(ms), list(n)
