@@ -69,45 +69,75 @@ def build_workload(args, rank, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML (nvidia_ml_py) in a thread at
+    ~2 ms period -- nvidia-smi -lms is too slow to start for millisecond-scale regions; falls back to one
+    nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
-
-    def start(self):
+        self.idx, self.sm, self.reasons, self.max_mhz, self.run, self.th, self.ok = gpu_index, [], set(), None, False, None, False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            uuid = None
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
             except Exception:
                 pass
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(max(mx)) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+            self.h = None
+            if uuid:
+                for cand in ("GPU-" + uuid, uuid):
+                    try:
+                        self.h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _loop(self):
+        nv = self.nv
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for nm, _, bit in names:
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self.run = True
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+
+    def stop(self):
+        if self.ok:
+            self.run = False
+            self.th.join(timeout=1.0)
+            return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.max_mhz,
+                        reasons=sorted(self.reasons), samples=len(self.sm), source="nvml")
+        try:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            o = subprocess.check_output(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"], text=True)
+            f = [x.strip() for x in o.strip().split(",")]
+            rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]) if v.lower().startswith("active")]
+            return dict(sm_mhz=float(f[0]), sm_max_mhz=float(f[1]), reasons=rs, samples=1, source="nvidia-smi (after the region)")
+        except Exception:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["clock query unavailable"], samples=0)
 
 
 def algorithmic_bytes_per_solve(Ns, Nm, nC, nw, bem=False):
@@ -167,7 +197,7 @@ def run_reference(args, rank, world):
     line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                 data="synthetic", config=cfg, impl="reference",
-                cpu_baseline=dict(value=val, unit=UNIT, cores=int(used), kind="port", sample=sample),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=int(min(used, len(cs["Hs"]))), kind="port", sample=sample),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
@@ -322,7 +352,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, used, done, dt = cpu_oracle_rate(designs[:4], cs, min_seconds=8.0)
-        cpu = dict(value=rate, unit=UNIT, cores=int(used), kind="port",
+        cpu = dict(value=rate, unit=UNIT, cores=int(min(used, len(cs["Hs"]))), kind="port",
                    sample="%d RAO solves of the same workload (%.1f s, OpenMP over cases, C oracle pinned to the reference)" % (done, dt))
 
     if rank == 0:

@@ -223,6 +223,9 @@ def system_solve(Z, F):
     return (F[:, :, 0] if squeeze else F), info
 
 
+_PINNED = []
+
+
 def pinned_empty(shape, dtype):
     """NumPy array backed by page-locked host memory (cudaHostAlloc) for the e2e path."""
     dtype = np.dtype(dtype)
@@ -232,7 +235,7 @@ def pinned_empty(shape, dtype):
         raise MemoryError("cudaHostAlloc failed")
     buf = (C.c_char * max(n, 1)).from_address(p)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    arr._raftk_pinned = (buf, p)    # keep alive; freed at process exit
+    _PINNED.append((buf, p))        # keep alive; page-locked blocks live until process exit
     return arr
 
 
