@@ -185,12 +185,13 @@ def run_reference(args, rank, world):
     nw = ods[0].nw
     units = len(designs) * len(cs["Hs"]) * nw
     used = 1
+    nthreads = os.cpu_count() or 1          # torchrun exports OMP_NUM_THREADS=1; the baseline may use every host core
     for _ in range(args.warmup):
-        orc.solve_cases(ods[0], cs, nIter=10)
+        orc.solve_cases(ods[0], cs, nIter=10, nthreads=nthreads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for od in ods:
-            _, _, used = orc.solve_cases(od, cs, nIter=10)
+            _, _, used = orc.solve_cases(od, cs, nIter=10, nthreads=nthreads)
     dt = time.perf_counter() - t0
     val = units * args.steps / dt
     sample = "%d design(s) x %d sea states x %d bins per step, %d steps" % (len(designs), len(cs["Hs"]), nw, args.steps)
@@ -351,7 +352,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, used, done, dt = cpu_oracle_rate(designs[:4], cs, min_seconds=8.0)
+        rate, used, done, dt = cpu_oracle_rate(designs[:4], cs, min_seconds=8.0, nthreads=os.cpu_count() or 1)
         cpu = dict(value=rate, unit=UNIT, cores=int(min(used, len(cs["Hs"]))), kind="port",
                    sample="%d RAO solves of the same workload (%.1f s, OpenMP over cases, C oracle pinned to the reference)" % (done, dt))
 
