@@ -45,7 +45,7 @@ enum {
 enum { RAFTK_SPEC_JONSWAP = 0, RAFTK_SPEC_UNIT = 1, RAFTK_SPEC_CONSTANT = 2, RAFTK_SPEC_NONE = 3 };
 
 /* status word per (design, case): int32[4] = {passes, converged, flags, reserved} */
-enum { RAFTK_FLAG_NAN = 1, RAFTK_FLAG_SINGULAR = 2 };
+enum { RAFTK_FLAG_NAN = 1, RAFTK_FLAG_SINGULAR = 2, RAFTK_FLAG_PLAN = 4 /* step-class tables overflowed the hint */ };
 
 /*
  * A batch of nD FOWT designs that share one frequency grid (w, k), water depth and density.
@@ -61,6 +61,10 @@ typedef struct raftk_designs {
     int32_t n_nodes_total;      /* sum of submerged strip nodes (NsTot)                        */
     int32_t max_nodes;          /* max submerged nodes of any one design (table stride)        */
     int32_t max_members;        /* max members of any one design                               */
+    int32_t max_w_classes;      /* hints for the fused solver's on-chip tables: max number of distinct     */
+    int32_t max_h_classes;      /* (q_x,q_y)*step resp. q_z*step node spacings of any design; 0 = worst case */
+    int32_t max_z_classes;      /* max distinct first-node depths z0 of any design's members; 0 = worst case   */
+    int32_t _pad1;
     double depth, rho, g, dw;   /* site (raft_fowt.py:167-173); dw = w[1]-w[0]                  */
     const double *w;            /* [nw] rad/s           raft_model.py:57                       */
     const double *k;            /* [nw] wave numbers    raft_fowt.py:170 (helpers.py:377)      */

@@ -13,7 +13,7 @@ c_int32_p = C.POINTER(C.c_int32)
 class RaftkDesigns(C.Structure):
     _fields_ = [
         ("n_designs", C.c_int32), ("nw", C.c_int32), ("n_members_total", C.c_int32), ("n_nodes_total", C.c_int32),
-        ("max_nodes", C.c_int32), ("max_members", C.c_int32),
+        ("max_nodes", C.c_int32), ("max_members", C.c_int32), ("max_w_classes", C.c_int32), ("max_h_classes", C.c_int32), ("max_z_classes", C.c_int32), ("_pad1", C.c_int32),
         ("depth", C.c_double), ("rho", C.c_double), ("g", C.c_double), ("dw", C.c_double),
         ("w", C.c_void_p), ("k", C.c_void_p), ("member_offset", C.c_void_p),
         ("mem_frame", C.c_void_p), ("mem_rA", C.c_void_p), ("mem_arm", C.c_void_p),

@@ -99,6 +99,34 @@ class DesignBatch:
         self.n_nodes_total = int(mem_node_start[-1])
         self.max_nodes = max(1, max_nodes)
         self.max_members = max(1, max_members)
+        self.max_w_classes, self.max_h_classes, self.max_z_classes = self._step_classes(packed)
+
+    @staticmethod
+    def _step_classes(packed):
+        """Upper bounds on the number of distinct node spacings per design, as the fused kernel
+        deduplicates them (phase classes keyed by (q_x,q_y)*step, depth classes by q_z*step), + slack."""
+        mw = mh = mz = 0
+        for P in packed:
+            wk, hk, zk = [], [], []
+            ms = np.asarray(P["mem_start"], dtype=np.int64)
+            for m in range(len(ms) - 1):
+                q = np.asarray(P["mem_q"][m], dtype=float)
+                ls = np.asarray(P["node_ls"][ms[m]:ms[m + 1]], dtype=float)
+                if len(ls):
+                    z0 = float(P["mem_rA"][m][2]) + ls[0] * q[2]
+                    if not any(abs(a - z0) <= 1e-12 * max(1.0, abs(z0)) for a in zk):
+                        zk.append(z0)
+                for step in np.diff(ls):
+                    kx, ky, kz = q[0] * step, q[1] * step, q[2] * step
+                    if abs(kx) > 1e-14 or abs(ky) > 1e-14:
+                        tol = 1e-11 * (abs(kx) + abs(ky))
+                        if not any(abs(a - kx) <= tol and abs(b - ky) <= tol for a, b in wk):
+                            wk.append((kx, ky))
+                    if abs(kz) > 1e-14:
+                        if not any(abs(a - kz) <= 1e-11 * abs(kz) for a in hk):
+                            hk.append(kz)
+            mw, mh, mz = max(mw, len(wk)), max(mh, len(hk)), max(mz, len(zk))
+        return max(1, mw), max(1, mh), max(1, mz)
 
     def input_bytes(self):
         return int(sum(v.nbytes for v in self.arrays.values()))
@@ -109,6 +137,7 @@ class DesignBatch:
         s.n_designs, s.nw = self.n_designs, self.nw
         s.n_members_total, s.n_nodes_total = self.n_members_total, self.n_nodes_total
         s.max_nodes, s.max_members = self.max_nodes, self.max_members
+        s.max_w_classes, s.max_h_classes, s.max_z_classes = self.max_w_classes, self.max_h_classes, self.max_z_classes
         s.depth, s.rho, s.g, s.dw = self.depth, self.rho, self.g, self.dw
         for name in ("w", "k", "member_offset", "mem_frame", "mem_rA", "mem_arm", "mem_node_start", "mem_circ",
                      "node_ls", "node_cd_q", "node_cd_p1", "node_cd_p2", "node_in_q", "node_in_p1", "node_in_p2",
