@@ -796,6 +796,7 @@ struct FusedParams {
     double2 *Xi_out, *Fdrag_out, *Finer_out, *Fbem_out;
     double *Bdrag_out, *zeta_out;
     int *status;
+    double2 *F0g;            // [units][6][nw] linear excitation kept in global memory (frees 96 B/bin of smem), or NULL
 };
 
 #define IMEM_STRIDE 6      // ints per member: node start, node end, circular, direction kinds, z-class, spare
@@ -807,11 +808,11 @@ struct FSmem {
     int *imem, *node_w, *node_h, *iscr, *cnt;
 };
 
-__host__ __device__ inline size_t fused_smem_bytes(int Nm, int NsP, int nchunk, int nwarps, int nwl, int maxW, int maxH, int maxZ)
+__host__ __device__ inline size_t fused_smem_bytes(int Nm, int NsP, int nchunk, int nwarps, int nwl, int maxW, int maxH, int maxZ, bool f0_smem)
 {
     size_t dbl = (size_t)Nm * MEM_STRIDE + 4 * (size_t)NsP + NCOEF * (size_t)NsP + (size_t)Nm * 8 + 108
                  + (size_t)nchunk * nwarps * 32 + 2 * ((size_t)nchunk * 32 + 2) + (size_t)nchunk * 32
-                 + (12 + 12 + 4) * (size_t)nwl + 2 * (size_t)maxW + (size_t)maxH + (size_t)maxZ + 3 * (size_t)NsP
+                 + (12 + (f0_smem ? 12 : 0) + 4) * (size_t)nwl + 2 * (size_t)maxW + (size_t)maxH + (size_t)maxZ + 3 * (size_t)NsP
                  + 2 * ((size_t)Nm + maxZ + maxW + maxH) * nwl;
     size_t ints = (size_t)Nm * IMEM_STRIDE + 4 * (size_t)NsP + 8;
     return dbl * sizeof(double) + ints * sizeof(int) + 32;
@@ -872,7 +873,7 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         S.sums = p; p += 2 * ((size_t)nchunk * 32 + 2);
         S.tot = p; p += (size_t)nchunk * 32;
         S.xi = p; p += 12 * (size_t)nwl;
-        S.f0 = p; p += 12 * (size_t)nwl;
+        S.f0 = p; p += P.F0g ? 0 : 12 * (size_t)nwl;
         S.ckpt = p; p += 4 * (size_t)nwl;
         S.wkey = p; p += 2 * (size_t)P.maxW;
         S.hkey = p; p += (size_t)P.maxH;
@@ -1122,7 +1123,8 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         }
 #pragma unroll
         for (int a = 0; a < 6; a++) {
-            S.f0[(2 * a) * nwl + t] = Fr[a]; S.f0[(2 * a + 1) * nwl + t] = Fi[a];
+            if (P.F0g) P.F0g[ogl + (size_t)a * nw + i] = make_double2(Fr[a], Fi[a]);
+            else { S.f0[(2 * a) * nwl + t] = Fr[a]; S.f0[(2 * a + 1) * nwl + t] = Fi[a]; }
             S.xi[(2 * a) * nwl + t] = P.xi_start; S.xi[(2 * a + 1) * nwl + t] = 0.0;
         }
     }
@@ -1328,8 +1330,13 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
                 for (int a = 0; a < 6; a++) P.Fdrag_out[ogl + (size_t)a * nw + i] = make_double2(br[a], bi[a]);
             }
             double ar[6][6], ai[6][6];
+            if (P.F0g) {
 #pragma unroll
-            for (int a = 0; a < 6; a++) { br[a] += S.f0[(2 * a) * nwl + t]; bi[a] += S.f0[(2 * a + 1) * nwl + t]; }
+                for (int a = 0; a < 6; a++) { const double2 f = P.F0g[ogl + (size_t)a * nw + i]; br[a] += f.x; bi[a] += f.y; }
+            } else {
+#pragma unroll
+                for (int a = 0; a < 6; a++) { br[a] += S.f0[(2 * a) * nwl + t]; bi[a] += S.f0[(2 * a + 1) * nwl + t]; }
+            }
             const double w2 = w * w;
             if (Aw) {                      // frequency-dependent added mass / damping tables (BEM, aero)
 #pragma unroll
@@ -1568,9 +1575,9 @@ static int make_plan(const raftk_designs *d, int units_hint, int requested_cs, P
 }
 
 // ---- fused (v2) planner / launcher -----------------------------------------------------------------
-struct FPlan { int CS, nwl, T, nchunk, maxW, maxH, maxZ; size_t smem; };
+struct FPlan { int CS, nwl, T, nchunk, maxW, maxH, maxZ; size_t smem; bool f0_global; };
 
-static bool fused_try(const raftk_designs *d, int cs, FPlan &pl)
+static bool fused_try(const raftk_designs *d, int cs, bool have_ws, FPlan &pl)
 {
     pl.CS = cs;
     pl.nwl = (d->nw + cs - 1) / cs;
@@ -1579,30 +1586,38 @@ static bool fused_try(const raftk_designs *d, int cs, FPlan &pl)
     pl.maxW = d->max_w_classes > 0 ? d->max_w_classes : d->max_nodes;
     pl.maxH = d->max_h_classes > 0 ? d->max_h_classes : d->max_nodes;
     pl.maxZ = d->max_z_classes > 0 ? std::min(d->max_z_classes, d->max_members) : d->max_members;
-    pl.smem = fused_smem_bytes(d->max_members, d->max_nodes, pl.nchunk, pl.T / 32, pl.nwl, pl.maxW, pl.maxH, pl.maxZ);
-    const size_t limit = (pl.T == 128) ? (size_t)112 * 1024 : (size_t)226 * 1024;   // 2 resp. 1 CTA per SM
+    // 255 registers cap residency at 256 threads per SM (measured: 168 registers / 3 CTAs is slower, the LU
+    // spills); shared memory must allow 2 CTAs of 128 threads or 1 of 256.  The linear excitation F0 lives in
+    // shared memory when it fits, else in the caller's workspace.
+    const size_t limit = (pl.T == 128) ? (size_t)112 * 1024 : (size_t)226 * 1024;
+    pl.f0_global = false;
+    pl.smem = fused_smem_bytes(d->max_members, d->max_nodes, pl.nchunk, pl.T / 32, pl.nwl, pl.maxW, pl.maxH, pl.maxZ, true);
+    if (pl.smem > limit && have_ws) {
+        pl.f0_global = true;
+        pl.smem = fused_smem_bytes(d->max_members, d->max_nodes, pl.nchunk, pl.T / 32, pl.nwl, pl.maxW, pl.maxH, pl.maxZ, false);
+    }
     return pl.smem <= limit && pl.nwl <= 2 * pl.T;
 }
 
-static bool fused_plan(const raftk_designs *d, int units, int requested_cs, FPlan &pl)
+static bool fused_plan(const raftk_designs *d, int units, int requested_cs, bool have_ws, FPlan &pl)
 {
     if (getenv("RAFTK_FORCE_V1")) return false;
     if (requested_cs == 1 || requested_cs == 2 || requested_cs == 4 || requested_cs == 8) {
         int cs = requested_cs;
         while (cs > 1 && d->nw / cs < 32) cs >>= 1;
-        return fused_try(d, cs, pl);
+        return fused_try(d, cs, have_ws, pl);
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     FPlan best; bool have = false;
     if (units >= 4 * sms) {                       // plenty of units: smallest cluster whose slice fits on chip
-        for (int cs = 1; cs <= 8 && !have; cs <<= 1) { FPlan t; if (fused_try(d, cs, t) && t.nwl <= t.T) { best = t; have = true; } }
-        for (int cs = 1; cs <= 8 && !have; cs <<= 1) { FPlan t; if (fused_try(d, cs, t)) { best = t; have = true; } }
+        for (int cs = 1; cs <= 8 && !have; cs <<= 1) { FPlan t; if (fused_try(d, cs, have_ws, t) && t.nwl <= t.T) { best = t; have = true; } }
+        for (int cs = 1; cs <= 8 && !have; cs <<= 1) { FPlan t; if (fused_try(d, cs, have_ws, t)) { best = t; have = true; } }
     } else {                                      // few units: largest cluster that keeps >= 128 bins per CTA
         for (int cs = 8; cs >= 1 && !have; cs >>= 1) {
             if (cs > 1 && d->nw / cs < 128) continue;
-            FPlan t; if (fused_try(d, cs, t)) { best = t; have = true; }
+            FPlan t; if (fused_try(d, cs, have_ws, t)) { best = t; have = true; }
         }
     }
     if (have) pl = best;
@@ -1641,7 +1656,7 @@ static int fused_launch(const DesignsDev &D, const CasesDev &C, const FusedParam
 }
 
 static int run_fused(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o, const raftk_outputs *out,
-                     const FPlan &pl, cudaStream_t st)
+                     const FPlan &pl, void *workspace, cudaStream_t st)
 {
     prof_begin_call();
     DesignsDev D = to_dev(d, d->max_nodes, d->max_members);
@@ -1654,6 +1669,7 @@ static int run_fused(const raftk_designs *d, const raftk_cases *c, const raftk_s
     P.Finer_out = reinterpret_cast<double2 *>(out->F_iner);
     P.Fbem_out = reinterpret_cast<double2 *>(out->F_BEM);
     P.Bdrag_out = out->B_drag; P.zeta_out = out->zeta; P.status = out->status;
+    P.F0g = pl.f0_global ? reinterpret_cast<double2 *>(workspace) : nullptr;
     const int units = d->n_designs * c->n_cases;
     if (pl.T == 128) return fused_launch<128>(D, C, P, pl, units, st);
     return fused_launch<256>(D, C, P, pl, units, st);
@@ -1668,7 +1684,8 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
     const int nD = d->n_designs, nC = c->n_cases, nw = d->nw;
     if (mode == 0) {                                   // fused on-chip solver when the slice fits in shared memory
         FPlan fp;
-        if (fused_plan(d, nD * nC, o ? o->cluster_size : 0, fp)) return run_fused(d, c, o, out, fp, st);
+        const bool have_ws = workspace && wbytes >= (size_t)nD * nC * 6 * nw * sizeof(double2);
+        if (fused_plan(d, nD * nC, o ? o->cluster_size : 0, have_ws, fp)) return run_fused(d, c, o, out, fp, workspace, st);
     }
     if (do_excitation) prof_begin_call();
     DesignsDev D = to_dev(d, d->max_nodes, d->max_members);
@@ -1856,7 +1873,7 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     if (Xi_in) obytes += align_up(resp, 256);
     size_t wb = raftk_workspace_bytes(d, (int32_t)nC);
     if (mode != 0) wb = chunk_bytes((int)nD, (int)nC, d->max_nodes, (int)nw);   // single chunk required
-    else { FPlan fp; if (fused_plan(d, (int)(nD * nC), o ? o->cluster_size : 0, fp)) wb = 256; }
+    else { FPlan fp; if (fused_plan(d, (int)(nD * nC), o ? o->cluster_size : 0, true, fp)) wb = resp; }
     const size_t total = in_bytes(d, c) + obytes + align_up(wb, 256) + 4096;
     if (g_arena.reserve(total)) return set_err(RAFTK_ENOMEM, "device arena allocation failed");
     Arena &A = g_arena;
