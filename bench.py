@@ -61,7 +61,11 @@ def build_workload(args, rank, world):
         from raft_b200 import sweep
         nD = args.designs or 1250
         nC = args.cases or 16
-        designs = sweep.volturnus_variants(nD * world, seed=40, nw=args.nw or 512, max_freq=0.40)[rank * nD:(rank + 1) * nD]
+        base = json.load(open(os.path.join(ROOT, "tests", "golden", "designs.json")))["cfg2_VolturnUS-S_nw64"]
+        z = np.load(os.path.join(ROOT, "tests", "golden", "cfg2_VolturnUS-S_nw64.npz"))
+        mats = dict(M_struc=z["P_M0"] - z["A_hydro_morison"], C_struc=z["P_C0"] - z["C_moor"], C_moor=z["C_moor"])
+        fac = sweep.sample_factors(nD * world, seed=40)[rank * nD:(rank + 1) * nD]
+        designs = sweep.build_variants(base, mats, fac, nw=args.nw or 512, max_freq=0.40, depth=float(z["P_depth"]))
         cs = sea_states(4, nC)
         cfg = dict(workload="sweep: %d synthetic VolturnUS-S geometry variants x %d sea states x %d bins per GPU, fp64" % (nD, nC, len(designs[0]["w"])),
                    designs_per_gpu=nD, cases_per_gpu=nC, nw=len(designs[0]["w"]))

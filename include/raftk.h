@@ -148,8 +148,14 @@ long long raftk_launch_count(void);
 void raftk_profile_enable(int on);
 int raftk_profile_read(double ms[3], int launches[3]);
 
-/* Bytes of device workspace the *_dev entry points need for (designs, n_cases). */
+/* Bytes of device workspace the *_dev entry points need for (designs, n_cases): the wave-kinematics
+ * tables of raftk_hydro_excitation_dev / raftk_hydro_linearization_dev (capped at 8 GiB; solves chunk). */
 size_t raftk_workspace_bytes(const raftk_designs *d, int32_t n_cases);
+
+/* Bytes raftk_solve_dynamics_dev alone needs: the fused solver keeps its tables in shared memory and only
+ * parks the linear excitation in the workspace (16*6*nw bytes per unit); falls back to the value above when
+ * a design's frequency slice does not fit on chip. */
+size_t raftk_solve_workspace_bytes(const raftk_designs *d, int32_t n_cases);
 
 /*
  * FOWT.calcHydroExcitation (raft_fowt.py:1732-1888) + Member.computeWaveKinematics /

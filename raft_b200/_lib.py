@@ -47,7 +47,7 @@ class RaftkOutputs(C.Structure):
 # every symbol include/raftk.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "raftk_version", "raftk_last_error", "raftk_launch_count", "raftk_profile_enable", "raftk_profile_read",
-    "raftk_workspace_bytes",
+    "raftk_workspace_bytes", "raftk_solve_workspace_bytes",
     "raftk_hydro_excitation_dev", "raftk_hydro_linearization_dev", "raftk_solve_dynamics_dev",
     "raftk_hydro_excitation_host", "raftk_hydro_linearization_host", "raftk_solve_dynamics_host",
     "raftk_system_solve_dev", "raftk_system_solve_host", "raftk_host_alloc", "raftk_host_free",
@@ -74,6 +74,8 @@ def _load():
     lib.raftk_profile_read.restype = C.c_int
     lib.raftk_workspace_bytes.restype = C.c_size_t
     lib.raftk_workspace_bytes.argtypes = [P(RaftkDesigns), C.c_int32]
+    lib.raftk_solve_workspace_bytes.restype = C.c_size_t
+    lib.raftk_solve_workspace_bytes.argtypes = [P(RaftkDesigns), C.c_int32]
     lib.raftk_hydro_excitation_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.raftk_hydro_linearization_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), C.c_void_p, P(RaftkOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.raftk_solve_dynamics_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkSolveOpts), P(RaftkOutputs), C.c_void_p, C.c_size_t, C.c_void_p]

@@ -1535,6 +1535,9 @@ extern "C" size_t raftk_workspace_bytes(const raftk_designs *d, int32_t n_cases)
     return full <= cap ? full : std::max(cap, one);
 }
 
+struct FPlan { int CS, nwl, T, nchunk, maxW, maxH, maxZ; size_t smem; bool f0_global; };
+static bool fused_plan(const raftk_designs *d, int units, int requested_cs, bool have_ws, FPlan &pl);
+
 static int validate(const raftk_designs *d, const raftk_cases *c)
 {
     if (!d || !c) return set_err(RAFTK_EINVAL, "null designs/cases");
@@ -1575,7 +1578,6 @@ static int make_plan(const raftk_designs *d, int units_hint, int requested_cs, P
 }
 
 // ---- fused (v2) planner / launcher -----------------------------------------------------------------
-struct FPlan { int CS, nwl, T, nchunk, maxW, maxH, maxZ; size_t smem; bool f0_global; };
 
 static bool fused_try(const raftk_designs *d, int cs, bool have_ws, FPlan &pl)
 {
@@ -1766,6 +1768,15 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
         CUDA_TRY(cudaGetLastError());
     }
     return RAFTK_OK;
+}
+
+extern "C" size_t raftk_solve_workspace_bytes(const raftk_designs *d, int32_t n_cases)
+{
+    if (!d || d->n_designs <= 0 || n_cases <= 0) return 0;
+    FPlan fp;
+    if (d->max_nodes > 0 && d->max_members > 0 && fused_plan(d, d->n_designs * n_cases, 0, true, fp))
+        return align_up((size_t)d->n_designs * n_cases * 6 * d->nw * sizeof(double2), 256);
+    return raftk_workspace_bytes(d, n_cases);
 }
 
 extern "C" int raftk_hydro_excitation_dev(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out,

@@ -14,16 +14,17 @@ def make_w(min_freq, max_freq):
 
 
 def wave_number(w, depth, e=0.001, g=9.81):
-    """k(w) by the reference's fixed-point iteration k <- w^2 / (g tanh(k h))  (helpers.py:377-392)."""
+    """k(w) by the reference's fixed-point iteration k <- w^2 / (g tanh(k h))  (helpers.py:377-392).
+
+    Long waves (k h << 1) need tens of thousands of iterations; only the still-active bins are iterated."""
     w = np.atleast_1d(np.asarray(w, dtype=float))
     k1 = w * w / g
     k2 = w * w / (np.tanh(k1 * depth) * g)
-    active = np.abs(k2 - k1) / k1 > e
-    while np.any(active):
-        k1 = np.where(active, k2, k1)
-        k2n = w * w / (np.tanh(k1 * depth) * g)
-        k2 = np.where(active, k2n, k2)
-        active = active & (np.abs(k2 - k1) / k1 > e)
+    idx = np.nonzero(np.abs(k2 - k1) / k1 > e)[0]
+    while idx.size:
+        k1[idx] = k2[idx]
+        k2[idx] = w[idx] * w[idx] / (np.tanh(k1[idx] * depth) * g)
+        idx = idx[np.abs(k2[idx] - k1[idx]) / k1[idx] > e]
     return k2
 
 

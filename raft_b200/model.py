@@ -1,0 +1,113 @@
+"""Model: host-side mirror of the reference's ``raft.Model`` for ``solveDynamics`` / ``analyzeCases``.
+
+Reference: raft_model.py:30-176 (construction), :264-433 (analyzeCases), :966-1302 (solveDynamics).
+The per-frequency work runs on the GPU through the C ABI; statics / mooring / aero are out of scope and are
+injected per FOWT (see ``raft_b200.fowt``).  Farms: every FOWT is linearised independently on the GPU, then the
+coupled 6N system (block-diagonal impedances + an injected array-mooring stiffness) is solved per frequency by
+``raftk_system_solve`` (raft_model.py:1164-1216).
+"""
+import numpy as np
+
+from . import grid, packer, solver
+from .fowt import FOWT
+
+
+class Model:
+    def __init__(self, design, matrices=None, array_stiffness=None):
+        s = design.setdefault("settings", {})
+        min_freq, max_freq = float(s.get("min_freq", 0.01)), float(s.get("max_freq", 1.00))
+        self.XiStart = float(s.get("XiStart", 0.1))
+        self.nIter = int(s.get("nIter", 15))
+        self.w = grid.make_w(min_freq, max_freq)
+        self.nw = len(self.w)
+        self.depth = float(design["site"]["water_depth"])
+        self.k = grid.wave_number(self.w, self.depth)
+        self.design = design
+        self.fowtList, self.coords = [], []
+        if "array" in design:
+            keys, rows = design["array"]["keys"], design["array"]["data"]
+            mats = matrices if isinstance(matrices, (list, tuple)) else [matrices] * len(rows)
+            for i, row in enumerate(rows):
+                info = dict(zip(keys, row))
+                d_i = dict(site=design["site"], platform=design["platforms"][int(info["platformID"]) - 1])
+                self.fowtList.append(FOWT(d_i, self.w, depth=self.depth, x_ref=info["x_location"], y_ref=info["y_location"],
+                                          heading_adjust=info.get("heading_adjust", 0), matrices=mats[i], k=self.k))
+                self.coords.append([info["x_location"], info["y_location"]])
+        else:
+            self.fowtList.append(FOWT(design, self.w, depth=self.depth, matrices=matrices, k=self.k))
+            self.coords.append([0.0, 0.0])
+        self.nFOWT = len(self.fowtList)
+        self.nDOF = 6 * self.nFOWT
+        self.C_array = None if array_stiffness is None else np.array(array_stiffness, dtype=float)   # stands in for ms.getCoupledStiffnessA
+        self.results = {}
+        for f in self.fowtList:
+            f.calcHydroConstants()
+
+    # raft_model.py:966-1302 -------------------------------------------------------------------------------
+    def solveDynamics(self, case, tol=0.01, conv_plot=0, RAO_plot=0, display=0):
+        """Response amplitudes for one load case -> self.Xi [nWaves+1, nDOF, nw] (last row zero, as :1195)."""
+        out = self._solve_batch([case], tol)
+        Xi = np.zeros([2, self.nDOF, self.nw], dtype=complex)
+        Xi[0] = out["Xi"][0]
+        self.Xi = Xi
+        for i, f in enumerate(self.fowtList):
+            f.Xi = Xi[:, 6 * i:6 * i + 6, :]
+            f.Xi_fullDOF = f.Xi
+        self.results["response"] = {}
+        return self.Xi
+
+    # raft_model.py:264-433 (dynamics part) ---------------------------------------------------------------------
+    def analyzeCases(self, cases=None, tol=0.01, display=0):
+        """All load cases in ONE batched GPU call.  ``cases``: list of case dicts (default: the design's table).
+        Fills results['freq_rad'], results['Xi'] [nCases, nDOF, nw], results['status'] [nCases, nFOWT, 4]."""
+        if cases is None:
+            keys = self.design["cases"]["keys"]
+            cases = [dict(zip(keys, row)) for row in self.design["cases"]["data"]]
+        out = self._solve_batch(cases, tol)
+        self.results["freq_rad"] = self.w
+        self.results["Xi"] = out["Xi"]
+        self.results["status"] = out["status"]
+        return self.results
+
+    def _solve_batch(self, cases, tol):
+        ct = solver.CaseTable(packer.pack_cases(cases))
+        nC = ct.n_cases
+        batch = solver.DesignBatch([f.pack() for f in self.fowtList])
+        want = ("Xi", "status", "B_drag", "F_drag", "F_iner", "F_BEM", "zeta")
+        o = solver.solve_dynamics(batch, ct, n_iter=self.nIter, tol=tol, xi_start=self.XiStart, want=want)
+        st = o["status"]                                                   # [nFOWT, nC, 4]
+        if np.any(st[..., 2] & 1):
+            raise Exception("Nan detected in response vector Xi.")          # raft_model.py:1098-1099
+        w = self.w
+        for i, f in enumerate(self.fowtList):
+            P = f.pack()
+            f.B_hydro_drag, f.F_hydro_drag = o["B_drag"][i, -1], o["F_drag"][i, -1]
+            f.zeta, f.F_BEM, f.F_hydro_iner = o["zeta"][-1:], o["F_BEM"][i, -1:], o["F_iner"][i, -1:]
+            M = P["M0"][:, :, None] + (P["A_w"] if "A_w" in P else 0.0)
+            B = (P["B0"] + f.B_hydro_drag)[:, :, None] + (P["B_w"] if "B_w" in P else 0.0)
+            f.Z = -w ** 2 * M + 1j * w * B + P["C0"][:, :, None]             # raft_model.py:1086, 1155 (last case)
+        Xi = np.moveaxis(o["Xi"], 0, 1).reshape(nC, self.nDOF, self.nw)     # [nC, 6N, nw]
+        if self.nFOWT > 1 and self.C_array is not None:
+            # coupled system: Z_sys = blockdiag(Z_i) + C_array; F = Z_i Xi_i  (raft_model.py:1164-1216)
+            Xi = self._couple(o, cases)
+        return dict(Xi=Xi, status=np.moveaxis(st, 0, 1))
+
+    def _couple(self, o, cases):
+        nC, n, nw, w = len(cases), self.nDOF, self.nw, self.w
+        Xi = np.zeros([nC, n, nw], dtype=complex)
+        packs = [f.pack() for f in self.fowtList]
+        for c in range(nC):
+            Z = np.zeros([nw, n, n], dtype=complex)
+            F = np.zeros([nw, n], dtype=complex)
+            for i, P in enumerate(packs):
+                M = P["M0"][:, :, None] + (P["A_w"] if "A_w" in P else 0.0)
+                B = (P["B0"] + o["B_drag"][i, c])[:, :, None] + (P["B_w"] if "B_w" in P else 0.0)
+                Zi = np.moveaxis(-w ** 2 * M + 1j * w * B + P["C0"][:, :, None], 2, 0)     # [nw,6,6]
+                Z[:, 6 * i:6 * i + 6, 6 * i:6 * i + 6] = Zi
+                F[:, 6 * i:6 * i + 6] = np.moveaxis(o["F_BEM"][i, c] + o["F_iner"][i, c] + o["F_drag"][i, c], 0, 1)
+            Z += self.C_array[None, :, :]
+            X, info = solver.system_solve(Z, F)
+            if np.any(info):
+                raise np.linalg.LinAlgError("singular system impedance matrix")
+            Xi[c] = X.T
+        return Xi

@@ -271,7 +271,9 @@ def pinned_empty(shape, dtype):
 class DeviceSession:
     """Tables, workspace and outputs resident in HBM (torch tensors); kernels on torch's current stream."""
 
-    def __init__(self, batch, cases, device=None, want=("Xi", "status", "B_drag"), workspace_bytes=None):
+    def __init__(self, batch, cases, device=None, want=("Xi", "status", "B_drag"), workspace_bytes=None, tables=False):
+        """``tables=True`` sizes the workspace for ``excitation()`` / ``linearization()`` (global wave tables);
+        the default covers ``solve()`` only (the fused solver keeps its tables on chip)."""
         import torch
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -282,7 +284,7 @@ class DeviceSession:
             self.ct = {k: torch.from_numpy(v).to(self.device) for k, v in cases.arrays.items()}
             self.d_struct = batch.struct(lambda name: self.dt[name].data_ptr())
             self.c_struct = cases.struct(lambda name: self.ct[name].data_ptr())
-            need = lib.raftk_workspace_bytes(C.byref(self.d_struct), cases.n_cases)
+            need = (lib.raftk_workspace_bytes if tables else lib.raftk_solve_workspace_bytes)(C.byref(self.d_struct), cases.n_cases)
             self.workspace_bytes = int(need if workspace_bytes is None else workspace_bytes)
             self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
             nD, nC, nw = batch.n_designs, cases.n_cases, batch.nw

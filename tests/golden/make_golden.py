@@ -65,9 +65,28 @@ def run_solves(model, cases):
     return np.array(Xi), np.array(passes, dtype=np.int32)
 
 
+DESIGNS = {}
+
+
+def _plain(x):
+    """YAML-loaded design section -> plain JSON types."""
+    if isinstance(x, dict):
+        return {str(k): _plain(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_plain(v) for v in x]
+    if isinstance(x, np.ndarray):
+        return x.tolist()
+    if isinstance(x, (np.floating, np.integer)):
+        return x.item()
+    return x
+
+
 def fixture(name, yaml_path, nw=None, max_freq=None, solve_cases=(), pickles=None, lin_check=True):
     t0 = time.time()
     design = rh.load_design(yaml_path, nw=nw, max_freq=max_freq)
+    # the input side of the fixture: the design sections the hot path reads (platform members, site, settings)
+    plat = {k: v for k, v in design["platform"].items() if k not in ("hydroPath",)}
+    DESIGNS[name] = _plain(dict(settings=design.get("settings", {}), site=design["site"], platform=plat))
     model = rh.build_model(design)
     fowt = model.fowtList[0]
     P = packer.pack_fowt(fowt)
@@ -142,6 +161,10 @@ def main():
         if args.only and args.only not in j["name"]:
             continue
         fixture(**j)
+    if not args.only:
+        import json
+        with open(os.path.join(OUT, "designs.json"), "w") as f:
+            json.dump(DESIGNS, f, indent=0, sort_keys=True)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,117 @@
+"""Host logic (CPU): the node-table builder against tables packed from the live reference, the Model/FOWT
+mirror's construction, and the multi-GPU sharding logic on world_size-2 gloo."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden, relerr
+
+DESIGNS = json.load(open(os.path.join(GOLDEN, "designs.json")))
+TABLE_KEYS = ["mem_q", "mem_p1", "mem_p2", "mem_rA", "node_r", "node_ls", "node_cd_q", "node_cd_p1", "node_cd_p2",
+              "node_in_q", "node_in_p1", "node_in_p2", "node_pa", "node_a_i", "node_Imat", "k", "w"]
+
+
+@pytest.mark.parametrize("name", sorted(DESIGNS))
+def test_builder_matches_reference_tables(name):
+    """raft_b200.member/fowt rebuild, from the design dict alone, the tables packed from the reference's objects
+    (strip discretisation, frames, node positions, drag/inertia coefficients, MacCamy-Fuchs, A_hydro_morison)."""
+    from raft_b200.fowt import FOWT
+    G, P = load_golden(name)
+    f = FOWT(DESIGNS[name], P["w"], depth=float(P["depth"]))
+    A = f.calcHydroConstants()
+    Q = f.pack()
+    for k in TABLE_KEYS:
+        assert np.asarray(Q[k]).shape == np.asarray(P[k]).shape, k
+        if np.asarray(P[k]).size and np.abs(P[k]).max() > 0:
+            assert relerr(Q[k], P[k]) < 1e-14, k
+    assert np.array_equal(Q["mem_circ"], P["mem_circ"]) and np.array_equal(Q["mem_start"], P["mem_start"])
+    if np.abs(G["A_hydro_morison"]).max() > 0:
+        assert relerr(A, G["A_hydro_morison"]) < 1e-14
+        if "ref_pickle_A_hydro_morison" in G:                     # the reference's own hydroConstants pickle
+            assert relerr(A, G["ref_pickle_A_hydro_morison"]) < 1e-12
+    if "node_in_p1_w" in P:
+        assert relerr(Q["node_in_p1_w"], P["node_in_p1_w"]) < 1e-13
+
+
+def test_member_input_errors():
+    from raft_b200.member import Member
+    base = dict(name="m", type="rigid", rA=[0, 0, -10], rB=[0, 0, 5], shape="circ", stations=[0, 1], d=2.0)
+    Member(base).setPosition()
+    with pytest.raises(ValueError):
+        Member(dict(base, rA=[0, 0, 0]))
+    with pytest.raises(ValueError):
+        Member(dict(base, stations=[1, 0]))
+    with pytest.raises(ValueError):
+        Member(dict(base, shape="hex"))
+    with pytest.raises(NotImplementedError):
+        Member(dict(base, type="beam"))
+    m = Member(dict(base, shape="rect", d=[2.0, 3.0], Cd=[0.5, 0.7])).setPosition()
+    assert m.ds.shape == (m.ns, 2) and np.all(m.Cd_p1 == 0.5) and np.all(m.Cd_p2 == 0.7)
+
+
+def test_model_construction_and_sweep_variants():
+    from raft_b200 import sweep
+    from raft_b200.model import Model
+    G, P = load_golden("cfg2_VolturnUS-S_nw64")
+    mats = dict(M_struc=P["M0"] - G["A_hydro_morison"], C_struc=P["C0"] - G["C_moor"], C_moor=G["C_moor"])
+    design = dict(DESIGNS["cfg2_VolturnUS-S_nw64"], site=dict(DESIGNS["cfg2_VolturnUS-S_nw64"]["site"], water_depth=float(P["depth"])))
+    m = Model(design, matrices=mats)
+    assert m.nw == 64 and m.nDOF == 6 and len(m.fowtList[0].memberList) == 10
+    Q = m.fowtList[0].pack()
+    assert relerr(Q["M0"], P["M0"]) < 1e-14 and relerr(Q["C0"], P["C0"]) < 1e-14
+    fac = sweep.sample_factors(5, seed=40)
+    assert fac.shape == (5, 5) and fac.min() >= 0.75 and fac.max() <= 1.25
+    V = sweep.build_variants(DESIGNS["cfg2_VolturnUS-S_nw64"], mats, fac[:3], nw=32, max_freq=0.4, depth=float(P["depth"]))
+    assert len(V) == 3 and all(len(v["w"]) == 32 for v in V)
+    assert not np.allclose(V[0]["node_cd_p1"][:5], V[1]["node_cd_p1"][:5])
+    one = sweep.build_variants(DESIGNS["cfg2_VolturnUS-S_nw64"], mats, np.ones((1, 5)), nw=64, max_freq=0.512, depth=float(P["depth"]))[0]
+    for k in ("node_ls", "node_cd_q", "node_in_p1", "mem_rA"):
+        assert relerr(one[k], P[k]) < 1e-12, k
+
+
+def test_shard_bounds():
+    from raft_b200.sweep import shard_bounds
+    for n, world in ((10000, 8), (7, 2), (3, 4), (0, 2)):
+        cuts = [shard_bounds(n, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+        sizes = [b - a for a, b in cuts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, n_items, q):
+    import torch
+    import torch.distributed as dist
+    from raft_b200.sweep import all_gather_blocks, shard_bounds
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_bounds(n_items, rank, world)
+    idx = torch.arange(lo, hi, dtype=torch.float64)
+    local = (idx[:, None, None] * 10 + torch.arange(3, dtype=torch.float64)[None, :, None] + 1j * torch.arange(2)[None, None, :]).to(torch.complex128)
+    full = all_gather_blocks(local, n_items)
+    st = all_gather_blocks(torch.arange(lo, hi, dtype=torch.int32)[:, None].repeat(1, 4), n_items)
+    q.put((rank, full.numpy(), st.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [6, 7])
+def test_all_gather_blocks_gloo_world2(n_items):
+    """The N>1 data path (contiguous design shards + one all-gather, ragged by one) on 2 gloo ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + n_items
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_items, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = (np.arange(n_items)[:, None, None] * 10 + np.arange(3)[None, :, None] + 1j * np.arange(2)[None, None, :])
+    for rank, full, st in got:
+        assert full.shape == (n_items, 3, 2) and np.array_equal(full, want)
+        assert np.array_equal(st[:, 0], np.arange(n_items))

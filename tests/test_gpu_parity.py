@@ -172,3 +172,106 @@ def test_system_solve_vs_oracle(solver, oracle):
         for r in range(nrhs):
             Xo = oracle.system_response(A, F[:, :, r])
             assert relerr(X[:, :, r], Xo) < 1e-11
+
+
+# ---- reference-facing API mirror (raft_b200.Model / FOWT) ------------------------------------------------------
+def _model_from_golden(name):
+    import json, os
+    from conftest import GOLDEN
+    from raft_b200.model import Model
+    G, P = load_golden(name)
+    D = json.load(open(os.path.join(GOLDEN, "designs.json")))[name]
+    design = dict(D, site=dict(D["site"], water_depth=float(P["depth"])))
+    mats = dict(M_struc=P["M0"] - G["A_hydro_morison"], C_struc=P["C0"] - G["C_moor"], C_moor=G["C_moor"])
+    return Model(design, matrices=mats), G, P
+
+
+@pytest.mark.parametrize("name", ["cfg2_VolturnUS-S_nw64", "cfg1_OC3spar", "test_VolturnUS-S"])
+def test_model_api_vs_reference_run(name, solver):
+    """Design dict -> own builder -> packer -> C ABI -> kernels, against the unmodified reference's responses."""
+    model, G, P = _model_from_golden(name)
+    for i, (Hs, Tp, beta) in enumerate(G["ref_run_solve_cases"]):
+        case = dict(wave_spectrum="JONSWAP", wave_height=Hs, wave_period=Tp, wave_heading=beta, wave_gamma=0.0)
+        Xi = model.solveDynamics(case)
+        assert Xi.shape == (2, 6, model.nw) and np.all(Xi[1] == 0)
+        assert response_err(Xi[0], G["ref_run_solve_Xi"][i]) < RTOL
+    # all cases of the fixture in one batched analyzeCases call
+    cases = [dict(wave_spectrum="JONSWAP", wave_height=h, wave_period=t, wave_heading=b) for h, t, b in G["ref_run_solve_cases"]]
+    res = model.analyzeCases(cases)
+    assert np.array_equal(res["status"][:, 0, 0], G["ref_run_solve_passes"])
+    assert response_err(res["Xi"], G["ref_run_solve_Xi"]) < RTOL
+    # fowt.Z left behind = impedance of the last pass (raft_model.py:1155): Z Xi = F_BEM + F_iner + F_drag
+    f = model.fowtList[0]
+    lhs = np.einsum("abw,bw->aw", f.Z, res["Xi"][-1])
+    rhs = f.F_BEM[0] + f.F_hydro_iner[0] + f.F_hydro_drag
+    assert relerr(lhs, rhs) < 1e-9
+
+
+def test_fowt_api_vs_reference_run(solver):
+    """FOWT.calcHydroExcitation / calcHydroLinearization / calcDragExcitation mirror on the reference's own recipe."""
+    model, G, P = _model_from_golden("test_VolturnUS-S")
+    f = model.fowtList[0]
+    f.calcHydroExcitation(dict(wave_spectrum="unit", wave_heading=0, wave_period=10, wave_height=2))
+    assert f.nWaves == 1 and relerr(f.zeta[0], G["ref_run_lin_zeta"]) < 1e-14
+    assert relerr(f.F_hydro_iner[0], G["ref_run_lin_F_hydro_iner"]) < RTOL
+    B = f.calcHydroLinearization(G["ref_run_lin_Xi"])
+    assert relerr(B, G["ref_pickle_lin_B_hydro_drag"]) < RTOL
+    assert relerr(f.calcDragExcitation(0), G["ref_pickle_lin_F_hydro_drag"]) < RTOL
+    with pytest.raises(ValueError):
+        f.calcHydroExcitation(dict(wave_spectrum="bogus", wave_heading=0, wave_period=10, wave_height=2))
+
+
+def test_sweep_single_gpu_vs_oracle(solver, oracle):
+    """Synthetic geometry variants (ragged node counts) in one batch: every design against the oracle."""
+    import json, os
+    import torch
+    from conftest import GOLDEN
+    from raft_b200 import sweep
+    G, P = load_golden("cfg2_VolturnUS-S_nw64")
+    D = json.load(open(os.path.join(GOLDEN, "designs.json")))["cfg2_VolturnUS-S_nw64"]
+    mats = dict(M_struc=P["M0"] - G["A_hydro_morison"], C_struc=P["C0"] - G["C_moor"], C_moor=G["C_moor"])
+    V = sweep.build_variants(D, mats, sweep.sample_factors(12, seed=40), nw=160, max_freq=0.4, depth=float(P["depth"]))
+    assert len(set(len(v["node_ls"]) for v in V)) > 1
+    cs = sea_states(4, 3)
+    Xi, st = sweep.solve_sweep(V, cs, n_iter=10)
+    torch.cuda.synchronize()
+    Xi, st = Xi.cpu().numpy(), st.cpu().numpy()
+    assert np.all(st[..., 2] == 0)
+    for d, Q in enumerate(V):
+        Xi_o, st_o, _ = oracle.solve_cases(oracle.OracleDesign(Q), cs, nIter=10)
+        assert np.array_equal(st[d, :, 0], st_o[:, 0]), d
+        assert response_err(Xi[d], Xi_o) < RTOL, d
+
+
+def test_farm_coupled_response_vs_oracle(solver, oracle):
+    """Two-unit farm (raft_model.py:1164-1216): independent linearisation per FOWT, then the coupled 12x12 system
+    with an injected array-mooring stiffness, against the oracle's Z / inverse-based system response."""
+    import json, os
+    from conftest import GOLDEN
+    from raft_b200.model import Model
+    G, P = load_golden("cfg2_VolturnUS-S_nw64")
+    D = json.load(open(os.path.join(GOLDEN, "designs.json")))["cfg2_VolturnUS-S_nw64"]
+    mats = dict(M_struc=P["M0"] - G["A_hydro_morison"], C_struc=P["C0"] - G["C_moor"], C_moor=G["C_moor"])
+    design = dict(settings=D["settings"], site=dict(D["site"], water_depth=float(P["depth"])), platforms=[D["platform"]],
+                  array=dict(keys=["ID", "turbineID", "platformID", "mooringID", "x_location", "y_location", "heading_adjust"],
+                             data=[[1, 0, 1, 0, 0.0, 0.0, 0.0], [2, 0, 1, 0, 1600.0, 0.0, 0.0]]))
+    rng = np.random.default_rng(1)
+    A = rng.normal(size=(12, 12)) * 2e4
+    C_arr = A @ A.T / 12 + np.diag([5e4] * 12)
+    model = Model(design, matrices=mats, array_stiffness=C_arr)
+    assert model.nDOF == 12
+    case = dict(wave_spectrum="JONSWAP", wave_height=6.0, wave_period=12.0, wave_heading=20.0)
+    Xi = model.solveDynamics(case)[0]                       # [12, nw]
+    # oracle: per-FOWT loop (Z_i, F_i = Z_i Xi_i), then inv(Z_sys) F
+    nw = model.nw
+    Z = np.zeros([nw, 12, 12], dtype=complex)
+    F = np.zeros([nw, 12], dtype=complex)
+    for i, f in enumerate(model.fowtList):
+        Xi_i, st, Z_i, _ = oracle.solve_dynamics(oracle.OracleDesign(f.pack()), 0, 6.0, 12.0, 0.0, 20.0, nIter=model.nIter,
+                                                 XiStart=model.XiStart, want_Z=True)
+        Z[:, 6 * i:6 * i + 6, 6 * i:6 * i + 6] = Z_i
+        F[:, 6 * i:6 * i + 6] = np.einsum("wab,bw->wa", Z_i, Xi_i)
+    Xo = oracle.system_response(Z + C_arr[None], F).T
+    assert response_err(np.stack([Xi[:6], Xi[6:]]), np.stack([Xo[:6], Xo[6:]])) < 1e-9
+    # the second unit sees the wave later: phase differs, amplitude spectrum of the uncoupled problem would not
+    assert not np.allclose(Xi[:6], Xi[6:])
