@@ -301,7 +301,7 @@ def main():
     solver.profile_enable(False)
     k2_ms = kms[2] / max(kn[2], 1)
     launches_per_step = kn[2] / reps
-    Ns, Nm = batch.max_nodes, batch.max_members
+    Ns, Nm = batch.n_nodes_total / batch.n_designs, batch.n_members_total / batch.n_designs      # mean per design
     b_alg = algorithmic_bytes_per_solve(Ns, Nm, nC, nw, bem=batch.n_bem_head > 0)
     units_per_launch = units / launches_per_step
     peaks = {}
@@ -317,7 +317,8 @@ def main():
     except Exception:
         pass
     roofline = dict(bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak, traffic=traffic,
-                    kernel="k_drag_solve", kernel_ms=k2_ms, share_of_step=kms[2] / max(sum(kms), 1e-30),
+                    kernel="k_rao_fused (excitation + drag linearisation + 6x6 solves, on-chip)" if kn[1] == 0 else "k_drag_solve",
+                    kernel_ms=k2_ms, share_of_step=kms[2] / max(sum(kms), 1e-30),
                     algorithmic_bytes_per_solve=b_alg, peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                     other_kernels_ms=dict(depth_table=kms[0] / max(kn[0], 1), excitation=kms[1] / max(kn[1], 1)))
     fp64_peak = solver.fp64_peak_gflops(20000) if rank == 0 else 0.0
