@@ -57,6 +57,25 @@ def build_workload(args, rank, world):
                             "%d freq bins x %d sea states per GPU, fp64, nIter=10, tol=0.01" % (len(P["w"]), nC),
                    designs_per_gpu=1, cases_per_gpu=nC, nw=len(P["w"]), submerged_nodes=int(len(P["node_ls"])))
         return [P], cs, cfg
+    elif args.workload == "cfg3":
+        # BASELINE.json configs[2]: OC4semi with WAMIT added-mass/damping/excitation tables, 2048 bins x 256 sea states
+        from raft_b200 import bem, packer
+        from raft_b200.fowt import FOWT
+        nw, nC = args.nw or 2048, args.cases or 256
+        D = json.load(open(os.path.join(ROOT, "tests", "golden", "designs.json")))["cfg3_OC4semi-WAMIT_nw128"]
+        z = np.load(os.path.join(ROOT, "tests", "golden", "cfg3_OC4semi-WAMIT_nw128.npz"))
+        t = np.load(os.path.join(ROOT, "tests", "golden", "wamit_marin_semi.npz"))
+        w = grid.make_w(0.256 / nw, 0.256)
+        H = bem.read_hydro(t["A"], t["B"], t["w1"], t["Re"], t["Im"], t["w3"], t["heads"], w, rho=float(z["P_rho"]), g=float(z["P_g"]))
+        mats = dict(M_struc=z["P_M0"] - z["A_hydro_morison"], C_struc=z["P_C0"] - z["C_moor"], C_moor=z["C_moor"], **H)
+        f = FOWT(D, w, depth=float(z["P_depth"]), matrices=mats)
+        f.calcHydroConstants()
+        cs_all = sea_states(3, nC * world)
+        cs = {k: v[rank * nC:(rank + 1) * nC] for k, v in cs_all.items()}
+        cfg = dict(workload="cfg3: examples/OC4semi-WAMIT_Coefs.yaml (potModMaster 3: BEM A/B/X tables via readHydro of marin_semi.1/.3, "
+                            "drag-only strips), %d freq bins x %d sea states per GPU, fp64" % (nw, nC),
+                   designs_per_gpu=1, cases_per_gpu=nC, nw=nw)
+        return [f.pack()], cs, cfg
     else:
         from raft_b200 import sweep
         nD = args.designs or 1250
@@ -213,7 +232,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "sweep"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "sweep"])
     ap.add_argument("--nw", type=int, default=0)
     ap.add_argument("--cases", type=int, default=0)
     ap.add_argument("--designs", type=int, default=0)

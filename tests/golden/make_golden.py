@@ -162,6 +162,15 @@ def main():
             continue
         fixture(**j)
     if not args.only:
+        # raw WAMIT tables of the OC4 semi (reference data files examples/OC4semi-WAMIT_Coefs/marin_semi.1/.3),
+        # read with the product reader, so that readHydro can be exercised at any grid size off the build box
+        from raft_b200 import bem
+        hp = os.path.join(REF, "examples", "OC4semi-WAMIT_Coefs", "marin_semi")
+        A, B, w1 = bem.read_wamit1(hp + ".1")
+        _, _, Re, Im, w3, heads = bem.read_wamit3(hp + ".3")
+        np.savez_compressed(os.path.join(OUT, "wamit_marin_semi.npz"), A=A, B=B, w1=w1, Re=Re.astype(np.float64),
+                            Im=Im.astype(np.float64), w3=w3, heads=heads)
+        print("wamit_marin_semi.npz %.0f KB" % (os.path.getsize(os.path.join(OUT, "wamit_marin_semi.npz")) / 1024))
         import json
         with open(os.path.join(OUT, "designs.json"), "w") as f:
             json.dump(DESIGNS, f, indent=0, sort_keys=True)

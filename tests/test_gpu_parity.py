@@ -275,3 +275,26 @@ def test_farm_coupled_response_vs_oracle(solver, oracle):
     assert response_err(np.stack([Xi[:6], Xi[6:]]), np.stack([Xo[:6], Xo[6:]])) < 1e-9
     # the second unit sees the wave later: phase differs, amplitude spectrum of the uncoupled problem would not
     assert not np.allclose(Xi[:6], Xi[6:])
+
+
+def test_cfg3_bem_tables_from_wamit_vs_oracle(solver, oracle):
+    """configs[2] pipeline off the build box: raw WAMIT tables -> readHydro on a 512-bin grid -> fused solver, vs oracle."""
+    import json, os
+    from conftest import GOLDEN
+    from raft_b200 import bem, grid
+    from raft_b200.fowt import FOWT
+    G, P = load_golden("cfg3_OC4semi-WAMIT_nw128")
+    D = json.load(open(os.path.join(GOLDEN, "designs.json")))["cfg3_OC4semi-WAMIT_nw128"]
+    t = np.load(os.path.join(GOLDEN, "wamit_marin_semi.npz"))
+    w = grid.make_w(0.256 / 512, 0.256)
+    H = bem.read_hydro(t["A"], t["B"], t["w1"], t["Re"], t["Im"], t["w3"], t["heads"], w, rho=float(P["rho"]), g=float(P["g"]))
+    mats = dict(M_struc=P["M0"] - G["A_hydro_morison"], C_struc=P["C0"] - G["C_moor"], C_moor=G["C_moor"], **H)
+    f = FOWT(D, w, depth=float(P["depth"]), matrices=mats)
+    f.calcHydroConstants()
+    Q = f.pack()
+    assert Q["X_BEM"].shape == (37, 6, 512) and Q["A_w"].shape == (6, 6, 512)
+    cs = sea_states(3, 6)
+    out = solver.solve_dynamics(solver.DesignBatch(Q), solver.CaseTable(cs), n_iter=10)
+    Xi_o, st_o, _ = oracle.solve_cases(oracle.OracleDesign(Q), cs, nIter=10)
+    assert np.array_equal(out["status"][0, :, 0], st_o[:, 0])
+    assert response_err(out["Xi"][0], Xi_o) < RTOL
