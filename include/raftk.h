@@ -201,6 +201,18 @@ int raftk_system_solve_dev(int32_t n, int32_t nw, int32_t nrhs, double *Z, doubl
                            void *stream);
 int raftk_system_solve_host(int32_t n, int32_t nw, int32_t nrhs, double *Z, double *F, int32_t *info);
 
+/*
+ * Response statistics of FOWT.saveTurbineOutputs (raft_fowt.py:2299-2353) as reductions over Xi:
+ * for every unit (design, case) and DOF   std = sqrt(1/2 sum_w |Xi|^2)   (helpers.getRMS, helpers.py:678-684)
+ * and, if psd != NULL,                    PSD(w) = 1/2 |Xi(w)|^2 / dw    (helpers.getPSD, helpers.py:687-700).
+ * Rotational DOFs (3..5) are converted to degrees first when rot_deg != 0, like the reference's roll/pitch/yaw.
+ * Xi complex [n_units,6,nw] -> std [n_units,6], psd [n_units,6,nw].
+ */
+int raftk_response_stats_dev(int32_t n_units, int32_t nw, double dw, int32_t rot_deg, const double *Xi,
+                             double *std, double *psd, void *stream);
+int raftk_response_stats_host(int32_t n_units, int32_t nw, double dw, int32_t rot_deg, const double *Xi,
+                              double *std, double *psd);
+
 /* Pinned host memory for the *_host paths and the e2e benchmark (cudaHostAlloc / cudaFreeHost). */
 void *raftk_host_alloc(size_t bytes);
 void raftk_host_free(void *p);

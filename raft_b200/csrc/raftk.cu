@@ -1472,6 +1472,28 @@ __global__ void __launch_bounds__(128) k_system_solve(int n, int nrhs, double2 *
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4: response statistics (std, PSD) -- one CTA per (unit, dof), fixed-order block reduction over frequency
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_response_stats(int nw, double dw, int rot_deg, const double2 *Xi, double *sd, double *psd)
+{
+    __shared__ double part[4];
+    const int row = blockIdx.x, dof = row % 6, tid = threadIdx.x;
+    const double scale = (rot_deg && dof >= 3) ? (180.0 / CUDART_PI) : 1.0;      // np.rad2deg
+    const double2 *x = Xi + (size_t)row * nw;
+    double s = 0.0;
+    for (int i = tid; i < nw; i += 128) {
+        const double re = x[i].x * scale, im = x[i].y * scale;
+        const double a2 = re * re + im * im;
+        s += a2;
+        if (psd) psd[(size_t)row * nw + i] = 0.5 * a2 / dw;
+    }
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) part[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) sd[row] = sqrt(0.5 * (((part[0] + part[1]) + part[2]) + part[3]));
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 FMA peak micro-kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters)
@@ -1971,6 +1993,34 @@ extern "C" int raftk_system_solve_host(int32_t n, int32_t nw, int32_t nrhs, doub
         if (info) CUDA_TRY(cudaMemcpy(info, dI, ib, cudaMemcpyDeviceToHost));
     }
     cudaFree(dZ); cudaFree(dF); cudaFree(dI);
+    return rc;
+}
+
+extern "C" int raftk_response_stats_dev(int32_t n_units, int32_t nw, double dw, int32_t rot_deg, const double *Xi,
+                                        double *sd, double *psd, void *stream)
+{
+    if (n_units <= 0 || nw <= 0 || !Xi || !sd || !(dw > 0.0)) return set_err(RAFTK_EINVAL, "bad response-stats arguments");
+    k_response_stats<<<(unsigned)n_units * 6u, 128, 0, (cudaStream_t)stream>>>(nw, dw, rot_deg, reinterpret_cast<const double2 *>(Xi), sd, psd);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RAFTK_OK;
+}
+
+extern "C" int raftk_response_stats_host(int32_t n_units, int32_t nw, double dw, int32_t rot_deg, const double *Xi,
+                                         double *sd, double *psd)
+{
+    if (n_units <= 0 || nw <= 0 || !Xi || !sd || !(dw > 0.0)) return set_err(RAFTK_EINVAL, "bad response-stats arguments");
+    const size_t xb = (size_t)n_units * 6 * nw * 16, sb = (size_t)n_units * 6 * 8, pb = (size_t)n_units * 6 * nw * 8;
+    double *dX = nullptr, *dS = nullptr, *dP = nullptr;
+    CUDA_TRY(cudaMalloc(&dX, xb)); CUDA_TRY(cudaMalloc(&dS, sb));
+    if (psd) CUDA_TRY(cudaMalloc(&dP, pb));
+    CUDA_TRY(cudaMemcpy(dX, Xi, xb, cudaMemcpyHostToDevice));
+    int rc = raftk_response_stats_dev(n_units, nw, dw, rot_deg, dX, dS, dP, nullptr);
+    if (!rc) {
+        CUDA_TRY(cudaMemcpy(sd, dS, sb, cudaMemcpyDeviceToHost));
+        if (psd) CUDA_TRY(cudaMemcpy(psd, dP, pb, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(dX); cudaFree(dS); if (dP) cudaFree(dP);
     return rc;
 }
 

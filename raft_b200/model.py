@@ -67,6 +67,22 @@ class Model:
         self.results["freq_rad"] = self.w
         self.results["Xi"] = out["Xi"]
         self.results["status"] = out["status"]
+        # response statistics per case and FOWT (raft_fowt.py:2299-2353; zero mean offsets: statics are out of scope)
+        nC = len(cases)
+        Xi_units = out["Xi"].reshape(nC, self.nFOWT, 6, self.nw)
+        sd, psd = solver.response_stats(Xi_units, self.w[1] - self.w[0])
+        names = ("surge", "sway", "heave", "roll", "pitch", "yaw")
+        self.results["case_metrics"] = {}
+        for ic in range(nC):
+            self.results["case_metrics"][ic] = {}
+            for i in range(self.nFOWT):
+                m = {}
+                for k_, nm in enumerate(names):
+                    m[nm + "_avg"], m[nm + "_std"] = 0.0, sd[ic, i, k_]
+                    m[nm + "_max"], m[nm + "_min"] = 3 * sd[ic, i, k_], -3 * sd[ic, i, k_]
+                    m[nm + "_PSD"] = psd[ic, i, k_]
+                    m[nm + "_RA"] = Xi_units[ic, i, k_] * (180 / np.pi if k_ >= 3 else 1.0)
+                self.results["case_metrics"][ic][i] = m
         return self.results
 
     def _solve_batch(self, cases, tol):

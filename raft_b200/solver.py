@@ -255,6 +255,21 @@ def system_solve(Z, F):
 _PINNED = []
 
 
+def response_stats(Xi, dw, psd=True, rot_deg=True):
+    """std / PSD per DOF of responses Xi [...,6,nw] (FOWT.saveTurbineOutputs, raft_fowt.py:2299-2353):
+    std = sqrt(1/2 sum |Xi|^2), PSD = 1/2 |Xi|^2 / dw, rotations in degrees.  -> (std [...,6], PSD [...,6,nw] or None)."""
+    Xi = np.ascontiguousarray(Xi, dtype=np.complex128)
+    lead, nw = Xi.shape[:-2], Xi.shape[-1]
+    if Xi.shape[-2] != 6:
+        raise ValueError("Xi must be [..., 6, nw]")
+    n = int(np.prod(lead)) if lead else 1
+    sd = np.zeros(lead + (6,))
+    P = np.zeros(lead + (6, nw)) if psd else None
+    check(lib.raftk_response_stats_host(n, nw, float(dw), 1 if rot_deg else 0, Xi.ctypes.data, sd.ctypes.data,
+                                        P.ctypes.data if psd else None))
+    return sd, P
+
+
 def pinned_empty(shape, dtype):
     """NumPy array backed by page-locked host memory (cudaHostAlloc) for the e2e path."""
     dtype = np.dtype(dtype)

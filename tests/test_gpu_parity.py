@@ -298,3 +298,20 @@ def test_cfg3_bem_tables_from_wamit_vs_oracle(solver, oracle):
     Xi_o, st_o, _ = oracle.solve_cases(oracle.OracleDesign(Q), cs, nIter=10)
     assert np.array_equal(out["status"][0, :, 0], st_o[:, 0])
     assert response_err(out["Xi"][0], Xi_o) < RTOL
+
+
+def test_response_stats_vs_reference_formulas(solver):
+    """std / PSD reductions of saveTurbineOutputs (helpers.getRMS :684, getPSD :694, rad2deg on rotations)."""
+    rng = np.random.default_rng(9)
+    Xi = (rng.normal(size=(3, 5, 6, 333)) + 1j * rng.normal(size=(3, 5, 6, 333))) * rng.uniform(0.01, 2, size=(3, 5, 6, 1))
+    dw = 0.0123
+    sd, psd = solver.response_stats(Xi, dw)
+    Xd = Xi.copy(); Xd[..., 3:, :] = np.rad2deg(Xd[..., 3:, :])
+    assert relerr(sd, np.sqrt(0.5 * np.sum(np.abs(Xd) ** 2, axis=-1))) < 1e-14
+    assert relerr(psd, 0.5 * np.abs(Xd) ** 2 / dw) < 1e-14
+    model, G, P = _model_from_golden("cfg1_OC3spar")
+    res = model.analyzeCases([dict(wave_spectrum="JONSWAP", wave_height=2.0, wave_period=8.0, wave_heading=0.0)])
+    m = res["case_metrics"][0][0]
+    ref = G["ref_run_solve_Xi"][0]
+    assert abs(m["surge_std"] - np.sqrt(0.5 * np.sum(np.abs(ref[0]) ** 2))) < 1e-10 * m["surge_std"]
+    assert relerr(m["pitch_PSD"], 0.5 * np.abs(np.rad2deg(ref[4])) ** 2 / (P["w"][1] - P["w"][0])) < 1e-9
