@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libraftk.so")
+LIB_PATH = os.environ.get("RAFTK_LIB", os.path.join(HERE, "csrc", "libraftk.so"))   # RAFTK_LIB: A/B builds of the same ABI
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

@@ -392,6 +392,7 @@ __device__ __forceinline__ bool solve6(double (&ar)[6][6], double (&ai)[6][6], d
             if (t > best) { best = t; p = i; }
         });
         if (best == 0.0) ok = false;
+        // (measured: guarding the swaps with a warp vote "does any lane pivot here?" is 4 % slower than always selecting)
         static_for<k + 1, 6>([&](auto I) {
             constexpr int i = decltype(I)::value;
             // row swap as register selects (a dynamic row index would push the matrix to local memory)
@@ -803,7 +804,7 @@ struct FusedParams {
 #define NCOEF 5            // per-node linearised coefficients: bq, b1, ls*b1, b2, ls*b2
 
 struct FSmem {
-    double *mem, *node, *coef, *msum, *mat, *warp_part, *sums, *tot, *xi, *f0, *ckpt, *wkey, *hkey, *zkey, *scr;
+    double *mem, *node, *coef, *msum, *mat, *warp_part, *sums, *tot, *xi, *f0, *ckpt, *wkey, *hkey, *zkey, *scr, *trans;
     double2 *ebase, *abase, *wtab, *htab;
     int *imem, *node_w, *node_h, *iscr, *cnt;
 };
@@ -811,7 +812,7 @@ struct FSmem {
 __host__ __device__ inline size_t fused_smem_bytes(int Nm, int NsP, int nchunk, int nwarps, int nwl, int maxW, int maxH, int maxZ, bool f0_smem)
 {
     size_t dbl = (size_t)Nm * MEM_STRIDE + 4 * (size_t)NsP + NCOEF * (size_t)NsP + (size_t)Nm * 8 + 108
-                 + (size_t)nchunk * nwarps * 32 + 2 * ((size_t)nchunk * 32 + 2) + (size_t)nchunk * 32
+                 + (size_t)nchunk * nwarps * 32 + 2 * ((size_t)nchunk * 32 + 2) + (size_t)nchunk * 32 + (size_t)nwarps * 16 * 33
                  + (12 + (f0_smem ? 12 : 0) + 4) * (size_t)nwl + 2 * (size_t)maxW + (size_t)maxH + (size_t)maxZ + 3 * (size_t)NsP
                  + 2 * ((size_t)Nm + maxZ + maxW + maxH) * nwl;
     size_t ints = (size_t)Nm * IMEM_STRIDE + 4 * (size_t)NsP + 8;
@@ -879,6 +880,7 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         S.hkey = p; p += (size_t)P.maxH;
         S.zkey = p; p += (size_t)P.maxZ;
         S.scr = p; p += 3 * (size_t)NsP;
+        S.trans = p; p += (size_t)nwarps * 16 * 33;
         S.imem = reinterpret_cast<int *>(p);
         S.node_w = S.imem + (size_t)NmP * IMEM_STRIDE;
         S.node_h = S.node_w + NsP;
@@ -1214,8 +1216,24 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
                     S.ckpt[t] = er; S.ckpt[nwl + t] = ei; S.ckpt[2 * nwl + t] = ap; S.ckpt[3 * nwl + t] = am;
                 }
             }
-            const double r = warp_multi_reduce32(acc);
-            S.warp_part[(ch * nwarps + warp) * 32 + lane] = r;
+            // warp sum of the 30 accumulators through a padded shared-memory transpose (16 values at a time):
+            // every lane stores its values, then lane l adds 16 lanes' worth of value (l & 15) -- fixed order.
+            {
+                double *tr = S.trans + warp * (16 * 33);
+                const int row = lane & 15, part = lane >> 4;
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+#pragma unroll
+                    for (int v = 0; v < 16; v++) tr[v * 33 + lane] = acc[half * 16 + v];
+                    __syncwarp();
+                    double sum = 0.0;
+#pragma unroll
+                    for (int x = 0; x < 16; x++) sum += tr[row * 33 + part * 16 + x];
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                    if (lane < 16) S.warp_part[(ch * nwarps + warp) * 32 + half * 16 + lane] = sum;
+                    __syncwarp();
+                }
+            }
         }
         __syncthreads();
         for (int t = tid; t < nchunk * 32; t += T) {
@@ -1287,6 +1305,7 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
 
         // ================= pass part 2: drag excitation, impedance, solve, convergence =============
         int conv_local = 1, nan_local = 0;
+        const double *cq_ = S.coef, *c1_ = S.coef + NsP, *cl1_ = S.coef + 2 * NsP, *c2_ = S.coef + 3 * NsP, *cl2_ = S.coef + 4 * NsP;
         for (int t = tid; t < nloc; t += T) {
             const int i = f_begin + t;
             const double w = D.w[i];
@@ -1307,7 +1326,7 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
                         if (wi >= 0) { const double2 W = S.wtab[wi * nwl + t]; const double tr = fma(er, W.x, -ei * W.y); ei = fma(er, W.y, ei * W.x); er = tr; }
                         if (hi >= 0) { const double2 H = S.htab[hi * nwl + t]; ap *= H.x; am *= H.y; }
                     }
-                    const double bq = S.coef[j], b1 = S.coef[NsP + j], lb1 = S.coef[2 * NsP + j], b2 = S.coef[3 * NsP + j], lb2 = S.coef[4 * NsP + j];
+                    const double bq = cq_[j], b1 = c1_[j], lb1 = cl1_[j], b2 = c2_[j], lb2 = cl2_[j];
                     const double Cc = ap + am, Sc = ap - am;
                     double cr, ci;
                     proj(kq, er, ei, Cc, Sc, hq, dzq, cr, ci);
