@@ -315,3 +315,22 @@ def test_response_stats_vs_reference_formulas(solver):
     ref = G["ref_run_solve_Xi"][0]
     assert abs(m["surge_std"] - np.sqrt(0.5 * np.sum(np.abs(ref[0]) ** 2))) < 1e-10 * m["surge_std"]
     assert relerr(m["pitch_PSD"], 0.5 * np.abs(ref[4] * 180.0 / np.pi) ** 2 / (P["w"][1] - P["w"][0])) < 1e-9
+
+
+def test_error_paths_nan_and_singular(solver):
+    """NaN in the response stops the unit and sets RAFTK_FLAG_NAN (the reference raises at raft_model.py:1098);
+    a singular impedance sets RAFTK_FLAG_SINGULAR; the Model mirror turns the NaN flag into the reference's exception."""
+    _, P = load_golden("cfg1_OC3spar")
+    cs = solver.CaseTable(dict(Hs=[3.0], Tp=[9.0], gamma=[0.0], beta_deg=[10.0], spec=np.array([0], dtype=np.int32)))
+    Q = dict(P); Q["M0"] = P["M0"].copy(); Q["M0"][2, 2] = np.nan
+    out = solver.solve_dynamics(solver.DesignBatch(Q), cs, n_iter=10)
+    assert out["status"][0, 0, 2] & 1 and out["status"][0, 0, 0] == 1 and out["status"][0, 0, 1] == 0
+    Z = dict(P); Z["M0"] = np.zeros((6, 6)); Z["B0"] = np.zeros((6, 6)); Z["C0"] = np.zeros((6, 6))
+    for k in ("node_cd_q", "node_cd_p1", "node_cd_p2"):
+        Z[k] = np.zeros_like(P[k])
+    out = solver.solve_dynamics(solver.DesignBatch(Z), cs, n_iter=2)
+    assert out["status"][0, 0, 2] & 2
+    model, G, _ = _model_from_golden("cfg1_OC3spar")
+    model.fowtList[0].M_struc[0, 0] = np.nan
+    with pytest.raises(Exception, match="Nan detected in response vector Xi."):
+        model.solveDynamics(dict(wave_spectrum="JONSWAP", wave_height=2.0, wave_period=8.0, wave_heading=0.0))
