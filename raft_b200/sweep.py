@@ -101,3 +101,52 @@ def solve_sweep(packed_designs, cases, n_iter=10, tol=0.01, xi_start=0.0, device
     out = sess.solve(n_iter=n_iter, tol=tol, xi_start=xi_start)
     n_total = len(packed_designs) if n_total is None else n_total
     return all_gather_blocks(out["Xi"], n_total, group), all_gather_blocks(out["status"], n_total, group)
+
+
+class PipelinedSolve:
+    """Solve this rank's units in ``n_chunks`` launches and overlap each chunk's all-gather (NCCL, side stream)
+    with the next chunk's kernels -- the transfer of chunk i hides behind the compute of chunk i+1.
+
+    ``split="designs"`` chunks the design list (sweeps), ``split="cases"`` the case table (one design, many sea
+    states).  ``gathered[i]`` is [world, ...] for chunk i; with one rank nothing is gathered."""
+
+    def __init__(self, packed_designs, cases, n_chunks=2, split="designs", device=None, group=None, want=("Xi", "status")):
+        import torch
+        import torch.distributed as dist
+        from . import solver
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        designs = [packed_designs] if isinstance(packed_designs, dict) else list(packed_designs)
+        n = len(designs) if split == "designs" else len(cases["Hs"])
+        n_chunks = max(1, min(n_chunks, n))
+        self.sessions = []
+        for i in range(n_chunks):
+            lo, hi = shard_bounds(n, i, n_chunks)
+            if split == "designs":
+                sess = solver.DeviceSession(solver.DesignBatch(designs[lo:hi]), solver.CaseTable(cases), device=device, want=want)
+            else:
+                sub = {k: np.asarray(v)[lo:hi] for k, v in cases.items()}
+                sess = solver.DeviceSession(solver.DesignBatch(designs), solver.CaseTable(sub), device=device, want=want)
+            self.sessions.append(sess)
+        dev = self.sessions[0].device
+        self.comm = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.gathered = [torch.empty((self.world,) + tuple(s.out["Xi"].shape), dtype=s.out["Xi"].dtype, device=dev)
+                         if self.world > 1 else None for s in self.sessions]
+        self.units = sum(s.batch.n_designs * s.cases.n_cases * s.batch.nw for s in self.sessions)
+
+    def step(self, **solve_kw):
+        torch = self.torch
+        cur = torch.cuda.current_stream(self.sessions[0].device)
+        for sess, g in zip(self.sessions, self.gathered):
+            sess.solve(**solve_kw)
+            if self.world > 1:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(ev)
+                    self.dist.all_gather_into_tensor(g, sess.out["Xi"], group=self.group)
+        if self.world > 1:
+            cur.wait_stream(self.comm)
+
+    def status(self):
+        return np.concatenate([s.out["status"].cpu().numpy().reshape(-1, 4) for s in self.sessions], axis=0)
