@@ -195,6 +195,62 @@ __device__ __forceinline__ double jonswap(double w, double Hs, double Tp, double
     return 0.5 / CUDART_PI * C * 0.3125 * Hs * Hs * fpOvrf4 / f * exp(-1.25 * fpOvrf4) * pow(Gamma, Alpha);
 }
 
+// wave amplitude of one case at one frequency: explicit table or spectrum -> zeta = sqrt(2 S dw) (raft_fowt.py:1759-1774)
+__device__ __forceinline__ double sea_state_zeta(const CasesDev &Cs, int c, int i, int nw, double w, double dw)
+{
+    if (Cs.zeta_in) return Cs.zeta_in[(size_t)c * nw + i];
+    const int spec = Cs.spec[c];
+    double S;
+    if (spec == RAFTK_SPEC_JONSWAP) S = jonswap(w, Cs.Hs[c], Cs.Tp[c], Cs.gamma[c]);
+    else if (spec == RAFTK_SPEC_UNIT) S = 1.0;
+    else if (spec == RAFTK_SPEC_CONSTANT) S = Cs.Hs[c];
+    else S = 0.0;
+    return sqrt(2.0 * S * dw);
+}
+
+// BEM excitation of design d at frequency i for heading beta: bracket the heading in the (heading-relative)
+// coefficient table with wrap-around, interpolate, rotate back to the global frame, scale by the wave amplitude
+// and the array phase offset (raft_fowt.py:1796-1849).  Br/Bi receive the 6 complex force components.
+__device__ __forceinline__ void bem_excitation(const DesignsDev &D, int d, int i, double k, double beta, double sb, double cb,
+                                               double zeta, double (&Br)[6], double (&Bi)[6])
+{
+    const int nhs = D.n_bem_head, nw = D.nw;
+    const double *hd = D.bem_headings;
+    const double xr = D.bem_xyh[3 * d], yr = D.bem_xyh[3 * d + 1], hadj = D.bem_xyh[3 * d + 2];
+    double bdeg = fmod(beta * (180.0 / CUDART_PI) - hadj, 360.0);
+    if (bdeg < 0) bdeg += 360.0;                                   // python's % is non-negative
+    int i1 = 0, i2 = 0; double f2 = 0;
+    if (bdeg <= hd[0]) {
+        const double hlast = hd[nhs - 1] - 360.0;
+        i1 = nhs - 1; i2 = 0; f2 = (bdeg - hlast) / (hd[0] - hlast);
+    } else if (bdeg >= hd[nhs - 1]) {
+        const double hfirst = hd[0] + 360.0;
+        i1 = nhs - 1; i2 = 0; f2 = (bdeg - hd[nhs - 1]) / (hfirst - hd[nhs - 1]);
+    } else {
+        for (int t = 0; t < nhs - 1; t++) if (hd[t + 1] > bdeg) { i1 = t; i2 = t + 1; f2 = (bdeg - hd[t]) / (hd[t + 1] - hd[t]); break; }
+    }
+    const double f1 = 1.0 - f2;
+    const double2 *X = reinterpret_cast<const double2 *>(D.X_BEM) + (size_t)d * nhs * 6 * nw;
+    double Xr[6], Xi_[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+        const double2 x1 = X[((size_t)i1 * 6 + a) * nw + i], x2 = X[((size_t)i2 * 6 + a) * nw + i];
+        Xr[a] = x1.x * f1 + x2.x * f2; Xi_[a] = x1.y * f1 + x2.y * f2;
+    }
+    double Rr[6], Ri[6];
+    Rr[0] = Xr[0] * cb - Xr[1] * sb; Ri[0] = Xi_[0] * cb - Xi_[1] * sb;
+    Rr[1] = Xr[0] * sb + Xr[1] * cb; Ri[1] = Xi_[0] * sb + Xi_[1] * cb;
+    Rr[2] = Xr[2];                   Ri[2] = Xi_[2];
+    Rr[3] = Xr[3] * cb - Xr[4] * sb; Ri[3] = Xi_[3] * cb - Xi_[4] * sb;
+    Rr[4] = Xr[3] * sb + Xr[4] * cb; Ri[4] = Xi_[3] * sb + Xi_[4] * cb;
+    Rr[5] = Xr[5];                   Ri[5] = Xi_[5];
+    double sp, cp;
+    sincos(-(k * (xr * cb + yr * sb)), &sp, &cp);
+    const double pr = zeta * cp, pi = zeta * sp;
+#pragma unroll
+    for (int a = 0; a < 6; a++) { Br[a] = Rr[a] * pr - Ri[a] * pi; Bi[a] = Rr[a] * pi + Ri[a] * pr; }
+}
+
 struct ExcOut { double2 *F_iner, *F_BEM; double *zeta; };
 
 __global__ void __launch_bounds__(128) k_excitation(DesignsDev D, CasesDev Cs, Work W, ExcOut O)
@@ -205,18 +261,7 @@ __global__ void __launch_bounds__(128) k_excitation(DesignsDev D, CasesDev Cs, W
     const int nw = D.nw;
     const double w = D.w[i], k = D.k[i];
 
-    // sea state -> amplitude (raft_fowt.py:1759-1774)
-    double zeta;
-    if (Cs.zeta_in) zeta = Cs.zeta_in[(size_t)c * nw + i];
-    else {
-        const int spec = Cs.spec[c];
-        double S;
-        if (spec == RAFTK_SPEC_JONSWAP) S = jonswap(w, Cs.Hs[c], Cs.Tp[c], Cs.gamma[c]);
-        else if (spec == RAFTK_SPEC_UNIT) S = 1.0;
-        else if (spec == RAFTK_SPEC_CONSTANT) S = Cs.Hs[c];
-        else S = 0.0;
-        zeta = sqrt(2.0 * S * D.dw);
-    }
+    const double zeta = sea_state_zeta(Cs, c, i, nw, w, D.dw);
     if (dl == 0) {
         W.zeta[(size_t)c * nw + i] = zeta;
         if (O.zeta && W.d0 == 0) O.zeta[(size_t)c * nw + i] = zeta;
@@ -292,43 +337,8 @@ __global__ void __launch_bounds__(128) k_excitation(DesignsDev D, CasesDev Cs, W
     if (O.F_iner)
         for (int a = 0; a < 6; a++) O.F_iner[ogl + (size_t)a * nw + i] = make_double2(Fr[a], Fi[a]);
 
-    // BEM excitation with heading interpolation (raft_fowt.py:1796-1849)
     double Br[6] = {0, 0, 0, 0, 0, 0}, Bi[6] = {0, 0, 0, 0, 0, 0};
-    if (D.n_bem_head > 0) {
-        const int nhs = D.n_bem_head;
-        const double *hd = D.bem_headings;
-        const double xr = D.bem_xyh[3 * d], yr = D.bem_xyh[3 * d + 1], hadj = D.bem_xyh[3 * d + 2];
-        double bdeg = fmod(beta * (180.0 / CUDART_PI) - hadj, 360.0);
-        if (bdeg < 0) bdeg += 360.0;
-        int i1 = 0, i2 = 0; double f2 = 0;
-        if (bdeg <= hd[0]) {
-            const double hlast = hd[nhs - 1] - 360.0;
-            i1 = nhs - 1; i2 = 0; f2 = (bdeg - hlast) / (hd[0] - hlast);
-        } else if (bdeg >= hd[nhs - 1]) {
-            const double hfirst = hd[0] + 360.0;
-            i1 = nhs - 1; i2 = 0; f2 = (bdeg - hd[nhs - 1]) / (hfirst - hd[nhs - 1]);
-        } else {
-            for (int t = 0; t < nhs - 1; t++) if (hd[t + 1] > bdeg) { i1 = t; i2 = t + 1; f2 = (bdeg - hd[t]) / (hd[t + 1] - hd[t]); break; }
-        }
-        const double f1 = 1.0 - f2;
-        const double2 *X = reinterpret_cast<const double2 *>(D.X_BEM) + (size_t)d * nhs * 6 * nw;
-        double Xr[6], Xi_[6];
-        for (int a = 0; a < 6; a++) {
-            const double2 x1 = X[((size_t)i1 * 6 + a) * nw + i], x2 = X[((size_t)i2 * 6 + a) * nw + i];
-            Xr[a] = x1.x * f1 + x2.x * f2; Xi_[a] = x1.y * f1 + x2.y * f2;
-        }
-        double Rr[6], Ri[6];
-        Rr[0] = Xr[0] * cb - Xr[1] * sb; Ri[0] = Xi_[0] * cb - Xi_[1] * sb;
-        Rr[1] = Xr[0] * sb + Xr[1] * cb; Ri[1] = Xi_[0] * sb + Xi_[1] * cb;
-        Rr[2] = Xr[2];                   Ri[2] = Xi_[2];
-        Rr[3] = Xr[3] * cb - Xr[4] * sb; Ri[3] = Xi_[3] * cb - Xi_[4] * sb;
-        Rr[4] = Xr[3] * sb + Xr[4] * cb; Ri[4] = Xi_[3] * sb + Xi_[4] * cb;
-        Rr[5] = Xr[5];                   Ri[5] = Xi_[5];
-        double sp, cp;
-        sincos(-(k * (xr * cb + yr * sb)), &sp, &cp);
-        const double pr = zeta * cp, pi = zeta * sp;
-        for (int a = 0; a < 6; a++) { Br[a] = Rr[a] * pr - Ri[a] * pi; Bi[a] = Rr[a] * pi + Ri[a] * pr; }
-    }
+    if (D.n_bem_head > 0) bem_excitation(D, d, i, k, beta, sb, cb, zeta, Br, Bi);
     if (O.F_BEM)
         for (int a = 0; a < 6; a++) O.F_BEM[ogl + (size_t)a * nw + i] = make_double2(Br[a], Bi[a]);
     double2 *F0 = W.F0 + unit * 6 * nw;
@@ -1000,17 +1010,7 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
     for (int t = tid; t < nloc && !plan_overflow; t += T) {
         const int i = f_begin + t;
         const double w = D.w[i], k = D.k[i];
-        double zeta;
-        if (Cs.zeta_in) zeta = Cs.zeta_in[(size_t)c * nw + i];
-        else {
-            const int spec = Cs.spec[c];
-            double Sw;
-            if (spec == RAFTK_SPEC_JONSWAP) Sw = jonswap(w, Cs.Hs[c], Cs.Tp[c], Cs.gamma[c]);
-            else if (spec == RAFTK_SPEC_UNIT) Sw = 1.0;
-            else if (spec == RAFTK_SPEC_CONSTANT) Sw = Cs.Hs[c];
-            else Sw = 0.0;
-            zeta = sqrt(2.0 * Sw * D.dw);
-        }
+        const double zeta = sea_state_zeta(Cs, c, i, nw, w, D.dw);
         if (P.zeta_out && d == 0) P.zeta_out[(size_t)c * nw + i] = zeta;
         const double zw = zeta * w;
         const bool deep = k * D.depth > 89.4;
@@ -1089,36 +1089,12 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         if (P.Finer_out)
             for (int a = 0; a < 6; a++) P.Finer_out[ogl + (size_t)a * nw + i] = make_double2(Fr[a], Fi[a]);
         if (D.n_bem_head > 0) {
-            const int nhs = D.n_bem_head;
-            const double *hd = D.bem_headings;
-            const double xr = D.bem_xyh[3 * d], yr = D.bem_xyh[3 * d + 1], hadj = D.bem_xyh[3 * d + 2];
-            double bdeg = fmod(beta * (180.0 / CUDART_PI) - hadj, 360.0);
-            if (bdeg < 0) bdeg += 360.0;
-            int i1 = 0, i2 = 0; double f2 = 0;
-            if (bdeg <= hd[0]) { const double hlast = hd[nhs - 1] - 360.0; i1 = nhs - 1; i2 = 0; f2 = (bdeg - hlast) / (hd[0] - hlast); }
-            else if (bdeg >= hd[nhs - 1]) { const double hfirst = hd[0] + 360.0; i1 = nhs - 1; i2 = 0; f2 = (bdeg - hd[nhs - 1]) / (hfirst - hd[nhs - 1]); }
-            else { for (int x = 0; x < nhs - 1; x++) if (hd[x + 1] > bdeg) { i1 = x; i2 = x + 1; f2 = (bdeg - hd[x]) / (hd[x + 1] - hd[x]); break; } }
-            const double f1 = 1.0 - f2;
-            const double2 *X = reinterpret_cast<const double2 *>(D.X_BEM) + (size_t)d * nhs * 6 * nw;
-            double Xr[6], Xi_[6];
+            double Br[6], Bi[6];
+            bem_excitation(D, d, i, k, beta, sb, cb, zeta, Br, Bi);
+#pragma unroll
             for (int a = 0; a < 6; a++) {
-                const double2 x1 = X[((size_t)i1 * 6 + a) * nw + i], x2 = X[((size_t)i2 * 6 + a) * nw + i];
-                Xr[a] = x1.x * f1 + x2.x * f2; Xi_[a] = x1.y * f1 + x2.y * f2;
-            }
-            double Rr[6], Ri[6];
-            Rr[0] = Xr[0] * cb - Xr[1] * sb; Ri[0] = Xi_[0] * cb - Xi_[1] * sb;
-            Rr[1] = Xr[0] * sb + Xr[1] * cb; Ri[1] = Xi_[0] * sb + Xi_[1] * cb;
-            Rr[2] = Xr[2];                   Ri[2] = Xi_[2];
-            Rr[3] = Xr[3] * cb - Xr[4] * sb; Ri[3] = Xi_[3] * cb - Xi_[4] * sb;
-            Rr[4] = Xr[3] * sb + Xr[4] * cb; Ri[4] = Xi_[3] * sb + Xi_[4] * cb;
-            Rr[5] = Xr[5];                   Ri[5] = Xi_[5];
-            double sp, cp;
-            sincos(-(k * (xr * cb + yr * sb)), &sp, &cp);
-            const double pr = zeta * cp, pi = zeta * sp;
-            for (int a = 0; a < 6; a++) {
-                const double br_ = Rr[a] * pr - Ri[a] * pi, bi_ = Rr[a] * pi + Ri[a] * pr;
-                if (P.Fbem_out) P.Fbem_out[ogl + (size_t)a * nw + i] = make_double2(br_, bi_);
-                Fr[a] += br_; Fi[a] += bi_;
+                if (P.Fbem_out) P.Fbem_out[ogl + (size_t)a * nw + i] = make_double2(Br[a], Bi[a]);
+                Fr[a] += Br[a]; Fi[a] += Bi[a];
             }
         } else if (P.Fbem_out) {
             for (int a = 0; a < 6; a++) P.Fbem_out[ogl + (size_t)a * nw + i] = make_double2(0.0, 0.0);
