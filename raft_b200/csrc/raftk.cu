@@ -762,7 +762,9 @@ k_drag_solve(DesignsDev D, CasesDev Cs, Work W, SolveParams P)
 
         // ---- all-reduce of (converged, flags) over the CTA and the cluster ----
         int conv_all = __syncthreads_and(conv_local);
-        int nan_all = __syncthreads_or(nan_local);
+        // __syncthreads_or returns a boolean, so reduce the two flag bits separately
+        int nan_all = (__syncthreads_or(nan_local & RAFTK_FLAG_NAN) ? RAFTK_FLAG_NAN : 0)
+                      | (__syncthreads_or(nan_local & RAFTK_FLAG_SINGULAR) ? RAFTK_FLAG_SINGULAR : 0);
         if (CS > 1) {
             if (tid == 0) { S.sums[par * sums_stride + nchunk * 32] = (double)conv_all; S.sums[par * sums_stride + nchunk * 32 + 1] = (double)nan_all; }
             cluster.sync();
@@ -1368,7 +1370,9 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         }
         passes++;
         int conv_all = __syncthreads_and(conv_local);
-        int nan_all = __syncthreads_or(nan_local);
+        // __syncthreads_or returns a boolean, so reduce the two flag bits separately
+        int nan_all = (__syncthreads_or(nan_local & RAFTK_FLAG_NAN) ? RAFTK_FLAG_NAN : 0)
+                      | (__syncthreads_or(nan_local & RAFTK_FLAG_SINGULAR) ? RAFTK_FLAG_SINGULAR : 0);
         if (CS > 1) {
             if (tid == 0) { S.sums[par * sums_stride + nchunk * 32] = (double)conv_all; S.sums[par * sums_stride + nchunk * 32 + 1] = (double)nan_all; }
             cluster.sync();
