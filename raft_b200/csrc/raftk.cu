@@ -823,11 +823,11 @@ struct FSmem {
 
 __host__ __device__ inline size_t fused_smem_bytes(int Nm, int NsP, int nchunk, int nwarps, int nwl, int maxW, int maxH, int maxZ, bool f0_smem)
 {
-    size_t dbl = (size_t)Nm * MEM_STRIDE + 4 * (size_t)NsP + NCOEF * (size_t)NsP + (size_t)Nm * 8 + 108
+    size_t dbl = (size_t)Nm * MEM_STRIDE + 4 * (size_t)NsP + 16 + NCOEF * (size_t)NsP + (size_t)Nm * 8 + 108
                  + (size_t)nchunk * nwarps * 32 + 2 * ((size_t)nchunk * 32 + 2) + (size_t)nchunk * 32 + (size_t)nwarps * 16 * 33
                  + (12 + (f0_smem ? 12 : 0) + 4) * (size_t)nwl + 2 * (size_t)maxW + (size_t)maxH + (size_t)maxZ + 3 * (size_t)NsP
-                 + 2 * ((size_t)Nm + maxZ + maxW + maxH) * nwl;
-    size_t ints = (size_t)Nm * IMEM_STRIDE + 4 * (size_t)NsP + 8;
+                 + 2 * ((size_t)Nm + maxZ + (maxW + 1) + (maxH + 1)) * nwl;       // +1: identity rows of the factor tables
+    size_t ints = (size_t)Nm * IMEM_STRIDE + 4 * (size_t)NsP + 40;
     return dbl * sizeof(double) + ints * sizeof(int) + 32;
 }
 
@@ -875,10 +875,10 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         double *p = smem_raw;
         S.ebase = reinterpret_cast<double2 *>(p); p += 2 * (size_t)NmP * nwl;
         S.abase = reinterpret_cast<double2 *>(p); p += 2 * (size_t)P.maxZ * nwl;
-        S.wtab = reinterpret_cast<double2 *>(p); p += 2 * (size_t)P.maxW * nwl;
-        S.htab = reinterpret_cast<double2 *>(p); p += 2 * (size_t)P.maxH * nwl;
+        S.wtab = reinterpret_cast<double2 *>(p); p += 2 * (size_t)(P.maxW + 1) * nwl;
+        S.htab = reinterpret_cast<double2 *>(p); p += 2 * (size_t)(P.maxH + 1) * nwl;
         S.mem = p; p += (size_t)NmP * MEM_STRIDE;
-        S.node = p; p += 4 * (size_t)NsP;
+        S.node = p; p += 4 * (size_t)NsP + 16;
         S.coef = p; p += NCOEF * (size_t)NsP;
         S.msum = p; p += (size_t)NmP * 8;
         S.mat = p; p += 108;
@@ -894,9 +894,9 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         S.scr = p; p += 3 * (size_t)NsP;
         S.trans = p; p += (size_t)nwarps * 16 * 33;
         S.imem = reinterpret_cast<int *>(p);
-        S.node_w = S.imem + (size_t)NmP * IMEM_STRIDE;
-        S.node_h = S.node_w + NsP;
-        S.iscr = S.node_h + NsP;            // 2*NsP ints
+        S.node_w = S.imem + (size_t)NmP * IMEM_STRIDE;     // per node: offset (class * nwl) of its step factors,
+        S.node_h = S.node_w + NsP + 12;                     // identity row for a member's first node / zero steps
+        S.iscr = S.node_h + NsP + 12;       // 2*NsP ints   (+12: the node loop prefetches up to 10 entries ahead)
         S.cnt = S.iscr + 2 * NsP;
     }
     const int sums_stride = nchunk * 32 + 2;
@@ -985,8 +985,10 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         if (hi >= P.maxH) { hi = 0; S.cnt[2] = 1; }
         if (rw == j && wi >= 0 && S.cnt[2] == 0) { S.wkey[2 * wi] = S.scr[j]; S.wkey[2 * wi + 1] = S.scr[NsP + j]; atomicMax(&S.cnt[0], wi + 1); }
         if (rh == j && hi >= 0 && S.cnt[2] == 0) { S.hkey[hi] = S.scr[2 * NsP + j]; atomicMax(&S.cnt[1], hi + 1); }
-        S.node_w[j] = wi; S.node_h[j] = hi;
+        S.node_w[j] = (wi >= 0 ? wi : P.maxW) * nwl;        // identity row when the phase / depth does not change
+        S.node_h[j] = (hi >= 0 ? hi : P.maxH) * nwl;
     }
+    for (int j = Ns + tid; j < NsP + 12; j += T) { S.node_w[j] = P.maxW * nwl; S.node_h[j] = P.maxH * nwl; }   // prefetch padding
     // z classes of the members' first nodes
     for (int m = tid; m < Nm; m += T) {
         const double z0 = S.mem[m * MEM_STRIDE + 21];
@@ -1026,6 +1028,8 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
             const double a = k * S.hkey[x];
             S.htab[x * nwl + t] = make_double2(exp(a), exp(-a));
         }
+        S.wtab[P.maxW * nwl + t] = make_double2(1.0, 0.0);
+        S.htab[P.maxH * nwl + t] = make_double2(1.0, 1.0);
         for (int x = 0; x < nZ; x++) {
             double S_, C_, P_;
             depth_funcs(k, D.depth, S.zkey[x], S_, C_, P_);
@@ -1048,10 +1052,10 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
             const double hq = o[18], h1 = o[19], h2 = o[20];
             double Aqr = 0, Aqi = 0, A1r = 0, A1i = 0, A2r = 0, A2i = 0, L1r = 0, L1i = 0, L2r = 0, L2i = 0;
             for (int j = j0; j < j1; j++) {
-                if (j > j0) {
-                    const int wi = S.node_w[j], hi = S.node_h[j];
-                    if (wi >= 0) { const double2 W = S.wtab[wi * nwl + t]; const double tr = fma(er, W.x, -ei * W.y); ei = fma(er, W.y, ei * W.x); er = tr; }
-                    if (hi >= 0) { const double2 H = S.htab[hi * nwl + t]; ap *= H.x; am *= H.y; }
+                {   // step factors (identity at the member's first node)
+                    const double2 W = S.wtab[S.node_w[j] + t], H = S.htab[S.node_h[j] + t];
+                    const double tr = fma(er, W.x, -ei * W.y); ei = fma(er, W.y, ei * W.x); er = tr;
+                    ap *= H.x; am *= H.y;
                 }
                 const int jg = nbase + j;
                 const double inq = D.node_in_q[jg], pa = D.node_pa[jg];
@@ -1130,6 +1134,7 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
                     for (int a = 0; a < 6; a++) { xr[a] = S.xi[(2 * a) * nwl + t]; xi[a] = S.xi[(2 * a + 1) * nwl + t]; }
                     // walking state: restored from the checkpoint when the chunk starts inside a member
                     double er = S.ckpt[t], ei = S.ckpt[nwl + t], ap = S.ckpt[2 * nwl + t], am = S.ckpt[3 * nwl + t];
+                    const double2 *wt_ = S.wtab + t, *ht_ = S.htab + t;
                     int mcur = -1, jj = 0;
                     while (jj < CHUNK_NODES && jc0 + jj < Ns) {
                         // (uniform) member entry: member-level projections of the body velocity, -i w (d . Xi_t + (a x d) . Xi_r)
@@ -1159,15 +1164,16 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
                             const double2 e0 = S.ebase[mcur * nwl + t], a0 = S.abase[S.imem[IMEM_STRIDE * mcur + 4] * nwl + t];
                             er = e0.x; ei = e0.y; ap = a0.x; am = a0.y;
                         }
-#define P1_NODE(JJ)                                                                                                  \
+                        // node body: branch-free; the step factors / ls of node JJ were loaded one node earlier
+                        // (CUR set) and those of node JJ+1 are requested first (NXT set), so the shared-memory
+                        // latency overlaps the arithmetic of this node.  Sets alternate with the parity of JJ.
+#define P1_NODE(JJ, CW, CH, CL, NW, NH, NL)                                                                        \
     {                                                                                                                \
-        const int j = jc0 + JJ;                                                                                      \
-        if (j != mstart) {                                                                                           \
-            const int wi = S.node_w[j], hi = S.node_h[j];                                                            \
-            if (wi >= 0) { const double2 W = S.wtab[wi * nwl + t]; const double tr = fma(er, W.x, -ei * W.y); ei = fma(er, W.y, ei * W.x); er = tr; } \
-            if (hi >= 0) { const double2 H = S.htab[hi * nwl + t]; ap *= H.x; am *= H.y; }                  \
-        }                                                                                                            \
-        const double ls = S.node[j], Cc = ap + am, Sc = ap - am;                                                     \
+        const int jn = jc0 + JJ + 1;                                                                                 \
+        NW = wt_[S.node_w[jn]]; NH = ht_[S.node_h[jn]]; NL = S.node[jn];                                             \
+        { const double tr = fma(er, CW.x, -ei * CW.y); ei = fma(er, CW.y, ei * CW.x); er = tr; }                     \
+        ap *= CH.x; am *= CH.y;                                                                                      \
+        const double ls = CL, Cc = ap + am, Sc = ap - am;                                                            \
         double ar_, ai_;                                                                                             \
         proj_add(kq, er, ei, Cc, Sc, hq, dzq, mqr, mqi, ar_, ai_);                                                   \
         acc[3 * JJ + 0] = fma(ar_, ar_, fma(ai_, ai_, acc[3 * JJ + 0]));                                             \
@@ -1177,17 +1183,20 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         acc[3 * JJ + 2] = fma(ar_, ar_, fma(ai_, ai_, acc[3 * JJ + 2]));                                             \
     }
                         // Duff-style dispatch: one copy of each node body (static accumulator index), re-entered per member
+                        double2 Wa, Ha, Wb, Hb; double La, Lb;
+                        if (jj & 1) { Wb = wt_[S.node_w[jfirst]]; Hb = ht_[S.node_h[jfirst]]; Lb = S.node[jfirst]; Wa = Wb; Ha = Hb; La = Lb; }
+                        else        { Wa = wt_[S.node_w[jfirst]]; Ha = ht_[S.node_h[jfirst]]; La = S.node[jfirst]; Wb = Wa; Hb = Ha; Lb = La; }
                         switch (jj) {
-                        case 0: P1_NODE(0); jj = 1; if (jlast <= 1) break;
-                        case 1: P1_NODE(1); jj = 2; if (jlast <= 2) break;
-                        case 2: P1_NODE(2); jj = 3; if (jlast <= 3) break;
-                        case 3: P1_NODE(3); jj = 4; if (jlast <= 4) break;
-                        case 4: P1_NODE(4); jj = 5; if (jlast <= 5) break;
-                        case 5: P1_NODE(5); jj = 6; if (jlast <= 6) break;
-                        case 6: P1_NODE(6); jj = 7; if (jlast <= 7) break;
-                        case 7: P1_NODE(7); jj = 8; if (jlast <= 8) break;
-                        case 8: P1_NODE(8); jj = 9; if (jlast <= 9) break;
-                        case 9: P1_NODE(9); jj = 10;
+                        case 0: P1_NODE(0, Wa, Ha, La, Wb, Hb, Lb); jj = 1; if (jlast <= 1) break;
+                        case 1: P1_NODE(1, Wb, Hb, Lb, Wa, Ha, La); jj = 2; if (jlast <= 2) break;
+                        case 2: P1_NODE(2, Wa, Ha, La, Wb, Hb, Lb); jj = 3; if (jlast <= 3) break;
+                        case 3: P1_NODE(3, Wb, Hb, Lb, Wa, Ha, La); jj = 4; if (jlast <= 4) break;
+                        case 4: P1_NODE(4, Wa, Ha, La, Wb, Hb, Lb); jj = 5; if (jlast <= 5) break;
+                        case 5: P1_NODE(5, Wb, Hb, Lb, Wa, Ha, La); jj = 6; if (jlast <= 6) break;
+                        case 6: P1_NODE(6, Wa, Ha, La, Wb, Hb, Lb); jj = 7; if (jlast <= 7) break;
+                        case 7: P1_NODE(7, Wb, Hb, Lb, Wa, Ha, La); jj = 8; if (jlast <= 8) break;
+                        case 8: P1_NODE(8, Wa, Ha, La, Wb, Hb, Lb); jj = 9; if (jlast <= 9) break;
+                        case 9: P1_NODE(9, Wb, Hb, Lb, Wa, Ha, La); jj = 10;
                         }
 #undef P1_NODE
                     }
@@ -1287,6 +1296,7 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         for (int t = tid; t < nloc; t += T) {
             const int i = f_begin + t;
             const double w = D.w[i];
+            const double2 *wt_ = S.wtab + t, *ht_ = S.htab + t;
             double br[6], bi[6];
 #pragma unroll
             for (int a = 0; a < 6; a++) { br[a] = 0.0; bi[a] = 0.0; }
@@ -1299,10 +1309,10 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
                 const double2 e0 = S.ebase[m * nwl + t], a0 = S.abase[S.imem[IMEM_STRIDE * m + 4] * nwl + t];
                 double er = e0.x, ei = e0.y, ap = a0.x, am = a0.y;
                 for (int j = j0; j < j1; j++) {
-                    if (j > j0) {
-                        const int wi = S.node_w[j], hi = S.node_h[j];
-                        if (wi >= 0) { const double2 W = S.wtab[wi * nwl + t]; const double tr = fma(er, W.x, -ei * W.y); ei = fma(er, W.y, ei * W.x); er = tr; }
-                        if (hi >= 0) { const double2 H = S.htab[hi * nwl + t]; ap *= H.x; am *= H.y; }
+                    {
+                        const double2 W = wt_[S.node_w[j]], H = ht_[S.node_h[j]];
+                        const double tr = fma(er, W.x, -ei * W.y); ei = fma(er, W.y, ei * W.x); er = tr;
+                        ap *= H.x; am *= H.y;
                     }
                     const double bq = cq_[j], b1 = c1_[j], lb1 = cl1_[j], b2 = c2_[j], lb2 = cl2_[j];
                     const double Cc = ap + am, Sc = ap - am;
