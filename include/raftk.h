@@ -113,6 +113,11 @@ typedef struct raftk_cases {
     const double *beta_deg;  /* [nC] wave_heading [deg]                                         */
     const int32_t *spec;     /* [nC] RAFTK_SPEC_*                                               */
     const double *zeta;      /* optional [nC,nw] explicit amplitudes (overrides spec) or NULL   */
+    const int32_t *primary;  /* optional [nC]: wave trains of one RAFT case (raft_fowt.py:1742-1752).  primary[c] == c:
+                                the case drives its own drag linearisation; primary[c] = p != c: secondary train --
+                                its response uses the impedance and per-node drag coefficients of case p
+                                (raft_model.py:1200-1236; p must be a primary).  NULL: all cases independent.
+                                Only raftk_solve_dynamics_*; needs raftk_solve_workspace_bytes() of workspace. */
 } raftk_cases;
 
 /* Fixed-point loop controls (raft_model.py:966 tol, :977 nIter, :978 XiStart, :1133 relaxation) */

@@ -197,6 +197,20 @@ def solve_dynamics(od, spec, Hs, Tp, gamma, beta_deg, nIter=10, tol=0.01, XiStar
     return (Xi, st, Z, Bd) if want_Z else (Xi, st)
 
 
+def solve_dynamics_trains(od, spec, Hs, Tp, gamma, beta_deg, nIter=10, tol=0.01, XiStart=0.0):
+    """Model.solveDynamics for one case with several wave trains -> Xi[nH,6,nw], status (train 0 drives the linearisation)."""
+    spec = np.ascontiguousarray(spec, dtype=np.int32)
+    Hs, Tp, gamma, beta_deg = (np.ascontiguousarray(x, dtype=np.float64) for x in (Hs, Tp, gamma, beta_deg))
+    nH = len(spec)
+    Xi = np.zeros([nH, 6, od.nw], dtype=np.complex128)
+    st = np.zeros(3, dtype=np.int32)
+    rc = lib().ro_solve_dynamics_trains(C.byref(od.c), C.c_int(nH), _ip(spec), _dp(Hs), _dp(Tp), _dp(gamma), _dp(beta_deg),
+                                        C.c_int(nIter), C.c_double(tol), C.c_double(XiStart), Xi.ctypes.data_as(C.c_void_p), _ip(st))
+    if rc:
+        raise ValueError("Wave spectrum input not recognized.")
+    return Xi, st
+
+
 def solve_cases(od, cases, nIter=10, tol=0.01, XiStart=0.0, nthreads=0):
     """Batched over a packed case table (raft_b200.packer.pack_cases) -> Xi[nC,6,nw], status[nC,3], threads."""
     nC = len(cases["Hs"])

@@ -511,6 +511,103 @@ done:
     return rc;
 }
 
+/* raft_member.py:2128-2152 + raft_fowt.py:1940-1957: drag excitation of one wave train with the Bmat left
+ * behind by the last calcHydroLinearization.  u [Ns][3][nw], Bmat [Ns][3][3] -> F_drag [6][nw]. */
+static void drag_excitation(const ro_design *d, const cplx *u_all, const double *Bmat_all, cplx *F_drag)
+{
+    int nw = d->nw, Ns = d->n_nodes, Nm = d->n_members;
+    cplx *Fm = malloc(sizeof(cplx) * 6 * nw);
+    for (int i = 0; i < 6 * nw; i++) F_drag[i] = 0;
+    for (int m = 0; m < Nm; m++) {
+        const double *rn = d->mem_rA + 3 * m;
+        double dd[3] = { rn[0] - d->prp[0], rn[1] - d->prp[1], rn[2] - d->prp[2] }, T[6][6];
+        node_T(dd, T);
+        for (int i = 0; i < 6 * nw; i++) Fm[i] = 0;
+        for (int il = 0; il < Ns; il++) {
+            if (d->node_mem[il] != m) continue;
+            const double *r = d->node_r + 3 * il, *B = Bmat_all + 9 * il;
+            const cplx *u = u_all + (size_t)il * 3 * nw;
+            double rr[3] = { r[0] - rn[0], r[1] - rn[1], r[2] - rn[2] };
+            for (int i = 0; i < nw; i++) {
+                cplx f[3], f6[6];
+                for (int a = 0; a < 3; a++) f[a] = B[3 * a] * u[i] + B[3 * a + 1] * u[nw + i] + B[3 * a + 2] * u[2 * nw + i];
+                translate_force(f, rr, f6);
+                for (int a = 0; a < 6; a++) Fm[a * nw + i] += f6[a];
+            }
+        }
+        for (int i = 0; i < nw; i++)
+            for (int a = 0; a < 6; a++) {
+                cplx s = 0;
+                for (int b = 0; b < 6; b++) s += T[b][a] * Fm[b * nw + i];
+                F_drag[a * nw + i] += s;
+            }
+    }
+    free(Fm);
+}
+
+/* Model.solveDynamics for a case with nH wave trains (raft_fowt.py:1742-1752 lists; raft_model.py:1200-1236):
+ * the drag linearisation iterates on train 0 only (raft_fowt.py:1910); every train's response is then
+ * inv(Z_last) (F_BEM[ih] + F_iner[ih] + F_drag(Bmat_last, u[ih])).  Xi_out [nH][6][nw]. */
+int ro_solve_dynamics_trains(const ro_design *d, int nH, const int *spec, const double *Hs, const double *Tp,
+                             const double *gamma, const double *beta_deg, int nIter, double tol, double XiStart,
+                             cplx *Xi_out, int *status)
+{
+    int nw = d->nw, Ns = d->n_nodes > 0 ? d->n_nodes : 1;
+    cplx *Z = malloc(sizeof(cplx) * 36 * (size_t)nw);
+    double Bd[36];
+    int rc = ro_solve_dynamics(d, spec[0], Hs[0], Tp[0], gamma[0], beta_deg[0], nIter, tol, XiStart, Xi_out, status, Z, Bd);
+    if (rc || nH == 1) { free(Z); return rc; }
+    /* recover Bmat of the last pass: one more linearisation with the XiLast that produced Z is not available here, so
+       redo the loop bookkeeping explicitly: run the loop again keeping Bmat (cheap; this is test infrastructure) */
+    double *zeta = malloc(sizeof(double) * nw), *Bmat = malloc(sizeof(double) * 9 * Ns);
+    cplx *F_BEM = malloc(sizeof(cplx) * 6 * nw), *F_iner = malloc(sizeof(cplx) * 6 * nw), *u = malloc(sizeof(cplx) * (size_t)Ns * 3 * nw);
+    cplx *XiLast = malloc(sizeof(cplx) * 6 * nw), *Xi = malloc(sizeof(cplx) * 6 * nw), *F_drag = malloc(sizeof(cplx) * 6 * nw);
+    double B_drag[6][6];
+    ro_calc_hydro_excitation(d, spec[0], Hs[0], Tp[0], gamma[0], beta_deg[0], zeta, F_BEM, F_iner, u);
+    for (int i = 0; i < 6 * nw; i++) XiLast[i] = XiStart;
+    for (int iiter = 0; iiter < nIter + 1; iiter++) {
+        hydro_linearization(d, u, XiLast, Bmat, B_drag, F_drag);
+        for (int ii = 0; ii < nw; ii++) {
+            cplx A[36], b[6];
+            double wv = d->w[ii];
+            for (int a = 0; a < 6; a++) {
+                for (int c = 0; c < 6; c++) {
+                    double M = d->M0[6 * a + c], B = d->B0[6 * a + c];
+                    if (d->A_w) M += d->A_w[(size_t)(6 * a + c) * nw + ii];
+                    if (d->B_w) B += d->B_w[(size_t)(6 * a + c) * nw + ii];
+                    B += B_drag[a][c];
+                    A[6 * a + c] = -wv * wv * M + I * wv * B + d->C0[6 * a + c];
+                }
+                b[a] = (F_BEM[a * nw + ii] + F_iner[a * nw + ii]) + F_drag[a * nw + ii];
+            }
+            ro_zgesv(6, A, b);
+            for (int a = 0; a < 6; a++) Xi[a * nw + ii] = b[a];
+        }
+        int all = 1;
+        for (int i = 0; i < 6 * nw; i++) { double tc = cabs(Xi[i] - XiLast[i]) / (cabs(Xi[i]) + tol); if (!(tc < tol)) { all = 0; break; } }
+        if (all) break;
+        for (int i = 0; i < 6 * nw; i++) XiLast[i] = 0.2 * XiLast[i] + 0.8 * Xi[i];
+    }
+    for (int ih = 1; ih < nH; ih++) {
+        rc = ro_calc_hydro_excitation(d, spec[ih], Hs[ih], Tp[ih], gamma[ih], beta_deg[ih], zeta, F_BEM, F_iner, u);
+        if (rc) break;
+        drag_excitation(d, u, Bmat, F_drag);
+        cplx *Xo = Xi_out + (size_t)ih * 6 * nw;
+        for (int ii = 0; ii < nw; ii++) {
+            cplx A[36], Ai[36];
+            memcpy(A, Z + (size_t)ii * 36, sizeof(A));
+            if (ro_zinv(6, A, Ai)) { for (int a = 0; a < 6; a++) Xo[a * nw + ii] = NAN; continue; }
+            for (int a = 0; a < 6; a++) {
+                cplx s = 0;
+                for (int c = 0; c < 6; c++) s += Ai[6 * a + c] * ((F_BEM[c * nw + ii] + F_iner[c * nw + ii]) + F_drag[c * nw + ii]);
+                Xo[a * nw + ii] = s;
+            }
+        }
+    }
+    free(Z); free(zeta); free(Bmat); free(F_BEM); free(F_iner); free(u); free(XiLast); free(Xi); free(F_drag);
+    return rc;
+}
+
 /* Batched driver used for parity sweeps and the CPU baseline: nC cases of one design,
  * OpenMP over cases.  Xi_out [nC][6][nw], status [nC][3].  Returns the thread count used. */
 int ro_solve_cases(const ro_design *d, int nC, const int *spec, const double *Hs, const double *Tp,

@@ -31,7 +31,7 @@ class RaftkCases(C.Structure):
     _fields_ = [
         ("n_cases", C.c_int32), ("_pad0", C.c_int32),
         ("Hs", C.c_void_p), ("Tp", C.c_void_p), ("gamma", C.c_void_p), ("beta_deg", C.c_void_p),
-        ("spec", C.c_void_p), ("zeta", C.c_void_p),
+        ("spec", C.c_void_p), ("zeta", C.c_void_p), ("primary", C.c_void_p),
     ]
 
 

@@ -125,6 +125,7 @@ struct CasesDev {
     int nC;
     const double *Hs, *Tp, *gamma, *beta_deg, *zeta_in;
     const int *spec;
+    const int *primary;     // [nC] or NULL: case whose drag linearisation this case reuses (secondary wave trains)
 };
 
 struct Work {          // workspace views for one chunk of designs [d0, d0+nDc)
@@ -810,6 +811,8 @@ struct FusedParams {
     double *Bdrag_out, *zeta_out;
     int *status;
     double2 *F0g;            // [units][6][nw] linear excitation kept in global memory (frees 96 B/bin of smem), or NULL
+    double *lin_g;           // [units][NCOEF*max_nodes + 36] linearisation hand-over primary -> secondary wave trains, or NULL
+    int phase;               // -1: every case is its own primary; 0: run primaries only; 1: run secondaries only
 };
 
 #define IMEM_STRIDE 6      // ints per member: node start, node end, circular, direction kinds, z-class, spare
@@ -860,6 +863,11 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
     const int d = unit / Cs.nC, c = unit % Cs.nC;
     const int nw = D.nw, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nwarps = T / 32;
+    // wave trains: a secondary train reuses the linearisation (per-node coefficients, B_drag) of its primary case
+    // (raft_model.py:1200-1236); primaries and secondaries run in two launches (cluster-uniform early exit)
+    const int prim = (P.phase >= 0 && Cs.primary) ? Cs.primary[c] : c;
+    const bool secondary = prim != c;
+    if ((P.phase == 0 && secondary) || (P.phase == 1 && !secondary)) return;
 
     const int m0 = D.member_offset[d], Nm = D.member_offset[d + 1] - m0;
     const int nbase = D.mem_node_start[m0];
@@ -1117,9 +1125,17 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
     const double *Aw = D.A_w ? D.A_w + (size_t)d * 36 * nw : nullptr;
     const double *Bw = D.B_w ? D.B_w + (size_t)d * 36 * nw : nullptr;
     int passes = 0, converged = 0, flags = plan_overflow ? RAFTK_FLAG_PLAN : 0, par = 0;
-    const int max_pass = plan_overflow ? 0 : P.n_iter + 1;
+    const int max_pass = plan_overflow ? 0 : (secondary ? 1 : P.n_iter + 1);
+    const size_t lin_stride = (size_t)NCOEF * NsP + 36;
+    if (secondary && !plan_overflow) {          // frozen linearisation of the primary case
+        const double *src = P.lin_g + ((size_t)d * Cs.nC + prim) * lin_stride;
+        for (int t = tid; t < NCOEF * NsP; t += T) S.coef[t] = src[t];
+        for (int t = tid; t < 36; t += T) S.mat[36 + t] = src[NCOEF * NsP + t];
+        __syncthreads();
+    }
 
     for (int it = 0; it < max_pass; it++) {
+        if (!secondary) {
         // ================= pass part 1: sum_w |v_rel . d|^2 per node and direction =================
         for (int ch = 0; ch < nchunk; ch++) {
             double acc[32];
@@ -1289,6 +1305,12 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
             if (P.Bdrag_out && rank == 0) P.Bdrag_out[((size_t)d * Cs.nC + c) * 36 + tid] = s;
         }
         __syncthreads();
+        if (P.lin_g && P.phase == 0 && rank == 0) {      // hand the linearisation over to the secondary wave trains
+            double *dst = P.lin_g + ((size_t)d * Cs.nC + c) * lin_stride;
+            for (int t = tid; t < NCOEF * NsP; t += T) dst[t] = S.coef[t];
+            for (int t = tid; t < 36; t += T) dst[NCOEF * NsP + t] = S.mat[36 + t];
+        }
+        }   // !secondary
 
         // ================= pass part 2: drag excitation, impedance, solve, convergence =============
         int conv_local = 1, nan_local = 0;
@@ -1403,7 +1425,7 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
     }
     if (P.status && rank == 0 && tid == 0) {
         int *st = P.status + ((size_t)d * Cs.nC + c) * 4;
-        st[0] = passes; st[1] = converged; st[2] = flags; st[3] = 0;
+        st[0] = secondary ? 0 : passes; st[1] = secondary ? 1 : converged; st[2] = flags; st[3] = secondary ? prim + 1 : 0;
     }
     if (CS > 1) cluster.sync();
 }
@@ -1542,7 +1564,7 @@ static CasesDev to_dev(const raftk_cases *c)
 {
     CasesDev C;
     C.nC = c->n_cases; C.Hs = c->Hs; C.Tp = c->Tp; C.gamma = c->gamma; C.beta_deg = c->beta_deg;
-    C.zeta_in = c->zeta; C.spec = c->spec;
+    C.zeta_in = c->zeta; C.spec = c->spec; C.primary = c->primary;
     return C;
 }
 
@@ -1691,7 +1713,7 @@ static int fused_launch(const DesignsDev &D, const CasesDev &C, const FusedParam
 }
 
 static int run_fused(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o, const raftk_outputs *out,
-                     const FPlan &pl, void *workspace, cudaStream_t st)
+                     const FPlan &pl, void *workspace, size_t wbytes, cudaStream_t st)
 {
     prof_begin_call();
     DesignsDev D = to_dev(d, d->max_nodes, d->max_members);
@@ -1706,6 +1728,19 @@ static int run_fused(const raftk_designs *d, const raftk_cases *c, const raftk_s
     P.Bdrag_out = out->B_drag; P.zeta_out = out->zeta; P.status = out->status;
     P.F0g = pl.f0_global ? reinterpret_cast<double2 *>(workspace) : nullptr;
     const int units = d->n_designs * c->n_cases;
+    P.lin_g = nullptr; P.phase = -1;
+    if (c->primary) {                                  // wave trains: primaries first, then the trains that follow them
+        const size_t f0b = align_up((size_t)units * 6 * d->nw * sizeof(double2), 256);
+        const size_t need = f0b + (size_t)units * ((size_t)NCOEF * d->max_nodes + 36) * sizeof(double);
+        if (!workspace || wbytes < need) return set_err(RAFTK_ENOMEM, "wave-train cases need raftk_solve_workspace_bytes() of workspace");
+        P.lin_g = reinterpret_cast<double *>(static_cast<char *>(workspace) + f0b);
+        for (int phase = 0; phase < 2; phase++) {
+            P.phase = phase;
+            const int rc = (pl.T == 128) ? fused_launch<128>(D, C, P, pl, units, st) : fused_launch<256>(D, C, P, pl, units, st);
+            if (rc) return rc;
+        }
+        return RAFTK_OK;
+    }
     if (pl.T == 128) return fused_launch<128>(D, C, P, pl, units, st);
     return fused_launch<256>(D, C, P, pl, units, st);
 }
@@ -1720,8 +1755,10 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
     if (mode == 0) {                                   // fused on-chip solver when the slice fits in shared memory
         FPlan fp;
         const bool have_ws = workspace && wbytes >= (size_t)nD * nC * 6 * nw * sizeof(double2);
-        if (fused_plan(d, nD * nC, o ? o->cluster_size : 0, have_ws, fp)) return run_fused(d, c, o, out, fp, workspace, st);
+        if (fused_plan(d, nD * nC, o ? o->cluster_size : 0, have_ws, fp)) return run_fused(d, c, o, out, fp, workspace, wbytes, st);
+        if (c->primary) return set_err(RAFTK_EINVAL, "wave-train cases (cases.primary) need the fused solver; the design's frequency slice does not fit on chip");
     }
+    if (c->primary && mode != 2) return set_err(RAFTK_EINVAL, "cases.primary is only supported by raftk_solve_dynamics_*");
     if (do_excitation) prof_begin_call();
     DesignsDev D = to_dev(d, d->max_nodes, d->max_members);
     CasesDev C = to_dev(c);
@@ -1808,7 +1845,8 @@ extern "C" size_t raftk_solve_workspace_bytes(const raftk_designs *d, int32_t n_
     if (!d || d->n_designs <= 0 || n_cases <= 0) return 0;
     FPlan fp;
     if (d->max_nodes > 0 && d->max_members > 0 && fused_plan(d, d->n_designs * n_cases, 0, true, fp))
-        return align_up((size_t)d->n_designs * n_cases * 6 * d->nw * sizeof(double2), 256);
+        return align_up((size_t)d->n_designs * n_cases * 6 * d->nw * sizeof(double2), 256)
+               + align_up((size_t)d->n_designs * n_cases * ((size_t)NCOEF * d->max_nodes + 36) * sizeof(double), 256);
     return raftk_workspace_bytes(d, n_cases);
 }
 
@@ -1925,7 +1963,7 @@ static size_t in_bytes(const raftk_designs *d, const raftk_cases *c)
     if (d->B_w) add(nD * 36 * nw * 8);
     if (d->n_bem_head > 0) { add((size_t)d->n_bem_head * 8); add(nD * d->n_bem_head * 6 * nw * 16); add(nD * 24); }
     for (int t = 0; t < 4; t++) add(nC * 8);
-    add(nC * 4);
+    add(nC * 4); add(nC * 4);
     if (c->zeta) add(nC * nw * 8);
     return b;
 }
@@ -1946,7 +1984,7 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     if (Xi_in) obytes += align_up(resp, 256);
     size_t wb = raftk_workspace_bytes(d, (int32_t)nC);
     if (mode != 0) wb = chunk_bytes((int)nD, (int)nC, d->max_nodes, (int)nw);   // single chunk required
-    else { FPlan fp; if (fused_plan(d, (int)(nD * nC), o ? o->cluster_size : 0, true, fp)) wb = resp; }
+    else { FPlan fp; if (fused_plan(d, (int)(nD * nC), o ? o->cluster_size : 0, true, fp)) wb = raftk_solve_workspace_bytes(d, (int32_t)nC); }
     const size_t total = SMALL_REGION + in_bytes(d, c) + obytes + align_up(wb, 256) + 4096;
     if (g_arena.reserve(total)) return set_err(RAFTK_ENOMEM, "device arena allocation failed");
     Arena &A = g_arena;
@@ -1978,6 +2016,7 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     cc.Hs = up(A, c->Hs, nC, st, e); cc.Tp = up(A, c->Tp, nC, st, e); cc.gamma = up(A, c->gamma, nC, st, e);
     cc.beta_deg = up(A, c->beta_deg, nC, st, e); cc.spec = up(A, c->spec, nC, st, e);
     cc.zeta = up(A, c->zeta, nC * nw, st, e);
+    cc.primary = up(A, c->primary, c->primary ? nC : 0, st, e);
     const double *Xi_in_d = up(A, Xi_in, Xi_in ? nD * nC * 6 * nw * 2 : 0, st, e);
     {
         cudaError_t r = flush_small(A, st);

@@ -137,6 +137,6 @@ class FOWT:
             raise RuntimeError("calcHydroLinearization must be called first")
         if ih == 0:
             return self.F_hydro_drag
-        # Bmat comes from train 0; the excitation is linear in the wave velocity of train ih:
-        # F_drag(ih) = F_drag computed with train ih's kinematics and train 0's coefficients.
-        raise NotImplementedError("drag excitation of secondary wave trains is not on the B200 path yet")
+        # Bmat comes from train 0 (raft_member.py:2128-2152).  Stand-alone evaluation for a secondary train is not
+        # exposed; Model.solveDynamics handles multi-train cases inside the solver (cases.primary of the C ABI).
+        raise NotImplementedError("use Model.solveDynamics for cases with several wave trains")

@@ -47,8 +47,9 @@ class Model:
     def solveDynamics(self, case, tol=0.01, conv_plot=0, RAO_plot=0, display=0):
         """Response amplitudes for one load case -> self.Xi [nWaves+1, nDOF, nw] (last row zero, as :1195)."""
         out = self._solve_batch([case], tol)
-        Xi = np.zeros([2, self.nDOF, self.nw], dtype=complex)
-        Xi[0] = out["Xi"][0]
+        trains = out["Xi_trains"][0]                                      # [nWaves, nDOF, nw]
+        Xi = np.zeros([len(trains) + 1, self.nDOF, self.nw], dtype=complex)
+        Xi[:-1] = trains
         self.Xi = Xi
         for i, f in enumerate(self.fowtList):
             f.Xi = Xi[:, 6 * i:6 * i + 6, :]
@@ -66,6 +67,7 @@ class Model:
         out = self._solve_batch(cases, tol)
         self.results["freq_rad"] = self.w
         self.results["Xi"] = out["Xi"]
+        self.results["Xi_trains"] = out["Xi_trains"]
         self.results["status"] = out["status"]
         # response statistics per case and FOWT (raft_fowt.py:2299-2353; zero mean offsets: statics are out of scope)
         nC = len(cases)
@@ -86,12 +88,15 @@ class Model:
         return self.results
 
     def _solve_batch(self, cases, tol):
-        ct = solver.CaseTable(packer.pack_cases(cases))
-        nC = ct.n_cases
+        table, owner, first = packer.pack_case_trains(cases)
+        ct = solver.CaseTable(table)
+        nC = len(cases)
         batch = solver.DesignBatch([f.pack() for f in self.fowtList])
         want = ("Xi", "status", "B_drag", "F_drag", "F_iner", "F_BEM", "zeta")
         o = solver.solve_dynamics(batch, ct, n_iter=self.nIter, tol=tol, xi_start=self.XiStart, want=want)
-        st = o["status"]                                                   # [nFOWT, nC, 4]
+        if "primary" in table:                                              # secondary trains share their primary's B_drag
+            o["B_drag"] = o["B_drag"][:, table["primary"]]
+        st = o["status"][:, first]                                          # [nFOWT, nC, 4] (train 0 of every case)
         if np.any(st[..., 2] & 1):
             raise Exception("Nan detected in response vector Xi.")          # raft_model.py:1098-1099
         w = self.w
@@ -102,14 +107,16 @@ class Model:
             M = P["M0"][:, :, None] + (P["A_w"] if "A_w" in P else 0.0)
             B = (P["B0"] + f.B_hydro_drag)[:, :, None] + (P["B_w"] if "B_w" in P else 0.0)
             f.Z = -w ** 2 * M + 1j * w * B + P["C0"][:, :, None]             # raft_model.py:1086, 1155 (last case)
-        Xi = np.moveaxis(o["Xi"], 0, 1).reshape(nC, self.nDOF, self.nw)     # [nC, 6N, nw]
+        nT = ct.n_cases
+        Xi_all = np.moveaxis(o["Xi"], 0, 1).reshape(nT, self.nDOF, self.nw)  # [nTrains, 6N, nw]
         if self.nFOWT > 1 and self.C_array is not None:
             # coupled system: Z_sys = blockdiag(Z_i) + C_array; F = Z_i Xi_i  (raft_model.py:1164-1216)
-            Xi = self._couple(o, cases)
-        return dict(Xi=Xi, status=np.moveaxis(st, 0, 1))
+            Xi_all = self._couple(o, nT)
+        Xi_trains = [Xi_all[owner == ic] for ic in range(nC)]
+        return dict(Xi=Xi_all[first], Xi_trains=Xi_trains, status=np.moveaxis(st, 0, 1))
 
-    def _couple(self, o, cases):
-        nC, n, nw, w = len(cases), self.nDOF, self.nw, self.w
+    def _couple(self, o, nC):
+        n, nw, w = self.nDOF, self.nw, self.w
         Xi = np.zeros([nC, n, nw], dtype=complex)
         packs = [f.pack() for f in self.fowtList]
         for c in range(nC):

@@ -235,3 +235,27 @@ def pack_cases(cases):
         gam[i] = float(first(c.get("wave_gamma", 0.0)))
         beta[i] = float(first(c.get("wave_heading", 0.0)))
     return dict(Hs=Hs, Tp=Tp, gamma=gam, beta_deg=beta, spec=spec)
+
+
+def pack_case_trains(cases):
+    """Load cases with one or several wave trains each (lists in the case dict, raft_fowt.py:1742-1752) ->
+    flattened train table with the ``primary`` map of the C ABI: train 0 of every case drives the drag
+    linearisation (raft_fowt.py:1910), its other trains reuse it (raft_model.py:1200-1236).
+
+    Returns (table dict incl. ``primary`` [nT] int32, ``owner`` [nT] case index of every train,
+    ``first`` [nC] index of every case's train 0)."""
+    rows, owner, primary, first = [], [], [], []
+    for ic, c in enumerate(cases):
+        nH = 1 if np.isscalar(c.get("wave_heading", 0.0)) else len(c["wave_heading"])
+        first.append(len(rows))
+        for ih in range(nH):
+            pick = lambda key, dflt=None: (c.get(key, dflt) if np.isscalar(c.get(key, dflt)) or isinstance(c.get(key, dflt), str)
+                                           else c.get(key, dflt)[ih])
+            rows.append(dict(wave_spectrum=pick("wave_spectrum", "JONSWAP"), wave_period=pick("wave_period"),
+                             wave_height=pick("wave_height"), wave_heading=pick("wave_heading", 0.0), wave_gamma=pick("wave_gamma", 0.0)))
+            owner.append(ic)
+            primary.append(first[-1])
+    table = pack_cases(rows)
+    if len(rows) > len(cases):
+        table["primary"] = np.array(primary, dtype=np.int32)
+    return table, np.array(owner, dtype=np.int64), np.array(first, dtype=np.int64)

@@ -161,6 +161,11 @@ class CaseTable:
         self.n_cases = len(a["Hs"])
         if zeta is not None:
             a["zeta"] = np.ascontiguousarray(zeta, dtype=_F8)
+        if cases.get("primary") is not None:
+            pr = np.ascontiguousarray(cases["primary"], dtype=_I4)
+            if len(pr) != self.n_cases or np.any(pr < 0) or np.any(pr >= self.n_cases) or np.any(pr[pr] != pr):
+                raise ValueError("primary must map every case to a primary case (primary[primary[c]] == primary[c])")
+            a["primary"] = pr
 
     def input_bytes(self):
         return int(sum(v.nbytes for v in self.arrays.values()))
@@ -168,7 +173,7 @@ class CaseTable:
     def struct(self, ptr):
         s = RaftkCases()
         s.n_cases = self.n_cases
-        for name in ("Hs", "Tp", "gamma", "beta_deg", "spec", "zeta"):
+        for name in ("Hs", "Tp", "gamma", "beta_deg", "spec", "zeta", "primary"):
             setattr(s, name, ptr(name) if name in self.arrays else None)
         return s
 

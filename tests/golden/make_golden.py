@@ -81,7 +81,7 @@ def _plain(x):
     return x
 
 
-def fixture(name, yaml_path, nw=None, max_freq=None, solve_cases=(), pickles=None, lin_check=True):
+def fixture(name, yaml_path, nw=None, max_freq=None, solve_cases=(), pickles=None, lin_check=True, trains=None):
     t0 = time.time()
     design = rh.load_design(yaml_path, nw=nw, max_freq=max_freq)
     # the input side of the fixture: the design sections the hot path reads (platform members, site, settings)
@@ -131,6 +131,15 @@ def fixture(name, yaml_path, nw=None, max_freq=None, solve_cases=(), pickles=Non
         out["ref_run_solve_Xi"] = Xi
         out["ref_run_solve_passes"] = passes
 
+    if trains is not None:
+        # one case with several wave trains (lists in the case dict, raft_fowt.py:1742-1752): Model.Xi[ih]
+        case = rh.make_case()
+        case.update(wave_heading=[t[2] for t in trains], wave_period=[t[1] for t in trains], wave_height=[t[0] for t in trains],
+                    wave_spectrum=["JONSWAP"] * len(trains), wave_gamma=[0.0] * len(trains))
+        x = rh.solve_dynamics(model, case)
+        out["ref_run_trains"] = np.array(trains, dtype=float)                # rows (Hs, Tp, heading_deg)
+        out["ref_run_trains_Xi"] = np.array(x[:len(trains)])
+
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **out)
     print("%-28s nw=%4d Ns=%3d cases=%2d  %.1f s  %.0f KB" % (name, len(P["w"]), len(P["node_ls"]), len(solve_cases),
@@ -151,9 +160,10 @@ def main():
     # BASELINE.json configs at reduced size (same recipes as SURVEY.md 8d, fewer bins/cases)
     Hs, Tp, beta = seeded_cases(2, 6)
     jobs.append(dict(name="cfg1_OC3spar", yaml_path=os.path.join(REF, "designs", "OC3spar.yaml"),
-                     solve_cases=[(2.0, 8.0, 0.0)]))
+                     solve_cases=[(2.0, 8.0, 0.0)], trains=[(2.0, 8.0, 0.0), (3.0, 12.0, 45.0)]))
     jobs.append(dict(name="cfg2_VolturnUS-S_nw64", yaml_path=os.path.join(REF, "designs", "VolturnUS-S.yaml"),
-                     nw=64, max_freq=0.512, solve_cases=list(zip(Hs, Tp, beta))))
+                     nw=64, max_freq=0.512, solve_cases=list(zip(Hs, Tp, beta)),
+                     trains=[(6.0, 12.0, 30.0), (2.5, 7.0, -100.0), (1.0, 16.0, 170.0)]))
     Hs, Tp, beta = seeded_cases(3, 4)
     jobs.append(dict(name="cfg3_OC4semi-WAMIT_nw128", yaml_path=os.path.join(REF, "examples", "OC4semi-WAMIT_Coefs.yaml"),
                      nw=128, max_freq=0.256, solve_cases=list(zip(Hs, Tp, beta))))

@@ -358,3 +358,31 @@ def test_pipelined_solve_chunks_match_single_launch(solver):
     torch.cuda.synchronize()
     Xi = np.concatenate([s.out["Xi"].cpu().numpy() for s in pipe.sessions], axis=0)
     assert np.array_equal(Xi, both["Xi"])
+
+
+@pytest.mark.parametrize("name", ["cfg1_OC3spar", "cfg2_VolturnUS-S_nw64"])
+def test_wave_trains_vs_reference_run(name, solver, oracle):
+    """A case with several wave trains (lists in the case dict): train 0 drives the linearisation, every train's
+    response uses that impedance and drag coefficients (raft_model.py:1200-1236) -- against the unmodified reference."""
+    model, G, P = _model_from_golden(name)
+    tr = G["ref_run_trains"]
+    case = dict(wave_spectrum=["JONSWAP"] * len(tr), wave_height=list(tr[:, 0]), wave_period=list(tr[:, 1]),
+                wave_heading=list(tr[:, 2]), wave_gamma=[0.0] * len(tr))
+    Xi = model.solveDynamics(case)
+    assert Xi.shape == (len(tr) + 1, 6, model.nw) and np.all(Xi[-1] == 0)
+    for ih in range(len(tr)):
+        assert response_err(Xi[ih], G["ref_run_trains_Xi"][ih]) < RTOL, ih
+    # low level: mixed table (two independent cases + the trains), secondary status rows point at their primary
+    from raft_b200 import packer
+    cases = [dict(wave_spectrum="JONSWAP", wave_height=2.0, wave_period=9.0, wave_heading=10.0), case,
+             dict(wave_spectrum="JONSWAP", wave_height=4.0, wave_period=11.0, wave_heading=-60.0)]
+    table, owner, first = packer.pack_case_trains(cases)
+    out = solver.solve_dynamics(solver.DesignBatch(P), solver.CaseTable(table), n_iter=int(G["n_iter"]), xi_start=float(G["xi_start"]))
+    assert list(first) == [0, 1, 1 + len(tr)] and list(table["primary"]) == [0] + [1] * len(tr) + [1 + len(tr)]
+    assert np.array_equal(out["status"][0, 2:1 + len(tr), 3], np.full(len(tr) - 1, 2))
+    Xo, _ = oracle.solve_dynamics_trains(oracle.OracleDesign(P), table["spec"][1:1 + len(tr)], tr[:, 0], tr[:, 1], np.zeros(len(tr)), tr[:, 2],
+                                         nIter=int(G["n_iter"]), XiStart=float(G["xi_start"]))
+    assert response_err(out["Xi"][0, 1:1 + len(tr)], Xo) < RTOL
+    solo = solver.solve_dynamics(solver.DesignBatch(P), solver.CaseTable(packer.pack_cases([cases[0], cases[2]])), n_iter=int(G["n_iter"]),
+                                 xi_start=float(G["xi_start"]))
+    assert np.array_equal(solo["Xi"][0, 0], out["Xi"][0, 0]) and np.array_equal(solo["Xi"][0, 1], out["Xi"][0, -1])

@@ -127,3 +127,14 @@ def test_grid_recipes():
     from raft_b200 import grid
     for nw, mf in ((1024, 0.512), (2048, 0.256), (512, 0.40), (1024, 0.1024)):
         assert len(grid.make_w(mf / nw, mf)) == nw
+
+
+@pytest.mark.parametrize("name", ["cfg1_OC3spar", "cfg2_VolturnUS-S_nw64"])
+def test_wave_trains_vs_reference_run(name, oracle):
+    """Cases with several wave trains: Model.Xi[ih] of the unmodified reference (raft_model.py:1200-1236)."""
+    G, P = load_golden(name)
+    tr = G["ref_run_trains"]
+    Xi, st = oracle.solve_dynamics_trains(oracle.OracleDesign(P), np.zeros(len(tr), dtype=np.int32), tr[:, 0], tr[:, 1],
+                                          np.zeros(len(tr)), tr[:, 2], nIter=int(G["n_iter"]), XiStart=float(G["xi_start"]))
+    for ih in range(len(tr)):
+        assert response_err(Xi[ih], G["ref_run_trains_Xi"][ih]) < 1e-12
