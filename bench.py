@@ -237,7 +237,8 @@ def main():
     ap.add_argument("--cases", type=int, default=0)
     ap.add_argument("--designs", type=int, default=0)
     ap.add_argument("--cluster", type=int, default=0)
-    ap.add_argument("--chunks", type=int, default=2, help="N>1: launches per step whose all-gathers overlap the next launch")
+    ap.add_argument("--chunks", type=int, default=0, help="N>1: launches per step whose all-gathers overlap the next launch "
+                                                          "(default 2 for cfg2/cfg3, 4 for the sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -271,6 +272,7 @@ def main():
     if world > 1:
         # N > 1: the step is two half-launches whose RAO all-gathers (NCCL, side stream) overlap the next half's kernels
         from raft_b200 import sweep as _sw
+        args.chunks = args.chunks or (2 if nD == 1 else 4)
         pipe = _sw.PipelinedSolve(designs, cs, n_chunks=args.chunks, split="cases" if nD == 1 else "designs", device=dev)
 
     def step():
@@ -281,6 +283,8 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    if pipe is not None:
+        pipe.drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -297,6 +301,11 @@ def main():
         a.record()
         step()
         b.record()
+    drain_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    drain_ev[0].record()
+    if pipe is not None:
+        pipe.drain()                         # timed: the last step's all-gathers must land inside the K-step total
+    drain_ev[1].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -304,7 +313,7 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = solver.launch_count() - launches0
     clocks = sampler.stop()
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+    ms = sum(a.elapsed_time(b) for a, b in ev) + drain_ev[0].elapsed_time(drain_ev[1])
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -390,7 +399,7 @@ def main():
         cfg.update(l2="flushed between timed steps (256 MiB write)", cluster_size=args.cluster or "auto",
                    units_per_step=units * world, mean_passes=mean_passes, wall_s_timed_region=t_wall,
                    collective=("%d x all_gather_into_tensor of Xi (%d B per rank per step in total), overlapped with the next "
-                               "chunk's kernels on a side stream" % (args.chunks, Xi.numel() * 16)) if world > 1 else "none")
+                               "chunk's / next step's kernels on a side stream" % (args.chunks, Xi.numel() * 16)) if world > 1 else "none")
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic", config=cfg, clocks=clocks, e2e=e2e, gpu_launches=int(launches),

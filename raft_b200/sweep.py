@@ -132,12 +132,18 @@ class PipelinedSolve:
         self.comm = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.gathered = [torch.empty((self.world,) + tuple(s.out["Xi"].shape), dtype=s.out["Xi"].dtype, device=dev)
                          if self.world > 1 else None for s in self.sessions]
+        self._ag_done = [None] * len(self.sessions)
         self.units = sum(s.batch.n_designs * s.cases.n_cases * s.batch.nw for s in self.sessions)
 
     def step(self, **solve_kw):
+        """Enqueue one step.  Software pipeline: chunk i's kernels only wait for the all-gather that last read chunk
+        i's output buffer (issued one step ago), so gathers also overlap the NEXT step's kernels; call ``drain()``
+        before reading ``gathered`` or stopping a timer."""
         torch = self.torch
         cur = torch.cuda.current_stream(self.sessions[0].device)
-        for sess, g in zip(self.sessions, self.gathered):
+        for i, (sess, g) in enumerate(zip(self.sessions, self.gathered)):
+            if self.world > 1 and self._ag_done[i] is not None:
+                cur.wait_event(self._ag_done[i])            # the previous gather of this buffer has consumed it
             sess.solve(**solve_kw)
             if self.world > 1:
                 ev = torch.cuda.Event()
@@ -145,8 +151,14 @@ class PipelinedSolve:
                 with torch.cuda.stream(self.comm):
                     self.comm.wait_event(ev)
                     self.dist.all_gather_into_tensor(g, sess.out["Xi"], group=self.group)
+                    done = torch.cuda.Event()
+                    done.record(self.comm)
+                self._ag_done[i] = done
+
+    def drain(self):
+        """Make the current stream wait for every outstanding all-gather."""
         if self.world > 1:
-            cur.wait_stream(self.comm)
+            self.torch.cuda.current_stream(self.sessions[0].device).wait_stream(self.comm)
 
     def status(self):
         return np.concatenate([s.out["status"].cpu().numpy().reshape(-1, 4) for s in self.sessions], axis=0)
