@@ -238,7 +238,8 @@ def main():
     ap.add_argument("--designs", type=int, default=0)
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--chunks", type=int, default=0, help="N>1: launches per step whose all-gathers overlap the next launch "
-                                                          "(default 2 for cfg2/cfg3, 4 for the sweep)")
+                                                          "(default 1: the gather overlaps the next step's kernels; more chunks make NCCL and the "
+                                                          "cluster kernels fight for SMs -- measured slower at N=2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -272,7 +273,7 @@ def main():
     if world > 1:
         # N > 1: the step is two half-launches whose RAO all-gathers (NCCL, side stream) overlap the next half's kernels
         from raft_b200 import sweep as _sw
-        args.chunks = args.chunks or (2 if nD == 1 else 4)
+        args.chunks = args.chunks or 1
         pipe = _sw.PipelinedSolve(designs, cs, n_chunks=args.chunks, split="cases" if nD == 1 else "designs", device=dev)
 
     def step():
