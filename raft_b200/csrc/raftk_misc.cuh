@@ -1,0 +1,112 @@
+// raftk_misc.cuh -- k_system_solve (farm 6N system), k_response_stats, k_fp64_peak (included by raftk.cu only).
+#pragma once
+
+// ------------------------------------------------------------------------------------------------
+// K3: dense complex solve per frequency (farm system response).  One CTA per frequency, matrix in
+// shared memory, LU with partial pivoting, nrhs right-hand sides.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_system_solve(int n, int nrhs, double2 *Z, double2 *F, int *info)
+{
+    extern __shared__ __align__(16) double smem_raw[];
+    double2 *A = reinterpret_cast<double2 *>(smem_raw);              // [n][n+nrhs] augmented
+    __shared__ int piv_s;
+    __shared__ double2 rinv_s;
+    const int iw = blockIdx.x, tid = threadIdx.x, nc = n + nrhs;
+    double2 *Zg = Z + (size_t)iw * n * n, *Fg = F + (size_t)iw * n * nrhs;
+    for (int t = tid; t < n * n; t += blockDim.x) A[(t / n) * nc + (t % n)] = Zg[t];
+    for (int t = tid; t < n * nrhs; t += blockDim.x) A[(t / nrhs) * nc + n + (t % nrhs)] = Fg[t];
+    __syncthreads();
+    int bad = 0;
+    for (int k = 0; k < n; k++) {
+        if (tid < 32) {                                              // pivot search by warp 0
+            double best = -1.0; int p = k;
+            for (int r = k + tid; r < n; r += 32) {
+                const double t = fabs(A[r * nc + k].x) + fabs(A[r * nc + k].y);
+                if (t > best) { best = t; p = r; }
+            }
+            for (int o = 16; o >= 1; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int op = __shfl_xor_sync(0xffffffffu, p, o);
+                if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+            }
+            if (tid == 0) {
+                piv_s = p;
+                const double2 pv = A[p * nc + k];
+                const double den = pv.x * pv.x + pv.y * pv.y;
+                rinv_s = (den > 0.0) ? make_double2(pv.x / den, -pv.y / den) : make_double2(0.0, 0.0);
+                if (!(den > 0.0)) bad = k + 1;
+            }
+        }
+        __syncthreads();
+        const int p = piv_s;
+        if (p != k) for (int t = tid; t < nc; t += blockDim.x) { const double2 tmp = A[k * nc + t]; A[k * nc + t] = A[p * nc + t]; A[p * nc + t] = tmp; }
+        __syncthreads();
+        const double2 ri = rinv_s;
+        for (int r = k + 1 + tid; r < n; r += blockDim.x) {
+            const double2 v = A[r * nc + k];
+            A[r * nc + k] = make_double2(v.x * ri.x - v.y * ri.y, v.x * ri.y + v.y * ri.x);
+        }
+        __syncthreads();
+        const int rows = n - k - 1, cols = nc - k - 1;
+        for (int t = tid; t < rows * cols; t += blockDim.x) {
+            const int r = k + 1 + t / cols, cidx = k + 1 + t % cols;
+            const double2 l = A[r * nc + k], u = A[k * nc + cidx];
+            double2 v = A[r * nc + cidx];
+            v.x -= l.x * u.x - l.y * u.y; v.y -= l.x * u.y + l.y * u.x;
+            A[r * nc + cidx] = v;
+        }
+        __syncthreads();
+    }
+    // back substitution, one thread per right-hand side
+    for (int rh = tid; rh < nrhs; rh += blockDim.x) {
+        for (int r = n - 1; r >= 0; r--) {
+            double2 s = A[r * nc + n + rh];
+            for (int cidx = r + 1; cidx < n; cidx++) {
+                const double2 a = A[r * nc + cidx], x = A[cidx * nc + n + rh];
+                s.x -= a.x * x.x - a.y * x.y; s.y -= a.x * x.y + a.y * x.x;
+            }
+            const double2 pv = A[r * nc + r];
+            const double den = pv.x * pv.x + pv.y * pv.y;
+            A[r * nc + n + rh] = make_double2((s.x * pv.x + s.y * pv.y) / den, (s.y * pv.x - s.x * pv.y) / den);
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < n * nrhs; t += blockDim.x) Fg[t] = A[(t / nrhs) * nc + n + (t % nrhs)];
+    if (tid == 0 && info) info[iw] = bad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: response statistics (std, PSD) -- one CTA per (unit, dof), fixed-order block reduction over frequency
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_response_stats(int nw, double dw, int rot_deg, const double2 *Xi, double *sd, double *psd)
+{
+    __shared__ double part[4];
+    const int row = blockIdx.x, dof = row % 6, tid = threadIdx.x;
+    const double scale = (rot_deg && dof >= 3) ? (180.0 / CUDART_PI) : 1.0;      // np.rad2deg
+    const double2 *x = Xi + (size_t)row * nw;
+    double s = 0.0;
+    for (int i = tid; i < nw; i += 128) {
+        const double re = x[i].x * scale, im = x[i].y * scale;
+        const double a2 = re * re + im * im;
+        s += a2;
+        if (psd) psd[(size_t)row * nw + i] = 0.5 * a2 / dw;
+    }
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) part[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) sd[row] = sqrt(0.5 * (((part[0] + part[1]) + part[2]) + part[3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 FMA peak micro-kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}

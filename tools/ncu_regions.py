@@ -2,7 +2,7 @@
 """Aggregate an ncu report's per-instruction stall samples by source line / kernel region.
 
 usage: tools/ncu_regions.py REPORT.ncu-rep KERNEL_MANGLED_SUBSTRING [top_n]
-Needs the in-tree libraftk.so built with -lineinfo (maps SASS offsets to raftk.cu lines via nvdisasm)."""
+Needs the in-tree libraftk.so built with -lineinfo (maps SASS offsets to raft_b200/csrc source lines via nvdisasm)."""
 import collections, csv, os, re, subprocess, sys, tempfile
 
 rep, kern = sys.argv[1], sys.argv[2]
@@ -19,9 +19,9 @@ for l in sass:
         infn = kern in l
     if not infn:
         continue
-    m = re.search(r'//## File ".*?raftk.cu", line (\d+)', l)
+    m = re.search(r'//## File ".*?/csrc/([\w.]+)", line (\d+)', l)
     if m:
-        cur = int(m.group(1)); continue
+        cur = (m.group(1), int(m.group(2))); continue
     m = re.search(r"/\*([0-9a-f]{4,})\*/\s+(\S+)", l)
     if m:
         off2line[int(m.group(1), 16)] = (cur, m.group(2))
@@ -42,9 +42,21 @@ for r in rows[2:]:
     s, e = int(r[isamp]), int(r[iex])
     per[ln] += s; perex[ln] += e; tot += s; totex += e
     ops[op.split(".")[0]] += e
-src = open(os.path.join(ROOT, "raft_b200", "csrc", "raftk.cu")).read().split("\n")
+_src = {}
+
+
+def src_line(key):
+    if not key:
+        return ""
+    f, n = key
+    if f not in _src:
+        try:
+            _src[f] = open(os.path.join(ROOT, "raft_b200", "csrc", f)).read().split("\n")
+        except OSError:
+            _src[f] = []
+    return _src[f][n - 1].strip()[:110] if 0 < n <= len(_src[f]) else ""
 print("total samples", tot, "total warp instructions", totex)
 print("opcode mix (executed):", ", ".join("%s %.1f%%" % (k, 100 * v / totex) for k, v in ops.most_common(18)))
 print("top lines (samples%, instr%):")
 for ln, s in per.most_common(topn):
-    print("%5s %6.2f%% %6.2f%%  %s" % (ln, 100 * s / tot, 100 * perex[ln] / totex, src[ln - 1].strip()[:110] if ln else ""))
+    print("%-22s %6.2f%% %6.2f%%  %s" % ("%s:%d" % ln if ln else "-", 100 * s / tot, 100 * perex[ln] / totex, src_line(ln)))
