@@ -386,3 +386,64 @@ def test_wave_trains_vs_reference_run(name, solver, oracle):
     solo = solver.solve_dynamics(solver.DesignBatch(P), solver.CaseTable(packer.pack_cases([cases[0], cases[2]])), n_iter=int(G["n_iter"]),
                                  xi_start=float(G["xi_start"]))
     assert np.array_equal(solo["Xi"][0, 0], out["Xi"][0, 0]) and np.array_equal(solo["Xi"][0, 1], out["Xi"][0, -1])
+
+
+def _random_design(rng, n_members):
+    """Synthetic platform with inclined / tapered / rectangular / potMod members (exercises both step-class kinds on
+    one member, ragged sections, surface-piercing strips)."""
+    members = []
+    for i in range(n_members):
+        kind = rng.integers(0, 4)
+        zA = -rng.uniform(8, 40)
+        if kind == 0:      # vertical column, possibly surface piercing, tapered
+            x, y = rng.uniform(-40, 40, 2)
+            rA, rB = [x, y, zA], [x, y, zA + rng.uniform(5, 60)]
+        elif kind == 1:    # horizontal pontoon
+            rA = [rng.uniform(-40, 40), rng.uniform(-40, 40), zA]
+            rB = [rA[0] + rng.uniform(5, 40), rA[1] + rng.uniform(-30, 30), zA]
+        else:              # inclined brace
+            rA = [rng.uniform(-40, 40), rng.uniform(-40, 40), zA]
+            rB = [rA[0] + rng.uniform(-30, 30), rA[1] + rng.uniform(-30, 30), zA + rng.uniform(3, 45)]
+        rect = rng.random() < 0.4
+        nst = int(rng.integers(2, 5))
+        st = np.sort(rng.uniform(0, 1, nst)); st[0], st[-1] = 0.0, 1.0
+        if rect:
+            d = [[float(rng.uniform(2, 9)), float(rng.uniform(2, 9))] for _ in range(nst)]
+        else:
+            d = [float(rng.uniform(2, 12)) for _ in range(nst)]
+        members.append(dict(name="m%d" % i, type="rigid", rA=[float(v) for v in rA], rB=[float(v) for v in rB],
+                            shape="rect" if rect else "circ", stations=[float(v) for v in st], d=d,
+                            gamma=float(rng.uniform(0, 90)) if rect else 0.0, potMod=bool(rng.random() < 0.25),
+                            Cd=float(rng.uniform(0.4, 1.2)), Ca=float(rng.uniform(0.5, 1.1)), CdEnd=0.6, CaEnd=0.6,
+                            Cd_q=float(rng.uniform(0.0, 0.1)), dlsMax=float(rng.uniform(1.5, 6.0))))
+    return dict(site=dict(water_depth=float(rng.uniform(60, 400)), rho_water=1025.0, g=9.81),
+                platform=dict(potModMaster=0, dlsMax=5.0, members=members))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_designs_vs_oracle(seed, solver, oracle):
+    """Randomised geometry / grid / sea states / cluster size against the oracle (generic code paths that the
+    BASELINE designs do not reach: inclined members, mixed step classes, tapered rectangular sections)."""
+    from raft_b200 import grid
+    from raft_b200.fowt import FOWT
+    rng = np.random.default_rng(seed)
+    design = _random_design(rng, int(rng.integers(2, 9)))
+    nw = int(rng.integers(40, 300))
+    w = grid.make_w(0.3 / nw, 0.3)
+    m = rng.uniform(0.5, 3.0) * 1e7
+    mats = dict(M_struc=np.diag([m, m, m, m * 900, m * 900, m * 1500]) + rng.normal(size=(6, 6)) * m * 0.01,
+                C_struc=np.diag([0, 0, 0, -m * 5, -m * 5, 0.0]),
+                C_hydro=np.diag([0, 0, rng.uniform(2, 6) * 1e6, rng.uniform(1, 4) * 1e9, rng.uniform(1, 4) * 1e9, 0.0]),
+                C_moor=np.diag([7e4, 7e4, 0, 0, 0, 1.2e8]), B_struc=np.diag(rng.uniform(0, 1e5, 6)))
+    f = FOWT(design, w, depth=design["site"]["water_depth"], matrices=mats)
+    f.calcHydroConstants()
+    Q = f.pack()
+    assert len(Q["node_ls"]) > 0
+    cs = sea_states(seed + 100, int(rng.integers(2, 7)))
+    cs["spec"][-1] = 1                                            # one unit-spectrum case
+    cluster = int(rng.choice([0, 1, 2, 4]))
+    out = solver.solve_dynamics(solver.DesignBatch(Q), solver.CaseTable(cs), n_iter=12, cluster_size=cluster)
+    Xi_o, st_o, _ = oracle.solve_cases(oracle.OracleDesign(Q), cs, nIter=12)
+    assert np.array_equal(out["status"][0, :, :2], st_o[:, :2]), (out["status"][0], st_o)
+    assert np.all(out["status"][0, :, 2] == 0)
+    assert response_err(out["Xi"][0], Xi_o) < RTOL
