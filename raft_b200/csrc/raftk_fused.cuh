@@ -13,8 +13,8 @@
 // C = A+ + A-, S = A+ - A-  (the depth functions cosh/sinh(k(z+h))/sinh(kh) split into their growing
 // and decaying exponentials, so there is no cancellation in either walking direction; rounding grows
 // ~1 ulp per node).  Distinct steps are deduplicated per design (8 classes for VolturnUS-S).
-// Directions that are exactly horizontal (d_z = 0) or vertical (d_x = d_y = 0) take 3-flop
-// projections instead of the generic 6-flop complex product.
+// The node body is branch-free: a member's first node and zero steps use identity rows of the factor tables,
+// and the factors of node j+1 are requested while node j is computed (shared-memory latency off the critical path).
 // ------------------------------------------------------------------------------------------------
 struct FusedParams {
     int n_iter, CS, nwl, maxW, maxH, maxZ;
@@ -27,7 +27,7 @@ struct FusedParams {
     int phase;               // -1: every case is its own primary; 0: run primaries only; 1: run secondaries only
 };
 
-#define IMEM_STRIDE 6      // ints per member: node start, node end, circular, direction kinds, z-class, spare
+#define IMEM_STRIDE 6      // ints per member: node start, node end, circular, (spare), z-class, (spare)
 #define NCOEF 5            // per-node linearised coefficients: bq, b1, ls*b1, b2, ls*b2
 
 struct FSmem {
@@ -49,14 +49,14 @@ __host__ __device__ inline size_t fused_smem_bytes(int Nm, int NsP, int nchunk, 
 // projection of the wave velocity on direction d plus a body-velocity term: a = E (C h + i S d_z) + m.
 // (A 3-way specialisation on exactly horizontal / vertical directions was measured: ptxas if-converts it
 // into predicated code that issues all variants, so the generic 6-flop form is kept.)
-__device__ __forceinline__ void proj_add(int, double er, double ei, double Cc, double Sc, double h, double dz,
+__device__ __forceinline__ void proj_add(double er, double ei, double Cc, double Sc, double h, double dz,
                                          double mr, double mi, double &ar, double &ai)
 {
     const double gr = Cc * h, gi = Sc * dz;
     ar = fma(er, gr, fma(-ei, gi, mr));
     ai = fma(er, gi, fma(ei, gr, mi));
 }
-__device__ __forceinline__ void proj(int, double er, double ei, double Cc, double Sc, double h, double dz, double &cr, double &ci)
+__device__ __forceinline__ void proj(double er, double ei, double Cc, double Sc, double h, double dz, double &cr, double &ci)
 {
     const double gr = Cc * h, gi = Sc * dz;
     cr = fma(er, gr, -ei * gi);
@@ -130,7 +130,6 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         const double *fr = D.mem_frame + 9 * (m0 + m);
         const double *arm = D.mem_arm + 3 * (m0 + m);
         double *o = S.mem + m * MEM_STRIDE;
-        int kinds = 0;
         for (int t = 0; t < 9; t++) o[t] = fr[t];
         for (int v = 0; v < 3; v++) {
             const double d0_ = fr[3 * v], d1_ = fr[3 * v + 1], d2_ = fr[3 * v + 2];
@@ -138,16 +137,12 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
             o[9 + 3 * v + 1] = arm[2] * d0_ - arm[0] * d2_;
             o[9 + 3 * v + 2] = arm[0] * d1_ - arm[1] * d0_;
             o[18 + v] = d0_ * cb + d1_ * sb;
-            int kd = 0;
-            if (fabs(d2_) < 1e-14) kd = 1;                               // horizontal direction: S d_z term vanishes
-            else if (fabs(d0_) < 1e-14 && fabs(d1_) < 1e-14) kd = 2;     // vertical direction: C h term vanishes
-            kinds |= kd << (2 * v);
         }
         const int js = D.mem_node_start[m0 + m] - nbase;
         S.imem[IMEM_STRIDE * m + 0] = js;
         S.imem[IMEM_STRIDE * m + 1] = D.mem_node_start[m0 + m + 1] - nbase;
         S.imem[IMEM_STRIDE * m + 2] = D.mem_circ[m0 + m];
-        S.imem[IMEM_STRIDE * m + 3] = kinds;
+        S.imem[IMEM_STRIDE * m + 3] = 0;
         o[21] = D.mem_rA[3 * (m0 + m) + 2] + D.node_ls[nbase + js] * fr[2];    // z of the first submerged node
     }
     for (int j = tid; j < NsP; j += T) {
@@ -259,7 +254,6 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         for (int m = 0; m < Nm; m++) {
             const double *o = S.mem + m * MEM_STRIDE;
             const int j0 = S.imem[IMEM_STRIDE * m], j1 = S.imem[IMEM_STRIDE * m + 1];
-            const int kinds = S.imem[IMEM_STRIDE * m + 3], kq = kinds & 3, k1 = (kinds >> 2) & 3, k2 = (kinds >> 4) & 3;
             const double *rA = D.mem_rA + 3 * (m0 + m);
             const double ls0 = S.node[j0];
             const double x0 = rA[0] + ls0 * o[0], y0 = rA[1] + ls0 * o[1];
@@ -287,11 +281,11 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
                 if (inq != 0.0 || in1 != 0.0 || in2 != 0.0 || in1i != 0.0 || in2i != 0.0 || pa != 0.0) {
                     const double ls = S.node[j], Cc = ap + am, Sc = ap - am;
                     double cr, ci;
-                    proj(kq, er, ei, Cc, Sc, hq, o[2], cr, ci);
+                    proj(er, ei, Cc, Sc, hq, o[2], cr, ci);
                     double fqr = -w * inq * ci, fqi = w * inq * cr;
-                    proj(k1, er, ei, Cc, Sc, h1, o[5], cr, ci);
+                    proj(er, ei, Cc, Sc, h1, o[5], cr, ci);
                     const double f1r = -w * (in1 * ci + in1i * cr), f1i = w * (in1 * cr - in1i * ci);
-                    proj(k2, er, ei, Cc, Sc, h2, o[8], cr, ci);
+                    proj(er, ei, Cc, Sc, h2, o[8], cr, ci);
                     const double f2r = -w * (in2 * ci + in2i * cr), f2i = w * (in2 * cr - in2i * ci);
                     if (pa != 0.0 && w != 0.0) {
                         // dynamic pressure: P = cosh(k(z+h))/cosh(kh) = C tanh(kh); deep-water branch of helpers.py:218
@@ -369,7 +363,6 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
                         const int jfirst = jc0 + jj;
                         do { mcur++; } while (jfirst >= S.imem[IMEM_STRIDE * mcur + 1]);
                         const int mstart = S.imem[IMEM_STRIDE * mcur], jlast = S.imem[IMEM_STRIDE * mcur + 1] - jc0;
-                        const int kinds = S.imem[IMEM_STRIDE * mcur + 3], kq = kinds & 3, k1 = (kinds >> 2) & 3, k2 = (kinds >> 4) & 3;
                         const double *o = S.mem + mcur * MEM_STRIDE;
                         double sr, si;
                         sr = o[0] * xr[0] + o[1] * xr[1] + o[2] * xr[2] + o[9] * xr[3] + o[10] * xr[4] + o[11] * xr[5];
@@ -403,11 +396,11 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         ap *= CH.x; am *= CH.y;                                                                                      \
         const double ls = CL, Cc = ap + am, Sc = ap - am;                                                            \
         double ar_, ai_;                                                                                             \
-        proj_add(kq, er, ei, Cc, Sc, hq, dzq, mqr, mqi, ar_, ai_);                                                   \
+        proj_add(er, ei, Cc, Sc, hq, dzq, mqr, mqi, ar_, ai_);                                                   \
         acc[3 * JJ + 0] = fma(ar_, ar_, fma(ai_, ai_, acc[3 * JJ + 0]));                                             \
-        proj_add(k1, er, ei, Cc, Sc, h1, dz1, fma(ls, t2r, m1r), fma(ls, t2i, m1i), ar_, ai_);                       \
+        proj_add(er, ei, Cc, Sc, h1, dz1, fma(ls, t2r, m1r), fma(ls, t2i, m1i), ar_, ai_);                       \
         acc[3 * JJ + 1] = fma(ar_, ar_, fma(ai_, ai_, acc[3 * JJ + 1]));                                             \
-        proj_add(k2, er, ei, Cc, Sc, h2, dz2, fma(-ls, t1r, m2r), fma(-ls, t1i, m2i), ar_, ai_);                     \
+        proj_add(er, ei, Cc, Sc, h2, dz2, fma(-ls, t1r, m2r), fma(-ls, t1i, m2i), ar_, ai_);                     \
         acc[3 * JJ + 2] = fma(ar_, ar_, fma(ai_, ai_, acc[3 * JJ + 2]));                                             \
     }
                         // Duff-style dispatch: one copy of each node body (static accumulator index), re-entered per member
@@ -537,7 +530,6 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
             for (int m = 0; m < Nm; m++) {
                 const double *o = S.mem + m * MEM_STRIDE;
                 const double hq = o[18], h1 = o[19], h2 = o[20], dzq = o[2], dz1 = o[5], dz2 = o[8];
-                const int kinds = S.imem[IMEM_STRIDE * m + 3], kq = kinds & 3, k1 = (kinds >> 2) & 3, k2 = (kinds >> 4) & 3;
                 double Aqr = 0, Aqi = 0, A1r = 0, A1i = 0, A2r = 0, A2i = 0, L1r = 0, L1i = 0, L2r = 0, L2i = 0;
                 const int j0 = S.imem[IMEM_STRIDE * m], j1 = S.imem[IMEM_STRIDE * m + 1];
                 const double2 e0 = S.ebase[m * nwl + t], a0 = S.abase[S.imem[IMEM_STRIDE * m + 4] * nwl + t];
@@ -552,11 +544,11 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
                     const double bq = cq_[j], b1 = c1_[j], lb1 = cl1_[j], b2 = c2_[j], lb2 = cl2_[j];
                     const double Cc = ap + am, Sc = ap - am;
                     double cr, ci;
-                    proj(kq, er, ei, Cc, Sc, hq, dzq, cr, ci);
+                    proj(er, ei, Cc, Sc, hq, dzq, cr, ci);
                     Aqr = fma(bq, cr, Aqr); Aqi = fma(bq, ci, Aqi);
-                    proj(k1, er, ei, Cc, Sc, h1, dz1, cr, ci);
+                    proj(er, ei, Cc, Sc, h1, dz1, cr, ci);
                     A1r = fma(b1, cr, A1r); A1i = fma(b1, ci, A1i); L1r = fma(lb1, cr, L1r); L1i = fma(lb1, ci, L1i);
-                    proj(k2, er, ei, Cc, Sc, h2, dz2, cr, ci);
+                    proj(er, ei, Cc, Sc, h2, dz2, cr, ci);
                     A2r = fma(b2, cr, A2r); A2i = fma(b2, ci, A2i); L2r = fma(lb2, cr, L2r); L2i = fma(lb2, ci, L2i);
                 }
 #pragma unroll
