@@ -18,8 +18,9 @@
  *   - *_host entry points take HOST pointers, stage through an internal device arena
  *     (grown on demand, cached per process), and are synchronous.
  *
- * Scope: rigid 6-DOF FOWTs, strip-theory members (+ optional BEM tables), one wave train drives
- * the drag linearisation (raft_fowt.py:1910).  See DESIGN.md for what is out of scope.
+ * Scope: rigid 6-DOF FOWTs, strip-theory members (+ optional BEM tables, + optional external QTF for
+ * second-order difference-frequency forces), one wave train drives the drag linearisation
+ * (raft_fowt.py:1910).  See DESIGN.md for what is out of scope.
  */
 #ifndef RAFTK_H
 #define RAFTK_H
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RAFTK_VERSION 100 /* 0.1.0 */
+#define RAFTK_VERSION 110 /* 0.1.1: + external-QTF second-order forces */
 
 enum {
     RAFTK_OK = 0,
@@ -100,6 +101,16 @@ typedef struct raftk_designs {
     const double *bem_headings; /* [n_bem_head] deg, ascending (shared by all designs)          */
     const double *X_BEM;        /* complex [nD, n_bem_head, 6, nw]                              */
     const double *bem_xyh;      /* [nD,3] x_ref, y_ref, heading_adjust(deg)                     */
+    /* external difference-frequency QTF (potSecOrder 2: the state FOWT.readQTF leaves behind,
+       raft_fowt.py:2081-2128), or n_qtf_w = 0 */
+    int32_t n_qtf_w;            /* QTF frequencies (w1_2nd == w2_2nd, raft_fowt.py:2105-2110)   */
+    int32_t n_qtf_head;         /* unidirectional QTF headings (heads_2nd)                      */
+    int32_t qtf_shared;         /* 1: qtf holds ONE table used by every design (no design axis) */
+    int32_t _pad2;
+    const double *qtf_w;        /* [n_qtf_w] rad/s, ascending                                   */
+    const double *qtf_heads;    /* [n_qtf_head] rad, ascending                                  */
+    const double *qtf;          /* complex [nD or 1, n_qtf_w, n_qtf_w, n_qtf_head, 6]: fowt.qtf, dimensional,
+                                   Hermitian-filled (raft_fowt.py:2112-2128)                     */
 } raftk_designs;
 
 /* Load cases, shared by all designs: units of work are (design, case) pairs.
@@ -118,6 +129,9 @@ typedef struct raftk_cases {
                                 its response uses the impedance and per-node drag coefficients of case p
                                 (raft_model.py:1200-1236; p must be a primary).  NULL: all cases independent.
                                 Only raftk_solve_dynamics_*; needs raftk_solve_workspace_bytes() of workspace. */
+    const double *F_2nd;     /* optional real [nD,nC,6,nw]: second-order force amplitudes (fowt.Fhydro_2nd, from
+                                raftk_second_order_force_*) added to the linear excitation F_BEM + F_iner of every
+                                unit (raft_model.py:1048, :1212).  NULL: none, or computed by the solve (see below). */
 } raftk_cases;
 
 /* Fixed-point loop controls (raft_model.py:966 tol, :977 nIter, :978 XiStart, :1133 relaxation) */
@@ -137,6 +151,8 @@ typedef struct raftk_outputs {
     double *F_iner;   /* complex [nD,nC,6,nw] strip inertial excitation (fowt.F_hydro_iner[0])  */
     double *F_BEM;    /* complex [nD,nC,6,nw] BEM excitation (fowt.F_BEM[0])                    */
     double *zeta;     /* [nC,nw] wave amplitudes (fowt.zeta[0])                                 */
+    double *F_2nd;    /* real [nD,nC,6,nw] difference-frequency force amplitudes (fowt.Fhydro_2nd)  */
+    double *F_2nd_mean; /* [nD,nC,6] mean drift force (fowt.Fhydro_2nd_mean)                        */
 } raftk_outputs;
 
 int raftk_version(void);
@@ -189,6 +205,22 @@ int raftk_hydro_linearization_dev(const raftk_designs *d, const raftk_cases *c, 
 int raftk_solve_dynamics_dev(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o,
                              const raftk_outputs *out, void *workspace, size_t workspace_bytes,
                              void *stream);
+
+/*
+ * FOWT.calcHydroForce_2ndOrd(beta, S0), interpMode 'qtf' (raft_fowt.py:2158-2253) for every (design, case):
+ * heading interpolation of the designs' QTF table, bilinear interpolation onto the model grid, the
+ * difference-frequency sums  f(mu) = 4 dw sqrt(sum_i S(w_i) S(w_i+mu) |Q(w_i, w_i+mu)|^2)  shifted by one bin
+ * (:2244-2245), and the mean drift  2 dw sum_i S(w_i) Re Q(w_i, w_i).  S is each case's wave spectrum
+ * (raft_fowt.py:1758-1772; zeta^2 / (2 dw) for explicit amplitudes).  Needs designs.qtf; reads only the grid,
+ * site and QTF fields of `d`.  Fills out->F_2nd (required) and out->F_2nd_mean (optional).
+ *
+ * Model.solveDynamics adds this force to the linear excitation when potSecOrder == 2 (raft_model.py:1035-1048,
+ * :1210-1212).  raftk_solve_dynamics_dev does so when cases.F_2nd is given; when the designs carry a QTF and
+ * cases.F_2nd is NULL it computes the force itself into out->F_2nd (then required as the buffer).
+ * raftk_solve_dynamics_host always computes it when the designs carry a QTF (out->F_2nd optional).
+ */
+int raftk_second_order_force_dev(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out, void *stream);
+int raftk_second_order_force_host(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out);
 
 /* Same three operations with HOST pointers everywhere (tables, cases, outputs). */
 int raftk_hydro_excitation_host(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out);

@@ -31,6 +31,8 @@ class RoDesign(C.Structure):
         ("M0", c_double_p), ("B0", c_double_p), ("C0", c_double_p),
         ("A_w", c_double_p), ("B_w", c_double_p),
         ("X_BEM", C.c_void_p), ("bem_headings", c_double_p), ("node_Imat_w", C.c_void_p),
+        ("n_qtf_w", C.c_int), ("n_qtf_head", C.c_int),
+        ("qtf_w", c_double_p), ("qtf_heads", c_double_p), ("qtf", C.c_void_p),
     ]
 
 
@@ -102,6 +104,14 @@ class OracleDesign:
         if "node_Imat_w" in P and P["node_Imat_w"] is not None:
             k["node_Imat_w"] = np.ascontiguousarray(P["node_Imat_w"], dtype=np.complex128)
             d.node_Imat_w = k["node_Imat_w"].ctypes.data_as(C.c_void_p)
+        if P.get("qtf") is not None:
+            # fowt.qtf [nw1, nw2, nheads, 6], fowt.w1_2nd, fowt.heads_2nd (raft_fowt.py:2100-2128)
+            k["qtf"] = np.ascontiguousarray(P["qtf"], dtype=np.complex128)
+            k["qtf_w"], k["qtf_heads"] = f8(P["qtf_w"]), f8(P["qtf_heads"])
+            d.n_qtf_w, d.n_qtf_head = len(k["qtf_w"]), len(k["qtf_heads"])
+            assert k["qtf"].shape == (d.n_qtf_w, d.n_qtf_w, d.n_qtf_head, 6)
+            d.qtf_w, d.qtf_heads = _dp(k["qtf_w"]), _dp(k["qtf_heads"])
+            d.qtf = k["qtf"].ctypes.data_as(C.c_void_p)
         self.c = d
 
 
@@ -179,6 +189,14 @@ def calc_hydro_linearization(od, u, Xi):
     lib().ro_calc_hydro_linearization(C.byref(od.c), u.ctypes.data_as(C.c_void_p), Xi.ctypes.data_as(C.c_void_p),
                                       _dp(Bmat), _dp(B), F.ctypes.data_as(C.c_void_p))
     return Bmat[:Ns], B, F
+
+
+def hydro_force_2nd(od, beta, S0):
+    """FOWT.calcHydroForce_2ndOrd(beta [rad], S0[nw]) with the design's QTF table -> f_mean[6], f[6,nw]."""
+    S0 = np.ascontiguousarray(S0, dtype=np.float64)
+    fm, f = np.zeros(6), np.zeros([6, od.nw])
+    lib().ro_hydro_force_2nd(C.byref(od.c), C.c_double(float(beta)), _dp(S0), _dp(fm), _dp(f))
+    return fm, f
 
 
 def solve_dynamics(od, spec, Hs, Tp, gamma, beta_deg, nIter=10, tol=0.01, XiStart=0.0, want_Z=False):

@@ -16,8 +16,9 @@
  * The loop structure, operation order and two-step (member node -> reduced DOF) translation of
  * the reference are kept on purpose: this is the checker for the restructured CUDA kernels.
  *
- * Scope: rigid 6-DOF FOWT (MacCamy-Fuchs Imat as an input table), no underwater rotor, no second-order forces
- * (BASELINE.json configs 1-4).
+ * Scope: rigid 6-DOF FOWT (MacCamy-Fuchs Imat as an input table), no underwater rotor; second-order forces only
+ * from an external QTF table (potSecOrder 2; raft_fowt.py:2158-2253), not the slender-body QTF (potSecOrder 1)
+ * (BASELINE.json configs 1-4; SURVEY.md section 8a rows a1-a11 + 8f row 3).
  */
 #include <complex.h>
 #include <math.h>
@@ -48,6 +49,11 @@ typedef struct {
     const cplx *X_BEM;                             /* [nhead,6,nw] or NULL (reference layout) */
     const double *bem_headings;                    /* [nhead] deg                             */
     const cplx *node_Imat_w;                       /* [Ns,3,3,nw] MacCamy-Fuchs Imat_MCF or NULL */
+    /* external difference-frequency QTF (fowt.qtf after readQTF, raft_fowt.py:2081-2128), or qtf == NULL */
+    int n_qtf_w, n_qtf_head;
+    const double *qtf_w;                           /* [n_qtf_w] rad/s ascending (w1_2nd == w2_2nd)   */
+    const double *qtf_heads;                       /* [n_qtf_head] rad ascending (heads_2nd)        */
+    const cplx *qtf;                               /* [n_qtf_w,n_qtf_w,n_qtf_head,6] (reference layout) */
 } ro_design;
 
 /* helpers.py:377-392 waveNumber(omega, h, e=0.001) */
@@ -420,6 +426,104 @@ int ro_zinv(int n, cplx *A, cplx *Ainv)
 
 /* ---- public entry points --------------------------------------------------------------- */
 
+/* FOWT.calcHydroForce_2ndOrd(beta, S0), interpMode 'qtf' (raft_fowt.py:2158-2253): difference-frequency force
+ * amplitudes from the QTF table.  S0 [nw] wave spectrum, beta [rad] -> f_mean [6], f [6][nw] (real amplitudes,
+ * already shifted by one bin, :2244-2245).
+ *   :2178-2187  heading: single table as is, else scipy interp1d(kind linear) along the heading axis with the first /
+ *               last table as fill value outside the range (slope form y = (y_hi-y_lo)/(x_hi-x_lo)*(x-x_lo)+y_lo)
+ *   :2221-2229  RegularGridInterpolator(linear, bounds_error False, fill_value 0) of Re and Im onto (w_i, w_j):
+ *               v00(1-ti)(1-tj) + v01(1-ti)tj + v10 ti(1-tj) + v11 ti tj, zero outside the table
+ *   :2231-2236  f[imu] = 4 sqrt(sum_i S0[i] S0[i+imu] |Q(w_i, w_{i+imu})|^2) dw, imu = 1..nw-1
+ *   :2239       f_mean = 2 sum_i S0[i] Re Q(w_i, w_i) dw */
+void ro_hydro_force_2nd(const ro_design *d, double beta, const double *S0, double *f_mean, double *f)
+{
+    int nw = d->nw, n2 = d->n_qtf_w, nh = d->n_qtf_head;
+    cplx *qb = malloc(sizeof(cplx) * (size_t)n2 * n2 * 6);
+    for (size_t e = 0; e < (size_t)n2 * n2; e++)
+        for (int a = 0; a < 6; a++) {
+            const cplx *row = d->qtf + (e * nh) * 6;
+            if (nh == 1) qb[e * 6 + a] = row[a];
+            else if (beta < d->qtf_heads[0]) qb[e * 6 + a] = row[a];
+            else if (beta > d->qtf_heads[nh - 1]) qb[e * 6 + a] = row[(size_t)(nh - 1) * 6 + a];
+            else {
+                int idx = 0;
+                while (idx < nh && d->qtf_heads[idx] < beta) idx++;          /* searchsorted, side left */
+                if (idx < 1) idx = 1;
+                if (idx > nh - 1) idx = nh - 1;
+                double xl = d->qtf_heads[idx - 1], xh = d->qtf_heads[idx];
+                cplx yl = row[(size_t)(idx - 1) * 6 + a], yh = row[(size_t)idx * 6 + a];
+                double re = (creal(yh) - creal(yl)) / (xh - xl) * (beta - xl) + creal(yl);
+                double im = (cimag(yh) - cimag(yl)) / (xh - xl) * (beta - xl) + cimag(yl);
+                qb[e * 6 + a] = re + I * im;
+            }
+        }
+    int *cell = malloc(sizeof(int) * nw);
+    double *t = malloc(sizeof(double) * nw);
+    for (int i = 0; i < nw; i++) {
+        double x = d->w[i];
+        if (x < d->qtf_w[0] || x > d->qtf_w[n2 - 1]) { cell[i] = -1; t[i] = 0; continue; }
+        int c = 0;
+        while (c < n2 - 2 && d->qtf_w[c + 1] <= x) c++;
+        cell[i] = c;
+        t[i] = (x - d->qtf_w[c]) / (d->qtf_w[c + 1] - d->qtf_w[c]);
+    }
+#define QTF_AT(i_, j_, a_, re_, im_) do {                                                            \
+        re_ = 0; im_ = 0;                                                                            \
+        if (cell[i_] >= 0 && cell[j_] >= 0) {                                                        \
+            int ci = cell[i_], cj = cell[j_];                                                        \
+            double ti = t[i_], tj = t[j_];                                                           \
+            cplx v00 = qb[((size_t)ci * n2 + cj) * 6 + a_], v01 = qb[((size_t)ci * n2 + cj + 1) * 6 + a_]; \
+            cplx v10 = qb[((size_t)(ci + 1) * n2 + cj) * 6 + a_], v11 = qb[((size_t)(ci + 1) * n2 + cj + 1) * 6 + a_]; \
+            double w00 = (1 - ti) * (1 - tj), w01 = (1 - ti) * tj, w10 = ti * (1 - tj), w11 = ti * tj; \
+            re_ = ((creal(v00) * w00 + creal(v01) * w01) + creal(v10) * w10) + creal(v11) * w11;     \
+            im_ = ((cimag(v00) * w00 + cimag(v01) * w01) + cimag(v10) * w10) + cimag(v11) * w11;     \
+        } } while (0)
+    for (int a = 0; a < 6; a++) {
+        double *fa = f + (size_t)a * nw;
+        fa[0] = 0;
+        for (int imu = 1; imu < nw; imu++) {
+            double s = 0;
+            for (int i = 0; i < nw - imu; i++) {
+                double re, im;
+                QTF_AT(i, i + imu, a, re, im);
+                s += S0[i] * S0[i + imu] * (re * re + im * im);
+            }
+            fa[imu] = 4 * sqrt(s) * d->dw;
+        }
+        double sm = 0;
+        for (int i = 0; i < nw; i++) {
+            double re, im;
+            QTF_AT(i, i, a, re, im);
+            (void)im;
+            sm += S0[i] * re;
+        }
+        f_mean[a] = 2 * sm * d->dw;
+        for (int i = 0; i < nw - 1; i++) fa[i] = fa[i + 1];                   /* :2244 */
+        fa[nw - 1] = 0;                                                       /* :2245 */
+    }
+#undef QTF_AT
+    free(qb); free(cell); free(t);
+}
+
+/* second-order force of one wave train as the solver adds it (raft_model.py:1035-1038, :1210-1211): zero unless
+ * the design carries a QTF table.  F2 [6][nw] real, F2_mean [6] (may be NULL). */
+static int second_order_force(const ro_design *d, int spec, double Hs, double Tp, double gamma, double beta_deg,
+                              double *F2, double *F2_mean)
+{
+    int nw = d->nw;
+    double fm[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 6 * nw; i++) F2[i] = 0;
+    if (d->qtf) {
+        double *S = malloc(sizeof(double) * nw), *z = malloc(sizeof(double) * nw);
+        int rc = ro_sea_state(d->w, nw, d->dw, spec, Hs, Tp, gamma, S, z);
+        if (!rc) ro_hydro_force_2nd(d, beta_deg * (M_PI / 180.0), S, fm, F2);
+        free(S); free(z);
+        if (rc) return rc;
+    }
+    if (F2_mean) memcpy(F2_mean, fm, sizeof(fm));
+    return 0;
+}
+
 /* FOWT.calcHydroExcitation for one single-train case: zeta[nw], F_BEM[6][nw], F_iner[6][nw], u[Ns][3][nw] */
 int ro_calc_hydro_excitation(const ro_design *d, int spec, double Hs, double Tp, double gamma, double beta_deg,
                              double *zeta, cplx *F_BEM, cplx *F_iner, cplx *u)
@@ -455,9 +559,11 @@ int ro_solve_dynamics(const ro_design *d, int spec, double Hs, double Tp, double
     cplx *XiLast = malloc(sizeof(cplx) * 6 * nw), *Xi = malloc(sizeof(cplx) * 6 * nw);
     cplx *F_drag = malloc(sizeof(cplx) * 6 * nw), *Z = malloc(sizeof(cplx) * 36 * (size_t)nw);
     double B_drag[6][6];
+    double *F2 = malloc(sizeof(double) * 6 * nw);
     int rc = ro_calc_hydro_excitation(d, spec, Hs, Tp, gamma, beta_deg, zeta, F_BEM, F_iner, u);
     status[0] = status[1] = status[2] = 0;
     if (rc) goto done;
+    second_order_force(d, spec, Hs, Tp, gamma, beta_deg, F2, NULL);             /* :1035-1038 */
     for (int i = 0; i < 6 * nw; i++) XiLast[i] = XiStart;
     int passes = 0, conv = 0;
     for (int iiter = 0; iiter < nIter + 1; iiter++) {                        /* :977, :1052 */
@@ -475,7 +581,7 @@ int ro_solve_dynamics(const ro_design *d, int spec, double Hs, double Tp, double
                     B += B_drag[a][c];
                     A[6 * a + c] = -wv * wv * M + I * wv * B + d->C0[6 * a + c];   /* :1086 */
                 }
-                b[a] = (F_BEM[a * nw + ii] + F_iner[a * nw + ii]) + F_drag[a * nw + ii]; /* :1048,:1081 */
+                b[a] = ((F_BEM[a * nw + ii] + F_iner[a * nw + ii]) + F2[a * nw + ii]) + F_drag[a * nw + ii]; /* :1048,:1081 */
             }
             memcpy(Z + (size_t)ii * 36, A, sizeof(A));
             ro_zgesv(6, A, b);                                               /* :1089 */
@@ -500,14 +606,14 @@ int ro_solve_dynamics(const ro_design *d, int spec, double Hs, double Tp, double
         for (int a = 0; a < 6; a++) {
             cplx s = 0;
             for (int c = 0; c < 6; c++)
-                s += Ai[6 * a + c] * ((F_BEM[c * nw + ii] + F_iner[c * nw + ii]) + F_drag[c * nw + ii]);
+                s += Ai[6 * a + c] * (((F_BEM[c * nw + ii] + F_iner[c * nw + ii]) + F_drag[c * nw + ii]) + F2[c * nw + ii]);  /* :1212 */
             Xi_out[a * nw + ii] = s;
         }
     }
     if (Z_out) memcpy(Z_out, Z, sizeof(cplx) * 36 * (size_t)nw);
     if (B_drag_out) memcpy(B_drag_out, B_drag, sizeof(B_drag));
 done:
-    free(zeta); free(Bmat); free(F_BEM); free(F_iner); free(u); free(XiLast); free(Xi); free(F_drag); free(Z);
+    free(zeta); free(Bmat); free(F_BEM); free(F_iner); free(u); free(XiLast); free(Xi); free(F_drag); free(Z); free(F2);
     return rc;
 }
 
@@ -563,7 +669,9 @@ int ro_solve_dynamics_trains(const ro_design *d, int nH, const int *spec, const 
     cplx *F_BEM = malloc(sizeof(cplx) * 6 * nw), *F_iner = malloc(sizeof(cplx) * 6 * nw), *u = malloc(sizeof(cplx) * (size_t)Ns * 3 * nw);
     cplx *XiLast = malloc(sizeof(cplx) * 6 * nw), *Xi = malloc(sizeof(cplx) * 6 * nw), *F_drag = malloc(sizeof(cplx) * 6 * nw);
     double B_drag[6][6];
+    double *F2 = malloc(sizeof(double) * 6 * nw);
     ro_calc_hydro_excitation(d, spec[0], Hs[0], Tp[0], gamma[0], beta_deg[0], zeta, F_BEM, F_iner, u);
+    second_order_force(d, spec[0], Hs[0], Tp[0], gamma[0], beta_deg[0], F2, NULL);
     for (int i = 0; i < 6 * nw; i++) XiLast[i] = XiStart;
     for (int iiter = 0; iiter < nIter + 1; iiter++) {
         hydro_linearization(d, u, XiLast, Bmat, B_drag, F_drag);
@@ -578,7 +686,7 @@ int ro_solve_dynamics_trains(const ro_design *d, int nH, const int *spec, const 
                     B += B_drag[a][c];
                     A[6 * a + c] = -wv * wv * M + I * wv * B + d->C0[6 * a + c];
                 }
-                b[a] = (F_BEM[a * nw + ii] + F_iner[a * nw + ii]) + F_drag[a * nw + ii];
+                b[a] = ((F_BEM[a * nw + ii] + F_iner[a * nw + ii]) + F2[a * nw + ii]) + F_drag[a * nw + ii];
             }
             ro_zgesv(6, A, b);
             for (int a = 0; a < 6; a++) Xi[a * nw + ii] = b[a];
@@ -591,6 +699,7 @@ int ro_solve_dynamics_trains(const ro_design *d, int nH, const int *spec, const 
     for (int ih = 1; ih < nH; ih++) {
         rc = ro_calc_hydro_excitation(d, spec[ih], Hs[ih], Tp[ih], gamma[ih], beta_deg[ih], zeta, F_BEM, F_iner, u);
         if (rc) break;
+        second_order_force(d, spec[ih], Hs[ih], Tp[ih], gamma[ih], beta_deg[ih], F2, NULL);   /* :1210-1211 */
         drag_excitation(d, u, Bmat, F_drag);
         cplx *Xo = Xi_out + (size_t)ih * 6 * nw;
         for (int ii = 0; ii < nw; ii++) {
@@ -599,12 +708,12 @@ int ro_solve_dynamics_trains(const ro_design *d, int nH, const int *spec, const 
             if (ro_zinv(6, A, Ai)) { for (int a = 0; a < 6; a++) Xo[a * nw + ii] = NAN; continue; }
             for (int a = 0; a < 6; a++) {
                 cplx s = 0;
-                for (int c = 0; c < 6; c++) s += Ai[6 * a + c] * ((F_BEM[c * nw + ii] + F_iner[c * nw + ii]) + F_drag[c * nw + ii]);
+                for (int c = 0; c < 6; c++) s += Ai[6 * a + c] * (((F_BEM[c * nw + ii] + F_iner[c * nw + ii]) + F_drag[c * nw + ii]) + F2[c * nw + ii]);
                 Xo[a * nw + ii] = s;
             }
         }
     }
-    free(Z); free(zeta); free(Bmat); free(F_BEM); free(F_iner); free(u); free(XiLast); free(Xi); free(F_drag);
+    free(Z); free(zeta); free(Bmat); free(F_BEM); free(F_iner); free(u); free(XiLast); free(Xi); free(F_drag); free(F2);
     return rc;
 }
 

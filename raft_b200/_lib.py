@@ -24,6 +24,8 @@ class RaftkDesigns(C.Structure):
         ("M0", C.c_void_p), ("B0", C.c_void_p), ("C0", C.c_void_p), ("A_w", C.c_void_p), ("B_w", C.c_void_p),
         ("n_bem_head", C.c_int32), ("_pad0", C.c_int32),
         ("bem_headings", C.c_void_p), ("X_BEM", C.c_void_p), ("bem_xyh", C.c_void_p),
+        ("n_qtf_w", C.c_int32), ("n_qtf_head", C.c_int32), ("qtf_shared", C.c_int32), ("_pad2", C.c_int32),
+        ("qtf_w", C.c_void_p), ("qtf_heads", C.c_void_p), ("qtf", C.c_void_p),
     ]
 
 
@@ -31,7 +33,7 @@ class RaftkCases(C.Structure):
     _fields_ = [
         ("n_cases", C.c_int32), ("_pad0", C.c_int32),
         ("Hs", C.c_void_p), ("Tp", C.c_void_p), ("gamma", C.c_void_p), ("beta_deg", C.c_void_p),
-        ("spec", C.c_void_p), ("zeta", C.c_void_p), ("primary", C.c_void_p),
+        ("spec", C.c_void_p), ("zeta", C.c_void_p), ("primary", C.c_void_p), ("F_2nd", C.c_void_p),
     ]
 
 
@@ -41,7 +43,8 @@ class RaftkSolveOpts(C.Structure):
 
 class RaftkOutputs(C.Structure):
     _fields_ = [("Xi", C.c_void_p), ("status", C.c_void_p), ("B_drag", C.c_void_p), ("F_drag", C.c_void_p),
-                ("F_iner", C.c_void_p), ("F_BEM", C.c_void_p), ("zeta", C.c_void_p)]
+                ("F_iner", C.c_void_p), ("F_BEM", C.c_void_p), ("zeta", C.c_void_p),
+                ("F_2nd", C.c_void_p), ("F_2nd_mean", C.c_void_p)]
 
 
 # every symbol include/raftk.h declares (tests/test_abi.py checks the header against this list)
@@ -50,6 +53,7 @@ SYMBOLS = [
     "raftk_workspace_bytes", "raftk_solve_workspace_bytes",
     "raftk_hydro_excitation_dev", "raftk_hydro_linearization_dev", "raftk_solve_dynamics_dev",
     "raftk_hydro_excitation_host", "raftk_hydro_linearization_host", "raftk_solve_dynamics_host",
+    "raftk_second_order_force_dev", "raftk_second_order_force_host",
     "raftk_system_solve_dev", "raftk_system_solve_host", "raftk_response_stats_dev", "raftk_response_stats_host", "raftk_host_alloc", "raftk_host_free",
     "raftk_fp64_peak_gflops",
 ]
@@ -82,6 +86,8 @@ def _load():
     lib.raftk_hydro_excitation_host.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkOutputs)]
     lib.raftk_hydro_linearization_host.argtypes = [P(RaftkDesigns), P(RaftkCases), C.c_void_p, P(RaftkOutputs)]
     lib.raftk_solve_dynamics_host.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkSolveOpts), P(RaftkOutputs)]
+    lib.raftk_second_order_force_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkOutputs), C.c_void_p]
+    lib.raftk_second_order_force_host.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkOutputs)]
     lib.raftk_system_solve_dev.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.raftk_system_solve_host.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.raftk_response_stats_dev.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -95,7 +101,8 @@ def _load():
     lib.raftk_fp64_peak_gflops.argtypes = [C.c_int]
     for fn in ("raftk_hydro_excitation_dev", "raftk_hydro_linearization_dev", "raftk_solve_dynamics_dev",
                "raftk_hydro_excitation_host", "raftk_hydro_linearization_host", "raftk_solve_dynamics_host",
-               "raftk_system_solve_dev", "raftk_system_solve_host"):
+               "raftk_system_solve_dev", "raftk_system_solve_host",
+               "raftk_second_order_force_dev", "raftk_second_order_force_host"):
         getattr(lib, fn).restype = C.c_int
     return lib
 

@@ -8,6 +8,9 @@ is not vendored in the reference -- its readers' contract is pinned by the refer
 
 Output layouts are the reference's: ``A_BEM, B_BEM [6,6,nw]``, ``X_BEM [nhead,6,nw]`` (heading-relative),
 ``BEM_headings [nhead]`` in degrees, ascending in [0, 360).
+
+Second order: ``read_qtf`` restates ``FOWT.readQTF`` (raft_fowt.py:2081-2128) for WAMIT ``.12d`` difference-frequency
+QTF files (potSecOrder 2).
 """
 import numpy as np
 
@@ -114,3 +117,30 @@ def read_hydro_files(hydro_path, w, **kw):
     A, B, w1 = read_wamit1(hydro_path + ".1", TFlag=True)
     _, _, Re, Im, w3, heads = read_wamit3(hydro_path + ".3", TFlag=True)
     return read_hydro(A, B, w1, Re, Im, w3, heads, w, **kw)
+
+
+def read_qtf(path, rho=1025.0, g=9.81, ULEN=1.0):
+    """WAMIT ``.12d`` difference-frequency QTF (FOWT.readQTF, raft_fowt.py:2081-2128): rows
+    ``T1 T2 head1 head2 dof |F| phase Re Im``, one triangle of the Hermitian matrix.
+    -> qtf complex [nw1, nw2, nheads, 6] (dimensionalised by rho g ULEN, moments by a further ULEN, other triangle
+    filled with the conjugate), w [nw1] rad/s ascending, heads [nheads] rad ascending.
+    Only unidirectional tables (head1 == head2) with identical frequency columns, as the reference."""
+    rows = np.loadtxt(path, ndmin=2)
+    rows[:, 0:2] = 2.0 * np.pi / rows[:, 0:2]                       # periods -> rad/s (:2095)
+    if not (rows[:, 2] == rows[:, 3]).all():
+        raise ValueError("Only unidirectional QTFs are supported for now.")                      # :2099
+    heads_deg = np.unique(rows[:, 2])
+    w1, w2 = np.unique(rows[:, 0]), np.unique(rows[:, 1])
+    if len(w1) != len(w2) or not (w1 == w2).all():
+        raise ValueError("Both frequency columns in the input QTF must contain the same values.")  # :2110
+    i1, i2 = np.searchsorted(w1, rows[:, 0]), np.searchsorted(w2, rows[:, 1])
+    ih = np.searchsorted(heads_deg, rows[:, 2])
+    idof = np.round(rows[:, 4] - 1).astype(int)
+    factor = np.where(idof >= 3, rho * g * ULEN * ULEN, rho * g * ULEN)
+    val = factor * (rows[:, 7] + 1j * rows[:, 8])
+    qtf = np.zeros([len(w1), len(w2), len(heads_deg), 6], dtype=complex)
+    for r in range(len(rows)):                                      # row order matters when a file repeats an entry
+        qtf[i1[r], i2[r], ih[r], idof[r]] = val[r]
+        if i1[r] != i2[r]:
+            qtf[i2[r], i1[r], ih[r], idof[r]] = np.conj(val[r])      # :2127-2128
+    return qtf, w1, heads_deg * 0.017453292519943295

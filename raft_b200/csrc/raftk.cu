@@ -104,6 +104,7 @@ extern "C" long long raftk_launch_count(void) { return g_launches; }
 #include "raftk_common.cuh"
 #include "raftk_tables.cuh"
 #include "raftk_fused.cuh"
+#include "raftk_qtf.cuh"
 #include "raftk_misc.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -130,7 +131,7 @@ static CasesDev to_dev(const raftk_cases *c)
 {
     CasesDev C;
     C.nC = c->n_cases; C.Hs = c->Hs; C.Tp = c->Tp; C.gamma = c->gamma; C.beta_deg = c->beta_deg;
-    C.zeta_in = c->zeta; C.spec = c->spec; C.primary = c->primary;
+    C.zeta_in = c->zeta; C.spec = c->spec; C.primary = c->primary; C.F_2nd = c->F_2nd;
     return C;
 }
 
@@ -167,6 +168,56 @@ static int validate(const raftk_designs *d, const raftk_cases *c)
     if (d->max_members > 512 || d->max_nodes > 4096) return set_err(RAFTK_EINVAL, "design too large for the shared-memory tables");
     if ((d->node_in_p1_w == nullptr) != (d->node_in_p2_w == nullptr)) return set_err(RAFTK_EINVAL, "node_in_p1_w / node_in_p2_w must both be given or both NULL");
     return 0;
+}
+
+// ---- second-order forces from the designs' QTF table -------------------------------------------------
+static int validate_qtf(const raftk_designs *d, const raftk_cases *c)
+{
+    if (!d || !c) return set_err(RAFTK_EINVAL, "null designs/cases");
+    if (d->n_designs <= 0 || d->nw <= 0 || c->n_cases <= 0) return set_err(RAFTK_EINVAL, "empty batch (n_designs, nw, n_cases must be > 0)");
+    if (d->n_qtf_w < 2 || d->n_qtf_head < 1 || !d->qtf || !d->qtf_w || !d->qtf_heads)
+        return set_err(RAFTK_EINVAL, "designs carry no QTF table (n_qtf_w >= 2, n_qtf_head >= 1, qtf, qtf_w, qtf_heads)");
+    if ((size_t)d->nw * 20 > 227 * 1024) return set_err(RAFTK_EINVAL, "nw too large for the second-order force kernel's shared-memory tables");
+    return 0;
+}
+
+static int run_qtf(const raftk_designs *d, const raftk_cases *c, double *F2, double *F2mean, cudaStream_t st)
+{
+    int rc = validate_qtf(d, c);
+    if (rc) return rc;
+    if (!F2) return set_err(RAFTK_EINVAL, "second-order force needs the F_2nd buffer");
+    CasesDev C = to_dev(c);
+    QtfParams P;
+    P.nD = d->n_designs; P.shared = d->qtf_shared ? 1 : 0;
+    P.n2 = d->n_qtf_w; P.nh = d->n_qtf_head; P.nw = d->nw; P.dw = d->dw;
+    P.w = d->w; P.qw = d->qtf_w; P.qh = d->qtf_heads;
+    P.qtf = reinterpret_cast<const double2 *>(d->qtf);
+    P.F2 = F2; P.F2mean = F2mean;
+    const size_t smem = (size_t)d->nw * 20;
+    static std::mutex mu;
+    static size_t smem_set = 48 * 1024;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (smem > smem_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_qtf_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_qtf_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+        }
+    }
+    const int ntasks = d->nw / 2 + 1, per_cta = (QTF_THREADS / 32) * QTF_TASKS_PER_WARP;
+    dim3 grid((ntasks + per_cta - 1) / per_cta, c->n_cases, P.shared ? 1 : d->n_designs);
+    if (grid.y > 65535u || grid.z > 65535u) return set_err(RAFTK_EINVAL, "second-order force: more than 65535 cases or designs per call");
+    if (P.nh > 1) k_qtf_force<true><<<grid, QTF_THREADS, smem, st>>>(C, P);
+    else k_qtf_force<false><<<grid, QTF_THREADS, smem, st>>>(C, P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RAFTK_OK;
+}
+
+extern "C" int raftk_second_order_force_dev(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out, void *stream)
+{
+    if (!out || !out->F_2nd) return set_err(RAFTK_EINVAL, "outputs.F_2nd is required");
+    return run_qtf(d, c, out->F_2nd, out->F_2nd_mean, (cudaStream_t)stream);
 }
 
 static int pick_cluster(int units, int nw, int requested)
@@ -436,6 +487,14 @@ extern "C" int raftk_solve_dynamics_dev(const raftk_designs *d, const raftk_case
                                         const raftk_outputs *out, void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!out || !out->Xi || !out->status || !o) return set_err(RAFTK_EINVAL, "Xi, status and opts are required");
+    if (d && c && d->n_qtf_w > 0 && !c->F_2nd) {          // potSecOrder 2: the solve computes the force itself (raft_model.py:1035-1038)
+        if (!out->F_2nd) return set_err(RAFTK_EINVAL, "designs carry a QTF: pass outputs.F_2nd as the buffer, or cases.F_2nd precomputed");
+        int rc = run_qtf(d, c, out->F_2nd, out->F_2nd_mean, (cudaStream_t)stream);
+        if (rc) return rc;
+        raftk_cases cc = *c;
+        cc.F_2nd = out->F_2nd;
+        return run(d, &cc, o, out, nullptr, 0, true, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
     return run(d, c, o, out, nullptr, 0, true, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -531,6 +590,11 @@ static size_t in_bytes(const raftk_designs *d, const raftk_cases *c)
     for (int t = 0; t < 4; t++) add(nC * 8);
     add(nC * 4); add(nC * 4);
     if (c->zeta) add(nC * nw * 8);
+    if (c->F_2nd) add(nD * nC * 6 * nw * 8);
+    if (d->n_qtf_w > 0) {
+        add((size_t)d->n_qtf_w * 8); add((size_t)d->n_qtf_head * 8);
+        add((d->qtf_shared ? 1 : nD) * (size_t)d->n_qtf_w * d->n_qtf_w * d->n_qtf_head * 96);
+    }
     return b;
 }
 
@@ -547,6 +611,8 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     auto oadd = [&](const void *p, size_t n) { if (p) obytes += align_up(n, 256); };
     oadd(out->Xi, resp); oadd(out->status, nD * nC * 16); oadd(out->B_drag, nD * nC * 288); oadd(out->F_drag, resp);
     oadd(out->F_iner, resp); oadd(out->F_BEM, resp); oadd(out->zeta, nC * nw * 8);
+    const bool qtf_solve = (mode == 0 && d->n_qtf_w > 0 && !c->F_2nd);   // potSecOrder 2: compute the force on the device first
+    if (qtf_solve) obytes += align_up(resp / 2, 256) + align_up(nD * nC * 48, 256);
     if (Xi_in) obytes += align_up(resp, 256);
     size_t wb = raftk_workspace_bytes(d, (int32_t)nC);
     if (mode != 0) wb = chunk_bytes((int)nD, (int)nC, d->max_nodes, (int)nw);   // single chunk required
@@ -583,6 +649,12 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     cc.beta_deg = up(A, c->beta_deg, nC, st, e); cc.spec = up(A, c->spec, nC, st, e);
     cc.zeta = up(A, c->zeta, nC * nw, st, e);
     cc.primary = up(A, c->primary, c->primary ? nC : 0, st, e);
+    cc.F_2nd = up(A, c->F_2nd, c->F_2nd ? nD * nC * 6 * nw : 0, st, e);
+    if (d->n_qtf_w > 0) {
+        dd.qtf_w = up(A, d->qtf_w, (size_t)d->n_qtf_w, st, e);
+        dd.qtf_heads = up(A, d->qtf_heads, (size_t)d->n_qtf_head, st, e);
+        dd.qtf = up(A, d->qtf, (d->qtf_shared ? 1 : nD) * (size_t)d->n_qtf_w * d->n_qtf_w * d->n_qtf_head * 12, st, e);
+    }
     const double *Xi_in_d = up(A, Xi_in, Xi_in ? nD * nC * 6 * nw * 2 : 0, st, e);
     {
         cudaError_t r = flush_small(A, st);
@@ -598,6 +670,13 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     if (out->F_iner) od.F_iner = static_cast<double *>(A.take(resp));
     if (out->F_BEM) od.F_BEM = static_cast<double *>(A.take(resp));
     if (out->zeta) od.zeta = static_cast<double *>(A.take(nC * nw * 8));
+    if (qtf_solve) {
+        od.F_2nd = static_cast<double *>(A.take(resp / 2));
+        od.F_2nd_mean = static_cast<double *>(A.take(nD * nC * 48));
+        rc = run_qtf(&dd, &cc, od.F_2nd, od.F_2nd_mean, st);
+        if (rc) return rc;
+        cc.F_2nd = od.F_2nd;
+    }
     void *ws = A.take(wb);
     if (mode == 0) rc = run(&dd, &cc, o, &od, nullptr, 0, true, ws, wb, st);
     else if (mode == 2) rc = run(&dd, &cc, nullptr, &od, nullptr, 2, true, ws, wb, st);
@@ -610,6 +689,7 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     down(out->Xi, od.Xi, resp); down(out->status, od.status, nD * nC * 16); down(out->B_drag, od.B_drag, nD * nC * 288);
     down(out->F_drag, od.F_drag, resp); down(out->F_iner, od.F_iner, resp); down(out->F_BEM, od.F_BEM, resp);
     down(out->zeta, od.zeta, nC * nw * 8);
+    down(out->F_2nd, od.F_2nd, resp / 2); down(out->F_2nd_mean, od.F_2nd_mean, nD * nC * 48);
     cudaError_t se = cudaStreamSynchronize(st);
     if (e != cudaSuccess || se != cudaSuccess)
         return set_err(RAFTK_ECUDA, "kernel/D2H: %s", cudaGetErrorString(se != cudaSuccess ? se : e));
@@ -629,6 +709,45 @@ extern "C" int raftk_solve_dynamics_host(const raftk_designs *d, const raftk_cas
 {
     if (!out || !out->Xi || !out->status || !o) return set_err(RAFTK_EINVAL, "Xi, status and opts are required");
     return host_run(d, c, o, out, nullptr, 0);
+}
+
+extern "C" int raftk_second_order_force_host(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out)
+{
+    if (!out || !out->F_2nd) return set_err(RAFTK_EINVAL, "outputs.F_2nd is required");
+    int rc = validate_qtf(d, c);
+    if (rc) return rc;
+    const size_t nD = d->n_designs, nw = d->nw, nC = c->n_cases, n2 = d->n_qtf_w, nh = d->n_qtf_head;
+    const size_t qb = (d->qtf_shared ? 1 : nD) * n2 * n2 * nh * 96, fb = nD * nC * 6 * nw * 8, mb = nD * nC * 48;
+    // one temporary block: grid, table axes, table, case columns, (zeta), outputs
+    size_t total = 0;
+    auto take = [&](size_t n) { size_t o = total; total += align_up(n, 256); return o; };
+    const size_t o_w = take(nw * 8), o_qw = take(n2 * 8), o_qh = take(nh * 8), o_q = take(qb);
+    const size_t o_hs = take(nC * 8), o_tp = take(nC * 8), o_ga = take(nC * 8), o_be = take(nC * 8), o_sp = take(nC * 4);
+    const size_t o_ze = take(c->zeta ? nC * nw * 8 : 0), o_f = take(fb), o_m = take(mb);
+    char *base = nullptr;
+    CUDA_TRY(cudaMalloc(&base, total));
+    cudaError_t e = cudaSuccess;
+    auto h2d = [&](size_t off, const void *h, size_t n) { if (h && n) { cudaError_t r = cudaMemcpy(base + off, h, n, cudaMemcpyHostToDevice); if (r != cudaSuccess) e = r; } };
+    h2d(o_w, d->w, nw * 8); h2d(o_qw, d->qtf_w, n2 * 8); h2d(o_qh, d->qtf_heads, nh * 8); h2d(o_q, d->qtf, qb);
+    h2d(o_hs, c->Hs, nC * 8); h2d(o_tp, c->Tp, nC * 8); h2d(o_ga, c->gamma, nC * 8); h2d(o_be, c->beta_deg, nC * 8);
+    h2d(o_sp, c->spec, nC * 4); h2d(o_ze, c->zeta, c->zeta ? nC * nw * 8 : 0);
+    raftk_designs dd = *d;
+    dd.w = reinterpret_cast<double *>(base + o_w); dd.qtf_w = reinterpret_cast<double *>(base + o_qw);
+    dd.qtf_heads = reinterpret_cast<double *>(base + o_qh); dd.qtf = reinterpret_cast<double *>(base + o_q);
+    raftk_cases cc = *c;
+    cc.Hs = reinterpret_cast<double *>(base + o_hs); cc.Tp = reinterpret_cast<double *>(base + o_tp);
+    cc.gamma = reinterpret_cast<double *>(base + o_ga); cc.beta_deg = reinterpret_cast<double *>(base + o_be);
+    cc.spec = reinterpret_cast<int32_t *>(base + o_sp);
+    cc.zeta = c->zeta ? reinterpret_cast<double *>(base + o_ze) : nullptr;
+    cc.primary = nullptr; cc.F_2nd = nullptr;
+    if (e == cudaSuccess) rc = run_qtf(&dd, &cc, reinterpret_cast<double *>(base + o_f), reinterpret_cast<double *>(base + o_m), nullptr);
+    if (e == cudaSuccess && !rc) {
+        e = cudaMemcpy(out->F_2nd, base + o_f, fb, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && out->F_2nd_mean) e = cudaMemcpy(out->F_2nd_mean, base + o_m, mb, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(base);
+    if (e != cudaSuccess) return set_err(RAFTK_ECUDA, "second-order force: %s", cudaGetErrorString(e));
+    return rc;
 }
 
 extern "C" int raftk_system_solve_host(int32_t n, int32_t nw, int32_t nrhs, double *Z, double *F, int32_t *info)

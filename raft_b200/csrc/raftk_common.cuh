@@ -26,6 +26,7 @@ struct CasesDev {
     const double *Hs, *Tp, *gamma, *beta_deg, *zeta_in;
     const int *spec;
     const int *primary;     // [nC] or NULL: case whose drag linearisation this case reuses (secondary wave trains)
+    const double *F_2nd;    // [nD][nC][6][nw] real second-order force amplitudes added to F_BEM + F_iner, or NULL
 };
 
 struct Work {          // workspace views for one chunk of designs [d0, d0+nDc)

@@ -319,6 +319,10 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         } else if (P.Fbem_out) {
             for (int a = 0; a < 6; a++) P.Fbem_out[ogl + (size_t)a * nw + i] = make_double2(0.0, 0.0);
         }
+        if (Cs.F_2nd) {                                  // difference-frequency force amplitudes (raft_model.py:1048, :1212)
+#pragma unroll
+            for (int a = 0; a < 6; a++) Fr[a] += Cs.F_2nd[ogl + (size_t)a * nw + i];
+        }
 #pragma unroll
         for (int a = 0; a < 6; a++) {
             if (P.F0g) P.F0g[ogl + (size_t)a * nw + i] = make_double2(Fr[a], Fi[a]);

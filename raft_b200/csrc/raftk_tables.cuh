@@ -48,17 +48,22 @@ __device__ __forceinline__ double jonswap(double w, double Hs, double Tp, double
     return 0.5 / CUDART_PI * C * 0.3125 * Hs * Hs * fpOvrf4 / f * exp(-1.25 * fpOvrf4) * pow(Gamma, Alpha);
 }
 
+// wave spectrum of one case at one frequency (raft_fowt.py:1758-1772); explicit amplitudes: S = zeta^2 / (2 dw)
+__device__ __forceinline__ double sea_state_S(const CasesDev &Cs, int c, int i, int nw, double w, double dw)
+{
+    if (Cs.zeta_in) { const double z = Cs.zeta_in[(size_t)c * nw + i]; return z * z / (2.0 * dw); }
+    const int spec = Cs.spec[c];
+    if (spec == RAFTK_SPEC_JONSWAP) return jonswap(w, Cs.Hs[c], Cs.Tp[c], Cs.gamma[c]);
+    if (spec == RAFTK_SPEC_UNIT) return 1.0;
+    if (spec == RAFTK_SPEC_CONSTANT) return Cs.Hs[c];
+    return 0.0;
+}
+
 // wave amplitude of one case at one frequency: explicit table or spectrum -> zeta = sqrt(2 S dw) (raft_fowt.py:1759-1774)
 __device__ __forceinline__ double sea_state_zeta(const CasesDev &Cs, int c, int i, int nw, double w, double dw)
 {
     if (Cs.zeta_in) return Cs.zeta_in[(size_t)c * nw + i];
-    const int spec = Cs.spec[c];
-    double S;
-    if (spec == RAFTK_SPEC_JONSWAP) S = jonswap(w, Cs.Hs[c], Cs.Tp[c], Cs.gamma[c]);
-    else if (spec == RAFTK_SPEC_UNIT) S = 1.0;
-    else if (spec == RAFTK_SPEC_CONSTANT) S = Cs.Hs[c];
-    else S = 0.0;
-    return sqrt(2.0 * S * dw);
+    return sqrt(2.0 * sea_state_S(Cs, c, i, nw, w, dw) * dw);
 }
 
 // BEM excitation of design d at frequency i for heading beta: bracket the heading in the (heading-relative)
@@ -195,7 +200,10 @@ __global__ void __launch_bounds__(128) k_excitation(DesignsDev D, CasesDev Cs, W
     if (O.F_BEM)
         for (int a = 0; a < 6; a++) O.F_BEM[ogl + (size_t)a * nw + i] = make_double2(Br[a], Bi[a]);
     double2 *F0 = W.F0 + unit * 6 * nw;
-    for (int a = 0; a < 6; a++) F0[(size_t)a * nw + i] = make_double2(Br[a] + Fr[a], Bi[a] + Fi[a]);
+    for (int a = 0; a < 6; a++) {
+        const double f2 = Cs.F_2nd ? Cs.F_2nd[ogl + (size_t)a * nw + i] : 0.0;      // raft_model.py:1048
+        F0[(size_t)a * nw + i] = make_double2((Br[a] + Fr[a]) + f2, Bi[a] + Fi[a]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ import copy
 
 import numpy as np
 
-from . import grid, packer, solver
+from . import bem, grid, packer, solver
 from .member import Member
 
 _MATS6 = ("M_struc", "B_struc", "C_struc", "C_hydro", "C_moor", "C_elast")
@@ -57,8 +57,23 @@ class FOWT:
                 self.memberList.append(Member(mi, self.nw, heading=float(h) + self.heading_adjust, part_of="platform"))
         self.potMod = any(bool(m.potMod) for m in self.memberList)
         self.potFirstOrder = int(plat.get("potFirstOrder", 0))
-        self.potSecOrder = 0
         mats = dict(matrices or {})
+        # second-order wave loads (raft_fowt.py:409-431): 0 none, 2 external QTF file <hydroPath>.12d (or an injected
+        # table matrices['qtf'], ['qtf_w'], ['qtf_heads']); 1 (slender-body QTF) is outside the B200 path
+        self.potSecOrder = int(plat.get("potSecOrder", 0) or 0)
+        self.outFolderQTF = None
+        if self.potSecOrder == 1:
+            raise NotImplementedError("potSecOrder 1 (slender-body QTF, raft_fowt.py:1988) is outside the B200 path")
+        if self.potSecOrder == 2:
+            if "qtf" in mats:
+                self.qtf = np.array(mats["qtf"], dtype=complex)
+                self.w1_2nd = self.w2_2nd = np.array(mats["qtf_w"], dtype=float)
+                self.heads_2nd = np.array(mats["qtf_heads"], dtype=float)
+            else:
+                if "hydroPath" not in plat:
+                    raise Exception("If potSecOrder==2, then hydroPath must be specified in the platform input.")
+                self.qtfPath = plat["hydroPath"] + ".12d"
+                self.readQTF(self.qtfPath)
         for nm in _MATS6:
             setattr(self, nm, np.array(mats.get(nm, np.zeros([6, 6])), dtype=float))
         self.A_BEM = np.array(mats.get("A_BEM", np.zeros([6, 6, self.nw])), dtype=float)
@@ -118,6 +133,25 @@ class FOWT:
         self.F_BEM = out["F_BEM"][0]
         self.F_hydro_iner = out["F_iner"][0]
         return self.F_hydro_iner
+
+    # raft_fowt.py:2081-2128 -------------------------------------------------------------------------------
+    def readQTF(self, flPath, ULEN=1):
+        """Read a WAMIT .12d QTF file into self.qtf [nw1,nw2,nheads,6], self.w1_2nd, self.w2_2nd, self.heads_2nd."""
+        self.qtf, self.w1_2nd, self.heads_2nd = bem.read_qtf(flPath, rho=self.rho_water, g=self.g, ULEN=ULEN)
+        self.w2_2nd = self.w1_2nd.copy()
+        self._batch = None
+
+    # raft_fowt.py:2158-2253 -------------------------------------------------------------------------------
+    def calcHydroForce_2ndOrd(self, beta, S0, iCase=None, iWT=None, interpMode="qtf"):
+        """Difference-frequency force amplitudes from the QTF table on the GPU: ``beta`` [rad], ``S0`` [nw] wave
+        spectrum -> (f_mean [6], f [6,nw] real).  Only the reference's default ``interpMode='qtf'``."""
+        if interpMode != "qtf":
+            raise NotImplementedError("only interpMode='qtf' (the reference's default) is on the B200 path")
+        S0 = np.asarray(S0, dtype=float)
+        one = solver.CaseTable(dict(Hs=[0.0], Tp=[1.0], gamma=[0.0], beta_deg=[float(beta) * 57.29577951308232], spec=[0]),
+                               zeta=np.sqrt(2.0 * S0 * self.dw)[None, :])
+        out = solver.second_order_force(self._get_batch(), one)
+        return out["F_2nd_mean"][0, 0], out["F_2nd"][0, 0]
 
     # raft_fowt.py:1891-1957 -------------------------------------------------------------------------------
     def calcHydroLinearization(self, Xi):

@@ -93,6 +93,8 @@ class Model:
         nC = len(cases)
         batch = solver.DesignBatch([f.pack() for f in self.fowtList])
         want = ("Xi", "status", "B_drag", "F_drag", "F_iner", "F_BEM", "zeta")
+        if batch.n_qtf_w:                                                   # potSecOrder 2 (raft_model.py:1035-1038)
+            want += ("F_2nd", "F_2nd_mean")
         o = solver.solve_dynamics(batch, ct, n_iter=self.nIter, tol=tol, xi_start=self.XiStart, want=want)
         if "primary" in table:                                              # secondary trains share their primary's B_drag
             o["B_drag"] = o["B_drag"][:, table["primary"]]
@@ -104,6 +106,12 @@ class Model:
             P = f.pack()
             f.B_hydro_drag, f.F_hydro_drag = o["B_drag"][i, -1], o["F_drag"][i, -1]
             f.zeta, f.F_BEM, f.F_hydro_iner = o["zeta"][-1:], o["F_BEM"][i, -1:], o["F_iner"][i, -1:]
+            last = np.nonzero(owner == nC - 1)[0]                           # the trains of the last case
+            f.Fhydro_2nd = np.zeros([len(last), 6, self.nw], dtype=complex)
+            f.Fhydro_2nd_mean = np.zeros([len(last), 6])
+            if "F_2nd" in o:
+                f.Fhydro_2nd[:] = o["F_2nd"][i, last]
+                f.Fhydro_2nd_mean[:] = o["F_2nd_mean"][i, last]
             M = P["M0"][:, :, None] + (P["A_w"] if "A_w" in P else 0.0)
             B = (P["B0"] + f.B_hydro_drag)[:, :, None] + (P["B_w"] if "B_w" in P else 0.0)
             f.Z = -w ** 2 * M + 1j * w * B + P["C0"][:, :, None]             # raft_model.py:1086, 1155 (last case)
@@ -127,7 +135,10 @@ class Model:
                 B = (P["B0"] + o["B_drag"][i, c])[:, :, None] + (P["B_w"] if "B_w" in P else 0.0)
                 Zi = np.moveaxis(-w ** 2 * M + 1j * w * B + P["C0"][:, :, None], 2, 0)     # [nw,6,6]
                 Z[:, 6 * i:6 * i + 6, 6 * i:6 * i + 6] = Zi
-                F[:, 6 * i:6 * i + 6] = np.moveaxis(o["F_BEM"][i, c] + o["F_iner"][i, c] + o["F_drag"][i, c], 0, 1)
+                Fi = o["F_BEM"][i, c] + o["F_iner"][i, c] + o["F_drag"][i, c]
+                if "F_2nd" in o:
+                    Fi = Fi + o["F_2nd"][i, c]                              # raft_model.py:1212
+                F[:, 6 * i:6 * i + 6] = np.moveaxis(Fi, 0, 1)
             Z += self.C_array[None, :, :]
             X, info = solver.system_solve(Z, F)
             if np.any(info):

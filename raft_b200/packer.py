@@ -206,7 +206,24 @@ def pack_fowt(fowt, w=None, k=None):
         out.update(bem)
     out.update(w=w, k=k, depth=np.float64(fowt.depth), dw=np.float64(w[1] - w[0]),
                x_ref=np.float64(getattr(fowt, "x_ref", 0.0)), y_ref=np.float64(getattr(fowt, "y_ref", 0.0)))
+    out.update(pack_qtf(fowt))
     return out
+
+
+def pack_qtf(fowt):
+    """External difference-frequency QTF of a FOWT (state left by FOWT.readQTF, raft_fowt.py:2081-2128):
+    ``qtf`` complex [nw1, nw2, nheads, 6] (dimensional, Hermitian-filled), ``qtf_w`` [nw1] rad/s, ``qtf_heads``
+    [nheads] rad.  Empty dict for potSecOrder 0; the slender-body QTF (potSecOrder 1) is not on this path."""
+    sec = int(getattr(fowt, "potSecOrder", 0) or 0)
+    if sec == 0:
+        return {}
+    if sec != 2:
+        raise NotImplementedError("potSecOrder 1 (slender-body QTF, raft_fowt.py:1988) is outside the B200 path")
+    w1, w2 = np.asarray(fowt.w1_2nd, dtype=float), np.asarray(fowt.w2_2nd, dtype=float)
+    if w1.shape != w2.shape or not (w1 == w2).all():
+        raise ValueError("Both frequency columns in the input QTF must contain the same values.")   # raft_fowt.py:2109
+    return dict(qtf=np.ascontiguousarray(fowt.qtf, dtype=np.complex128), qtf_w=w1,
+                qtf_heads=np.asarray(fowt.heads_2nd, dtype=float))
 
 
 SPECTRUM_IDS = {"JONSWAP": 0, "unit": 1, "constant": 2, "none": 3, "still": 3}

@@ -94,6 +94,27 @@ class DesignBatch:
             a["bem_xyh"] = np.ascontiguousarray(np.array(
                 [[float(P.get("x_ref", 0.0)), float(P.get("y_ref", 0.0)), float(P.get("heading_adjust", 0.0))] for P in packed],
                 dtype=_F8))
+        # external QTF (potSecOrder 2): packed [nw1,nw2,nheads,6] per design; one shared table when all designs
+        # carry the same one (a geometry-preserving sweep), else stacked on a design axis
+        self.n_qtf_w = self.n_qtf_head = 0
+        self.qtf_shared = 0
+        have_q = [P.get("qtf") is not None for P in packed]
+        if any(have_q):
+            if not all(have_q):
+                raise ValueError("either all or none of the designs of a batch carry a QTF table")
+            qw, qh = np.ascontiguousarray(P0["qtf_w"], dtype=_F8), np.ascontiguousarray(P0["qtf_heads"], dtype=_F8)
+            for P in packed:
+                if not (np.array_equal(P["qtf_w"], qw) and np.array_equal(P["qtf_heads"], qh)):
+                    raise ValueError("all designs of a batch must share the QTF frequency and heading axes")
+            self.n_qtf_w, self.n_qtf_head = len(qw), len(qh)
+            a["qtf_w"], a["qtf_heads"] = qw, qh
+            if all(P["qtf"] is P0["qtf"] for P in packed):
+                self.qtf_shared = 1
+                a["qtf"] = np.ascontiguousarray(P0["qtf"], dtype=np.complex128)
+            else:
+                a["qtf"] = np.ascontiguousarray(np.stack([np.asarray(P["qtf"], dtype=np.complex128) for P in packed]))
+            if a["qtf"].shape[-4:] != (self.n_qtf_w, self.n_qtf_w, self.n_qtf_head, 6):
+                raise ValueError("qtf must be [nw1, nw2, nheads, 6] with nw1 == nw2 == len(qtf_w)")
         a["w"], a["k"] = self.w, self.k
         self.n_members_total = int(member_offset[-1])
         self.n_nodes_total = int(mem_node_start[-1])
@@ -142,16 +163,18 @@ class DesignBatch:
         for name in ("w", "k", "member_offset", "mem_frame", "mem_rA", "mem_arm", "mem_node_start", "mem_circ",
                      "node_ls", "node_cd_q", "node_cd_p1", "node_cd_p2", "node_in_q", "node_in_p1", "node_in_p2",
                      "node_pa", "node_in_p1_w", "node_in_p2_w", "M0", "B0", "C0", "A_w", "B_w",
-                     "bem_headings", "X_BEM", "bem_xyh"):
+                     "bem_headings", "X_BEM", "bem_xyh", "qtf_w", "qtf_heads", "qtf"):
             setattr(s, name, ptr(name) if name in self.arrays else None)
         s.n_bem_head = self.n_bem_head
+        s.n_qtf_w, s.n_qtf_head, s.qtf_shared = self.n_qtf_w, self.n_qtf_head, self.qtf_shared
         return s
 
 
 class CaseTable:
     """SoA case table (``packer.pack_cases`` dict, or keyword arrays)."""
 
-    def __init__(self, cases, zeta=None):
+    def __init__(self, cases, zeta=None, F_2nd=None):
+        """``F_2nd``: optional real [nD,nC,6,nw] second-order force amplitudes added to the linear excitation."""
         self.arrays = a = {}
         for kname in ("Hs", "Tp", "gamma", "beta_deg"):
             a[kname] = np.ascontiguousarray(cases[kname], dtype=_F8)
@@ -166,6 +189,8 @@ class CaseTable:
             if len(pr) != self.n_cases or np.any(pr < 0) or np.any(pr >= self.n_cases) or np.any(pr[pr] != pr):
                 raise ValueError("primary must map every case to a primary case (primary[primary[c]] == primary[c])")
             a["primary"] = pr
+        if F_2nd is not None:
+            a["F_2nd"] = np.ascontiguousarray(F_2nd, dtype=_F8)
 
     def input_bytes(self):
         return int(sum(v.nbytes for v in self.arrays.values()))
@@ -173,7 +198,7 @@ class CaseTable:
     def struct(self, ptr):
         s = RaftkCases()
         s.n_cases = self.n_cases
-        for name in ("Hs", "Tp", "gamma", "beta_deg", "spec", "zeta", "primary"):
+        for name in ("Hs", "Tp", "gamma", "beta_deg", "spec", "zeta", "primary", "F_2nd"):
             setattr(s, name, ptr(name) if name in self.arrays else None)
         return s
 
@@ -185,13 +210,14 @@ def _host_ptr(arrays):
 def _alloc_outputs(nD, nC, nw, want, alloc=np.zeros):
     shapes = dict(Xi=([nD, nC, 6, nw], np.complex128), status=([nD, nC, 4], _I4), B_drag=([nD, nC, 6, 6], _F8),
                   F_drag=([nD, nC, 6, nw], np.complex128), F_iner=([nD, nC, 6, nw], np.complex128),
-                  F_BEM=([nD, nC, 6, nw], np.complex128), zeta=([nC, nw], _F8))
+                  F_BEM=([nD, nC, 6, nw], np.complex128), zeta=([nC, nw], _F8),
+                  F_2nd=([nD, nC, 6, nw], _F8), F_2nd_mean=([nD, nC, 6], _F8))
     return {k: alloc(shapes[k][0], dtype=shapes[k][1]) for k in want}
 
 
 def _out_struct(outs, ptr):
     o = RaftkOutputs()
-    for k in ("Xi", "status", "B_drag", "F_drag", "F_iner", "F_BEM", "zeta"):
+    for k in ("Xi", "status", "B_drag", "F_drag", "F_iner", "F_BEM", "zeta", "F_2nd", "F_2nd_mean"):
         setattr(o, k, ptr(outs[k]) if k in outs else None)
     return o
 
@@ -202,6 +228,8 @@ def solve_dynamics(batch, cases, n_iter=10, tol=0.01, xi_start=0.0, cluster_size
 
     Returns a dict of NumPy arrays: Xi [nD,nC,6,nw] complex128, status [nD,nC,4] int32
     (passes, converged, flags, 0), B_drag [nD,nC,6,6], and optionally F_drag / F_iner / F_BEM / zeta.
+    Designs that carry a QTF table (potSecOrder 2) get the difference-frequency force added to the linear
+    excitation (raft_model.py:1035-1048); ask for it with ``want`` F_2nd [nD,nC,6,nw] / F_2nd_mean [nD,nC,6].
     """
     want = tuple(dict.fromkeys(tuple(want) + ("Xi", "status")))
     outs = out if out is not None else _alloc_outputs(batch.n_designs, cases.n_cases, batch.nw, want)
@@ -220,6 +248,19 @@ def hydro_excitation(batch, cases, want=("F_iner", "F_BEM", "zeta")):
     c = cases.struct(_host_ptr(cases.arrays))
     os_ = _out_struct(outs, lambda a: a.ctypes.data)
     check(lib.raftk_hydro_excitation_host(C.byref(d), C.byref(c), C.byref(os_)))
+    return outs
+
+
+def second_order_force(batch, cases):
+    """FOWT.calcHydroForce_2ndOrd (raft_fowt.py:2158-2253) for every (design, case) from the designs' QTF table,
+    host buffers -> dict(F_2nd [nD,nC,6,nw] real amplitudes, F_2nd_mean [nD,nC,6])."""
+    if batch.n_qtf_w == 0:
+        raise ValueError("the designs carry no QTF table (potSecOrder 2 / packer.pack_qtf)")
+    outs = _alloc_outputs(batch.n_designs, cases.n_cases, batch.nw, ("F_2nd", "F_2nd_mean"))
+    d = batch.struct(_host_ptr(batch.arrays))
+    c = cases.struct(_host_ptr(cases.arrays))
+    os_ = _out_struct(outs, lambda a: a.ctypes.data)
+    check(lib.raftk_second_order_force_host(C.byref(d), C.byref(c), C.byref(os_)))
     return outs
 
 
@@ -308,8 +349,9 @@ class DeviceSession:
             self.workspace_bytes = int(need if workspace_bytes is None else workspace_bytes)
             self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
             nD, nC, nw = batch.n_designs, cases.n_cases, batch.nw
-            want = tuple(dict.fromkeys(tuple(want) + ("Xi", "status")))
+            want = tuple(dict.fromkeys(tuple(want) + ("Xi", "status") + (("F_2nd", "F_2nd_mean") if batch.n_qtf_w else ())))
             shapes = dict(Xi=([nD, nC, 6, nw], torch.complex128), status=([nD, nC, 4], torch.int32),
+                          F_2nd=([nD, nC, 6, nw], torch.float64), F_2nd_mean=([nD, nC, 6], torch.float64),
                           B_drag=([nD, nC, 6, 6], torch.float64), F_drag=([nD, nC, 6, nw], torch.complex128),
                           F_iner=([nD, nC, 6, nw], torch.complex128), F_BEM=([nD, nC, 6, nw], torch.complex128),
                           zeta=([nC, nw], torch.float64))
@@ -326,6 +368,13 @@ class DeviceSession:
             check(lib.raftk_solve_dynamics_dev(C.byref(self.d_struct), C.byref(self.c_struct), C.byref(o),
                                                C.byref(self.o_struct), self.workspace.data_ptr(), self.workspace_bytes,
                                                self._stream()))
+        return self.out
+
+    def second_order_force(self):
+        """Enqueue FOWT.calcHydroForce_2ndOrd for all units -> out['F_2nd'], out['F_2nd_mean'] (async)."""
+        with self.torch.cuda.device(self.device):
+            check(lib.raftk_second_order_force_dev(C.byref(self.d_struct), C.byref(self.c_struct), C.byref(self.o_struct),
+                                                   self._stream()))
         return self.out
 
     def excitation(self):

@@ -17,7 +17,11 @@ def pytest_configure(config):
 
 def golden_names():
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if n.startswith(("test_", "cfg"))]          # design fixtures (not the raw WAMIT tables)
+    # design fixtures (not the raw WAMIT tables; the second-order fixture has its own tests)
+    return [n for n in names if n.startswith(("test_", "cfg")) and n != QTF_GOLDEN]
+
+
+QTF_GOLDEN = "cfg3q_OC4semi-QTF_nw96"       # potSecOrder 2: external .12d QTF (make_golden.fixture_qtf)
 
 
 def load_golden(name):

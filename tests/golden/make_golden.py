@@ -146,6 +146,62 @@ def fixture(name, yaml_path, nw=None, max_freq=None, solve_cases=(), pickles=Non
                                                              time.time() - t0, os.path.getsize(path) / 1024))
 
 
+def fixture_qtf(name, yaml_path, nw, max_freq, solve_cases, trains):
+    """potSecOrder 2 (external .12d QTF): readQTF state, calcHydroForce_2ndOrd per case, Model.solveDynamics with the
+    second-order force added (raft_model.py:1035-1048, :1210-1212), a multi-train case, and a synthetic 4-heading table
+    (the shipped file has one heading) to exercise the heading interpolation (raft_fowt.py:2178-2187)."""
+    import contextlib
+    import io
+    t0 = time.time()
+    design = rh.load_design(yaml_path, nw=nw, max_freq=max_freq, sec_order=True)
+    assert int(design["platform"]["potSecOrder"]) == 2
+    model = rh.build_model(design)
+    fowt = model.fowtList[0]
+    P = packer.pack_fowt(fowt)
+    out = {"P_" + k: np.asarray(v) for k, v in P.items()}
+    out["n_iter"] = np.int32(int(model.nIter))
+    out["xi_start"] = np.float64(model.XiStart)
+    out["C_moor"] = np.array(fowt.C_moor)
+    out["A_hydro_morison"] = np.array(fowt.A_hydro_morison)
+    cnt, orig = count_passes(fowt)
+    Xi, passes, F2, F2m, S = [], [], [], [], []
+    for (Hs, Tp, beta) in solve_cases:
+        cnt[0] = 0
+        x = rh.solve_dynamics(model, rh.make_case(Hs, Tp, beta))
+        Xi.append(np.array(x[0])), passes.append(cnt[0])
+        F2.append(np.array(fowt.Fhydro_2nd[0].real)), F2m.append(np.array(fowt.Fhydro_2nd_mean[0])), S.append(np.array(fowt.S[0]))
+        assert np.abs(fowt.Fhydro_2nd[0].imag).max() == 0.0
+    fowt.calcHydroLinearization = orig
+    out["ref_run_solve_cases"] = np.array(solve_cases, dtype=float)
+    out["ref_run_solve_Xi"], out["ref_run_solve_passes"] = np.array(Xi), np.array(passes, dtype=np.int32)
+    out["ref_run_F2nd"], out["ref_run_F2nd_mean"], out["ref_run_S"] = np.array(F2), np.array(F2m), np.array(S)
+    case = rh.make_case()
+    case.update(wave_heading=[t[2] for t in trains], wave_period=[t[1] for t in trains], wave_height=[t[0] for t in trains],
+                wave_spectrum=["JONSWAP"] * len(trains), wave_gamma=[0.0] * len(trains))
+    x = rh.solve_dynamics(model, case)
+    out["ref_run_trains"] = np.array(trains, dtype=float)
+    out["ref_run_trains_Xi"] = np.array(x[:len(trains)])
+    out["ref_run_trains_F2nd"] = np.array(fowt.Fhydro_2nd.real)
+    # synthetic multi-heading table: scaled copies of the shipped one
+    scale = np.array([1.0, 0.7 + 0.2j, 1.3, -0.4 + 1.0j])
+    heads = np.deg2rad(np.array([-90.0, 0.0, 45.0, 180.0]))
+    q1 = fowt.qtf[:, :, 0, :]
+    fowt.qtf = np.stack([q1 * s for s in scale], axis=2)
+    fowt.heads_2nd = heads
+    betas = np.array([-120.0, -90.0, -30.0, 0.0, 20.0, 45.0, 100.0, 180.0, 200.0])
+    S0 = out["ref_run_S"][0]
+    f, fm = [], []
+    for b in betas:
+        with contextlib.redirect_stdout(io.StringIO()):
+            a, bb = fowt.calcHydroForce_2ndOrd(b * 0.017453292519943295, S0)
+        fm.append(np.array(a)), f.append(np.array(bb))
+    out["mh_scale"], out["mh_heads"], out["mh_betas_deg"] = scale, heads, betas
+    out["ref_run_mh_F2nd"], out["ref_run_mh_F2nd_mean"] = np.array(f), np.array(fm)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-28s nw=%4d cases=%2d  %.1f s  %.0f KB" % (name, nw, len(solve_cases), time.time() - t0, os.path.getsize(path) / 1024))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -171,6 +227,10 @@ def main():
         if args.only and args.only not in j["name"]:
             continue
         fixture(**j)
+    if not args.only or args.only in "cfg3q_OC4semi-QTF_nw96":
+        Hs, Tp, beta = seeded_cases(5, 3)
+        fixture_qtf("cfg3q_OC4semi-QTF_nw96", os.path.join(REF, "examples", "OC4semi-WAMIT_Coefs.yaml"), nw=96, max_freq=0.256,
+                    solve_cases=list(zip(Hs, Tp, beta)) + [(6.0, 12.0, 30.0)], trains=[(6.0, 12.0, 30.0), (2.5, 7.0, -100.0)])
     if not args.only:
         # raw WAMIT tables of the OC4 semi (reference data files examples/OC4semi-WAMIT_Coefs/marin_semi.1/.3),
         # read with the product reader, so that readHydro can be exercised at any grid size off the build box
@@ -178,8 +238,9 @@ def main():
         hp = os.path.join(REF, "examples", "OC4semi-WAMIT_Coefs", "marin_semi")
         A, B, w1 = bem.read_wamit1(hp + ".1")
         _, _, Re, Im, w3, heads = bem.read_wamit3(hp + ".3")
+        qtf_rows = np.loadtxt(hp + ".12d")                  # raw .12d rows, for the QTF reader test off the build box
         np.savez_compressed(os.path.join(OUT, "wamit_marin_semi.npz"), A=A, B=B, w1=w1, Re=Re.astype(np.float64),
-                            Im=Im.astype(np.float64), w3=w3, heads=heads)
+                            Im=Im.astype(np.float64), w3=w3, heads=heads, qtf_rows=qtf_rows.astype(np.float32))
         print("wamit_marin_semi.npz %.0f KB" % (os.path.getsize(os.path.join(OUT, "wamit_marin_semi.npz")) / 1024))
         import json
         with open(os.path.join(OUT, "designs.json"), "w") as f:

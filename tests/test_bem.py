@@ -46,3 +46,32 @@ def test_read_hydro_vs_reference(name):
     assert relerr(H["B_BEM"], P["B_w"].reshape(6, 6, -1)) < 1e-14
     assert relerr(H["X_BEM"], P["X_BEM"]) < 1e-14
     assert np.array_equal(H["BEM_headings"], P["bem_headings"])
+
+
+def test_qtf_reader_vs_reference_readQTF(tmp_path):
+    """bem.read_qtf on the shipped marin_semi.12d rows == the state FOWT.readQTF left in the reference run."""
+    from conftest import QTF_GOLDEN
+    from raft_b200 import bem
+    rows = np.load(os.path.join(GOLDEN, "wamit_marin_semi.npz"))["qtf_rows"]
+    path = str(tmp_path / "semi.12d")
+    np.savetxt(path, rows, fmt="%.5e")                     # the file carries 6 significant digits
+    qtf, w, heads = bem.read_qtf(path, rho=1025.0, g=9.81)
+    G, P = load_golden(QTF_GOLDEN)
+    assert qtf.shape == P["qtf"].shape == (56, 56, 1, 6)
+    assert np.array_equal(w, P["qtf_w"]) and np.array_equal(heads, P["qtf_heads"])
+    assert np.array_equal(qtf, P["qtf"])
+    off = ~np.eye(56, dtype=bool)                          # Hermitian fill of the other triangle (diagonal as read)
+    assert np.array_equal(qtf[:, :, 0, :][off], np.conj(np.swapaxes(qtf[:, :, 0, :], 0, 1))[off])
+
+
+def test_qtf_reader_errors(tmp_path):
+    from raft_b200 import bem
+    p = str(tmp_path / "bad.12d")
+    with open(p, "w") as f:
+        f.write("10 10 0 30 1 1 0 1 0\n")
+    with pytest.raises(ValueError, match="unidirectional"):
+        bem.read_qtf(p)
+    with open(p, "w") as f:
+        f.write("10 10 0 0 1 1 0 1 0\n10 8 0 0 1 1 0 1 0\n")
+    with pytest.raises(ValueError, match="frequency columns"):
+        bem.read_qtf(p)

@@ -447,3 +447,150 @@ def test_random_designs_vs_oracle(seed, solver, oracle):
     assert np.array_equal(out["status"][0, :, :2], st_o[:, :2]), (out["status"][0], st_o)
     assert np.all(out["status"][0, :, 2] == 0)
     assert response_err(out["Xi"][0], Xi_o) < RTOL
+
+
+# ---- second-order (difference-frequency) forces from an external QTF table: potSecOrder 2 -------------------------
+
+def test_second_order_force_vs_reference_run(solver, oracle):
+    """FOWT.calcHydroForce_2ndOrd for all cases in one launch + Model.solveDynamics with the force added
+    (raft_model.py:1035-1048), vs the unmodified reference run with the shipped marin_semi.12d."""
+    from conftest import QTF_GOLDEN
+    G, P = load_golden(QTF_GOLDEN)
+    cs = G["ref_run_solve_cases"]
+    n = len(cs)
+    table = dict(Hs=cs[:, 0], Tp=cs[:, 1], gamma=np.zeros(n), beta_deg=cs[:, 2], spec=np.zeros(n, dtype=np.int32))
+    b = solver.DesignBatch(P)
+    assert b.n_qtf_w == 56 and b.n_qtf_head == 1 and b.qtf_shared == 1
+    f2 = solver.second_order_force(b, solver.CaseTable(table))
+    assert relerr(f2["F_2nd"][0], G["ref_run_F2nd"]) < RTOL
+    assert relerr(f2["F_2nd_mean"][0], G["ref_run_F2nd_mean"]) < RTOL
+    assert np.all(f2["F_2nd"][0][:, :, -1] == 0.0)
+    # explicit amplitudes instead of a spectrum id: S = zeta^2 / (2 dw)
+    zeta = np.sqrt(2 * G["ref_run_S"] * float(P["dw"]))
+    f2z = solver.second_order_force(b, solver.CaseTable(table, zeta=zeta))
+    assert relerr(f2z["F_2nd"][0], G["ref_run_F2nd"]) < RTOL
+    for cluster in (0, 1, 2):
+        out = solver.solve_dynamics(b, solver.CaseTable(table), n_iter=int(G["n_iter"]), xi_start=float(G["xi_start"]),
+                                    cluster_size=cluster, want=("Xi", "status", "F_2nd", "F_2nd_mean"))
+        assert np.array_equal(out["status"][0, :, 0], G["ref_run_solve_passes"])
+        assert response_err(out["Xi"][0], G["ref_run_solve_Xi"]) < RTOL
+        assert relerr(out["F_2nd"][0], G["ref_run_F2nd"]) < RTOL
+    # device-resident route: the solve computes the force into out['F_2nd'] on the same stream
+    import torch
+    ses = solver.DeviceSession(b, solver.CaseTable(table))
+    o = ses.solve(n_iter=int(G["n_iter"]), xi_start=float(G["xi_start"]), cluster_size=2)
+    torch.cuda.synchronize()
+    assert np.array_equal(o["Xi"].cpu().numpy(), out["Xi"]) and np.array_equal(o["F_2nd"].cpu().numpy(), out["F_2nd"])
+    assert np.array_equal(ses.second_order_force()["F_2nd_mean"].cpu().numpy(), out["F_2nd_mean"])
+    # precomputed force handed in through cases.F_2nd == computed inside the solve; without it the response differs
+    P0 = {k: v for k, v in P.items() if not k.startswith("qtf")}
+    pre = solver.solve_dynamics(solver.DesignBatch(P0), solver.CaseTable(table, F_2nd=f2["F_2nd"]), n_iter=int(G["n_iter"]),
+                                xi_start=float(G["xi_start"]))
+    assert response_err(pre["Xi"][0], out["Xi"][0]) < 1e-13
+    none = solver.solve_dynamics(solver.DesignBatch(P0), solver.CaseTable(table), n_iter=int(G["n_iter"]), xi_start=float(G["xi_start"]))
+    assert response_err(none["Xi"][0], G["ref_run_solve_Xi"]) > 1e-4
+
+
+def test_second_order_heading_interpolation_and_design_axis(solver, oracle):
+    """4-heading synthetic table (interp1d incl. the clamped ends) vs the reference run; two designs with DIFFERENT
+    tables in one batch vs the oracle; a larger grid (odd nw) vs the oracle."""
+    from conftest import QTF_GOLDEN
+    G, P = load_golden(QTF_GOLDEN)
+    Pm = dict(P)
+    Pm["qtf"] = np.stack([P["qtf"][:, :, 0, :] * s for s in G["mh_scale"]], axis=2)
+    Pm["qtf_heads"] = G["mh_heads"]
+    betas = G["mh_betas_deg"]
+    n = len(betas)
+    zeta = np.repeat(np.sqrt(2 * G["ref_run_S"][:1] * float(P["dw"])), n, axis=0)
+    table = dict(Hs=np.ones(n), Tp=np.ones(n), gamma=np.zeros(n), beta_deg=betas, spec=np.zeros(n, dtype=np.int32))
+    f2 = solver.second_order_force(solver.DesignBatch(Pm), solver.CaseTable(table, zeta=zeta))
+    assert relerr(f2["F_2nd"][0], G["ref_run_mh_F2nd"]) < RTOL
+    assert relerr(f2["F_2nd_mean"][0], G["ref_run_mh_F2nd_mean"]) < RTOL
+    # design axis: [single-heading, 4-heading padded to a common axis is not allowed] -> two 4-heading designs
+    Pn = dict(Pm)
+    Pn["qtf"] = Pm["qtf"][:, :, ::-1, :] * (0.5 - 0.25j)
+    b2 = solver.DesignBatch([Pm, Pn])
+    assert b2.qtf_shared == 0
+    cs = sea_states(11, 5)
+    out = solver.solve_dynamics(b2, solver.CaseTable(cs), n_iter=10, want=("Xi", "status", "F_2nd", "F_2nd_mean"))
+    for d, Pd in enumerate((Pm, Pn)):
+        od = oracle.OracleDesign(Pd)
+        Xi_o, st_o, _ = oracle.solve_cases(od, cs, nIter=10)
+        assert np.array_equal(out["status"][d, :, 0], st_o[:, 0])
+        assert response_err(out["Xi"][d], Xi_o) < RTOL
+        for c in range(5):
+            S = oracle.jonswap(Pd["w"], cs["Hs"][c], cs["Tp"][c], 0.0)
+            fm, f = oracle.hydro_force_2nd(od, cs["beta_deg"][c] * 0.017453292519943295, S)
+            assert relerr(out["F_2nd"][d, c], f) < RTOL and relerr(out["F_2nd_mean"][d, c], fm) < RTOL
+    # shared table broadcast over a design axis (same dict object twice)
+    b3 = solver.DesignBatch([Pm, Pm])
+    assert b3.qtf_shared == 1
+    f3 = solver.second_order_force(b3, solver.CaseTable(cs))
+    assert np.array_equal(f3["F_2nd"][0], f3["F_2nd"][1]) and np.array_equal(f3["F_2nd"][0], out["F_2nd"][0])
+
+
+def test_second_order_model_api_from_files(solver, tmp_path):
+    """configs[2] from its shipped files, potFirstOrder 1 + potSecOrder 2: .1/.3 -> readHydro, .12d -> FOWT.readQTF,
+    Model.solveDynamics / analyzeCases incl. a multi-train case, vs the unmodified reference run."""
+    import json, os
+    from conftest import GOLDEN, QTF_GOLDEN
+    from raft_b200 import bem, grid
+    from raft_b200.model import Model
+    G, P = load_golden(QTF_GOLDEN)
+    D = json.load(open(os.path.join(GOLDEN, "designs.json")))["cfg3_OC4semi-WAMIT_nw128"]
+    t = np.load(os.path.join(GOLDEN, "wamit_marin_semi.npz"))
+    np.savetxt(str(tmp_path / "semi.12d"), t["qtf_rows"], fmt="%.5e")
+    nw = len(P["w"])
+    w = grid.make_w(0.256 / nw, 0.256)
+    assert np.array_equal(w, P["w"])
+    H = bem.read_hydro(t["A"], t["B"], t["w1"], t["Re"], t["Im"], t["w3"], t["heads"], w, rho=float(P["rho"]), g=float(P["g"]))
+    plat = dict(D["platform"], potSecOrder=2, hydroPath=str(tmp_path / "semi"))
+    design = dict(D, platform=plat, site=dict(D["site"], water_depth=float(P["depth"])),
+                  settings=dict(D["settings"], min_freq=0.256 / nw, max_freq=0.256))
+    mats = dict(M_struc=P["M0"] - G["A_hydro_morison"], C_struc=P["C0"] - G["C_moor"], C_moor=G["C_moor"], **H)
+    model = Model(design, matrices=mats)
+    f = model.fowtList[0]
+    assert f.potSecOrder == 2 and np.array_equal(f.qtf, P["qtf"])
+    cases = [dict(wave_spectrum="JONSWAP", wave_height=h, wave_period=tp, wave_heading=b) for h, tp, b in G["ref_run_solve_cases"]]
+    res = model.analyzeCases(cases)
+    assert np.array_equal(res["status"][:, 0, 0], G["ref_run_solve_passes"])
+    assert response_err(res["Xi"], G["ref_run_solve_Xi"]) < RTOL
+    assert relerr(f.Fhydro_2nd[0].real, G["ref_run_F2nd"][-1]) < RTOL and relerr(f.Fhydro_2nd_mean[0], G["ref_run_F2nd_mean"][-1]) < RTOL
+    tr = G["ref_run_trains"]
+    case = dict(wave_spectrum=["JONSWAP"] * len(tr), wave_height=list(tr[:, 0]), wave_period=list(tr[:, 1]),
+                wave_heading=list(tr[:, 2]), wave_gamma=[0.0] * len(tr))
+    Xi = model.solveDynamics(case)
+    for ih in range(len(tr)):
+        assert response_err(Xi[ih], G["ref_run_trains_Xi"][ih]) < RTOL, ih
+    assert relerr(f.Fhydro_2nd.real, G["ref_run_trains_F2nd"]) < RTOL
+    # FOWT.calcHydroForce_2ndOrd mirror
+    fm, f2 = f.calcHydroForce_2ndOrd(G["ref_run_solve_cases"][0, 2] * 0.017453292519943295, G["ref_run_S"][0])
+    assert relerr(f2, G["ref_run_F2nd"][0]) < RTOL and relerr(fm, G["ref_run_F2nd_mean"][0]) < RTOL
+
+
+def test_second_order_force_full_grid_properties(solver, oracle):
+    """BASELINE config-3 size (nw = 2048): spot-check a case against the oracle and check size-independent
+    properties -- scaling S by a makes f scale by a (f ~ sqrt(S S)), f_mean by a; zero outside the table's band."""
+    from conftest import QTF_GOLDEN
+    G, P = load_golden(QTF_GOLDEN)
+    nw = 2048
+    w = np.arange(1, nw + 1) * (2 * np.pi * 0.256 / nw)
+    Pb = dict(P, w=w, k=w ** 2 / 9.81, dw=w[1] - w[0])
+    for key in ("A_w", "B_w", "X_BEM", "bem_headings"):
+        Pb.pop(key, None)
+    b = solver.DesignBatch(Pb)
+    cs = sea_states(3, 6)
+    f = solver.second_order_force(b, solver.CaseTable(cs))
+    od = oracle.OracleDesign(Pb)
+    S = oracle.jonswap(w, cs["Hs"][2], cs["Tp"][2], 0.0)
+    fm_o, f_o = oracle.hydro_force_2nd(od, cs["beta_deg"][2] * 0.017453292519943295, S)
+    assert relerr(f["F_2nd"][0, 2], f_o) < RTOL and relerr(f["F_2nd_mean"][0, 2], fm_o) < RTOL
+    zeta = np.sqrt(2 * S * (w[1] - w[0]))
+    one = dict(Hs=[1.0, 1.0], Tp=[1.0, 1.0], gamma=[0.0, 0.0], beta_deg=[0.0, 0.0], spec=np.zeros(2, dtype=np.int32))
+    fz = solver.second_order_force(b, solver.CaseTable(one, zeta=np.stack([zeta, 2.0 * zeta])))
+    assert relerr(fz["F_2nd"][0, 1], 4.0 * fz["F_2nd"][0, 0]) < 1e-13
+    assert relerr(fz["F_2nd_mean"][0, 1], 4.0 * fz["F_2nd_mean"][0, 0]) < 1e-13
+    # difference frequencies beyond the table's span (w_max - w_min of the QTF axis) carry no force
+    span = P["qtf_w"][-1] - P["qtf_w"][0]
+    mu = np.arange(1, nw + 1) * (w[1] - w[0])              # bin m holds difference frequency (m+1) dw
+    assert np.all(fz["F_2nd"][0, 0][:, mu > span * (1 + 1e-12)] == 0.0)

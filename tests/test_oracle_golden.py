@@ -3,7 +3,7 @@ the unmodified reference run under the stub harness (tests/golden/*.npz, made by
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden, relerr, response_err
+from conftest import QTF_GOLDEN, golden_names, load_golden, relerr, response_err
 
 NAMES = golden_names()
 PICKLED = [n for n in NAMES if n.startswith("test_")]
@@ -138,3 +138,41 @@ def test_wave_trains_vs_reference_run(name, oracle):
                                           np.zeros(len(tr)), tr[:, 2], nIter=int(G["n_iter"]), XiStart=float(G["xi_start"]))
     for ih in range(len(tr)):
         assert response_err(Xi[ih], G["ref_run_trains_Xi"][ih]) < 1e-12
+
+
+def test_second_order_force_vs_reference_run(oracle):
+    """calcHydroForce_2ndOrd (potSecOrder 2, external .12d QTF) and solveDynamics with it, vs the reference run."""
+    G, P = load_golden(QTF_GOLDEN)
+    od = oracle.OracleDesign(P)
+    cases = G["ref_run_solve_cases"]
+    for i, (Hs, Tp, beta) in enumerate(cases):
+        fm, f = oracle.hydro_force_2nd(od, beta * 0.017453292519943295, G["ref_run_S"][i])
+        assert relerr(f, G["ref_run_F2nd"][i]) < 1e-13
+        assert relerr(fm, G["ref_run_F2nd_mean"][i]) < 1e-13
+        assert np.all(f[:, -1] == 0.0)                                   # raft_fowt.py:2245
+        Xi, st = oracle.solve_dynamics(od, 0, Hs, Tp, 0.0, beta, nIter=int(G["n_iter"]), XiStart=float(G["xi_start"]))
+        assert st[0] == G["ref_run_solve_passes"][i]
+        assert response_err(Xi, G["ref_run_solve_Xi"][i]) < 1e-12
+    # the force matters: without the table the response differs visibly
+    P0 = {k: v for k, v in P.items() if not k.startswith("qtf")}
+    Xi0, _ = oracle.solve_dynamics(oracle.OracleDesign(P0), 0, *cases[0][:2], 0.0, cases[0][2], nIter=int(G["n_iter"]),
+                                   XiStart=float(G["xi_start"]))
+    assert response_err(Xi0, G["ref_run_solve_Xi"][0]) > 1e-4
+    # wave trains: every train gets its own second-order force (raft_model.py:1210-1212)
+    tr = G["ref_run_trains"]
+    Xi, _ = oracle.solve_dynamics_trains(od, [0] * len(tr), tr[:, 0], tr[:, 1], [0.0] * len(tr), tr[:, 2],
+                                         nIter=int(G["n_iter"]), XiStart=float(G["xi_start"]))
+    assert response_err(Xi, G["ref_run_trains_Xi"]) < 1e-12
+
+
+def test_second_order_heading_interpolation_vs_reference_run(oracle):
+    """4-heading synthetic table: interp1d along the heading axis incl. the clamped ends (raft_fowt.py:2178-2187)."""
+    G, P = load_golden(QTF_GOLDEN)
+    P = dict(P)
+    P["qtf"] = np.stack([P["qtf"][:, :, 0, :] * s for s in G["mh_scale"]], axis=2)
+    P["qtf_heads"] = G["mh_heads"]
+    od = oracle.OracleDesign(P)
+    for i, b in enumerate(G["mh_betas_deg"]):
+        fm, f = oracle.hydro_force_2nd(od, b * 0.017453292519943295, G["ref_run_S"][0])
+        assert relerr(f, G["ref_run_mh_F2nd"][i]) < 1e-13
+        assert relerr(fm, G["ref_run_mh_F2nd_mean"][i]) < 1e-13
