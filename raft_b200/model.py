@@ -69,21 +69,29 @@ class Model:
         self.results["Xi"] = out["Xi"]
         self.results["Xi_trains"] = out["Xi_trains"]
         self.results["status"] = out["status"]
-        # response statistics per case and FOWT (raft_fowt.py:2299-2353; zero mean offsets: statics are out of scope)
+        # response statistics per case and FOWT (raft_fowt.py:2299-2353; zero mean offsets: statics are out of scope).
+        # getRMS / getPSD sum the squares over a case's wave trains (helpers.py:678-700), so the per-train device
+        # reductions are combined here: std = sqrt(sum std_t^2), PSD = sum PSD_t.
         nC = len(cases)
-        Xi_units = out["Xi"].reshape(nC, self.nFOWT, 6, self.nw)
-        sd, psd = solver.response_stats(Xi_units, self.w[1] - self.w[0])
+        owner = out["owner"]
+        Xi_units = out["Xi_all"].reshape(len(owner), self.nFOWT, 6, self.nw)                  # [nTrains, nFOWT, 6, nw]
+        sd_t, psd_t = solver.response_stats(Xi_units, self.w[1] - self.w[0])
         names = ("surge", "sway", "heave", "roll", "pitch", "yaw")
         self.results["case_metrics"] = {}
         for ic in range(nC):
+            idx = np.nonzero(owner == ic)[0]
+            sd = np.sqrt((sd_t[idx] ** 2).sum(axis=0))
+            psd = psd_t[idx].sum(axis=0)
             self.results["case_metrics"][ic] = {}
             for i in range(self.nFOWT):
                 m = {}
                 for k_, nm in enumerate(names):
-                    m[nm + "_avg"], m[nm + "_std"] = 0.0, sd[ic, i, k_]
-                    m[nm + "_max"], m[nm + "_min"] = 3 * sd[ic, i, k_], -3 * sd[ic, i, k_]
-                    m[nm + "_PSD"] = psd[ic, i, k_]
-                    m[nm + "_RA"] = Xi_units[ic, i, k_] * (180 / np.pi if k_ >= 3 else 1.0)
+                    m[nm + "_avg"], m[nm + "_std"] = 0.0, sd[i, k_]
+                    m[nm + "_max"], m[nm + "_min"] = 3 * sd[i, k_], -3 * sd[i, k_]
+                    m[nm + "_PSD"] = psd[i, k_]
+                    ra = np.zeros([len(idx) + 1, self.nw], dtype=complex)                     # all trains + the zero row (:1195)
+                    ra[:-1] = Xi_units[idx, i, k_] * (57.29577951308232 if k_ >= 3 else 1.0)
+                    m[nm + "_RA"] = ra
                 self.results["case_metrics"][ic][i] = m
         return self.results
 
@@ -121,7 +129,7 @@ class Model:
             # coupled system: Z_sys = blockdiag(Z_i) + C_array; F = Z_i Xi_i  (raft_model.py:1164-1216)
             Xi_all = self._couple(o, nT)
         Xi_trains = [Xi_all[owner == ic] for ic in range(nC)]
-        return dict(Xi=Xi_all[first], Xi_trains=Xi_trains, status=np.moveaxis(st, 0, 1))
+        return dict(Xi=Xi_all[first], Xi_trains=Xi_trains, status=np.moveaxis(st, 0, 1), Xi_all=Xi_all, owner=owner)
 
     def _couple(self, o, nC):
         n, nw, w = self.nDOF, self.nw, self.w

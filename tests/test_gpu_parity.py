@@ -315,6 +315,17 @@ def test_response_stats_vs_reference_formulas(solver):
     ref = G["ref_run_solve_Xi"][0]
     assert abs(m["surge_std"] - np.sqrt(0.5 * np.sum(np.abs(ref[0]) ** 2))) < 1e-10 * m["surge_std"]
     assert relerr(m["pitch_PSD"], 0.5 * np.abs(ref[4] * 180.0 / np.pi) ** 2 / (P["w"][1] - P["w"][0])) < 1e-9
+    # a case with several wave trains: getRMS / getPSD sum the squares over the trains (helpers.py:678-700)
+    tr = G["ref_run_trains"]
+    case = dict(wave_spectrum=["JONSWAP"] * len(tr), wave_height=list(tr[:, 0]), wave_period=list(tr[:, 1]),
+                wave_heading=list(tr[:, 2]), wave_gamma=[0.0] * len(tr))
+    m = model.analyzeCases([case])["case_metrics"][0][0]
+    ref = np.concatenate([G["ref_run_trains_Xi"], np.zeros_like(G["ref_run_trains_Xi"][:1])])      # [nWaves+1, 6, nw]
+    dw = P["w"][1] - P["w"][0]
+    assert abs(m["heave_std"] - np.sqrt(0.5 * np.sum(np.abs(ref[:, 2]) ** 2))) < 1e-10 * m["heave_std"]
+    assert relerr(m["roll_PSD"], np.sum(0.5 * np.abs(ref[:, 3] * 57.29577951308232) ** 2 / dw, axis=0)) < 1e-9
+    assert m["surge_RA"].shape == (len(tr) + 1, model.nw) and relerr(m["surge_RA"], ref[:, 0]) < 1e-9
+    assert m["surge_max"] == 3 * m["surge_std"]
 
 
 def test_error_paths_nan_and_singular(solver):
