@@ -250,6 +250,21 @@ int raftk_response_stats_dev(int32_t n_units, int32_t nw, double dw, int32_t rot
 int raftk_response_stats_host(int32_t n_units, int32_t nw, double dw, int32_t rot_deg, const double *Xi,
                               double *std, double *psd);
 
+/*
+ * Output channels of FOWT.saveTurbineOutputs beyond the platform DOFs -- nacelle accelerations
+ * (raft_fowt.py:2401-2444) and the tower-base fore-aft bending moment of a rigid tower (:2504-2538).  Each is a
+ * linear functional of the response, Y_ch(w) = sum_dof coef[ch,dof,w] Xi[dof,w]  (e.g. AxRNA: w^2 times the hub
+ * node's row of fowt.T; Mbase: m hArm w^2 (Xi_0 + zCG Xi_4) + (ICG w^2 + m g hArm + aero reaction) Xi_4), so the
+ * caller packs the turbine constants into coef once per design (raft_b200.packer.pack_turbine_channels) and gets
+ *   std = sqrt(1/2 sum_w |Y|^2) (helpers.getRMS),  PSD(w) = 1/2 |Y|^2 / dw (helpers.getPSD),  amp = Y (optional).
+ * coef complex [n_designs,n_ch,6,nw]; Xi complex [n_designs,n_cases,6,nw] -> std [n_designs,n_cases,n_ch],
+ * psd [n_designs,n_cases,n_ch,nw] or NULL, amp complex [n_designs,n_cases,n_ch,nw] or NULL.
+ */
+int raftk_channel_stats_dev(int32_t n_designs, int32_t n_cases, int32_t n_ch, int32_t nw, double dw, const double *coef,
+                            const double *Xi, double *std, double *psd, double *amp, void *stream);
+int raftk_channel_stats_host(int32_t n_designs, int32_t n_cases, int32_t n_ch, int32_t nw, double dw, const double *coef,
+                             const double *Xi, double *std, double *psd, double *amp);
+
 /* Pinned host memory for the *_host paths and the e2e benchmark (cudaHostAlloc / cudaFreeHost). */
 void *raftk_host_alloc(size_t bytes);
 void raftk_host_free(void *p);

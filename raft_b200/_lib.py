@@ -54,7 +54,8 @@ SYMBOLS = [
     "raftk_hydro_excitation_dev", "raftk_hydro_linearization_dev", "raftk_solve_dynamics_dev",
     "raftk_hydro_excitation_host", "raftk_hydro_linearization_host", "raftk_solve_dynamics_host",
     "raftk_second_order_force_dev", "raftk_second_order_force_host",
-    "raftk_system_solve_dev", "raftk_system_solve_host", "raftk_response_stats_dev", "raftk_response_stats_host", "raftk_host_alloc", "raftk_host_free",
+    "raftk_system_solve_dev", "raftk_system_solve_host", "raftk_response_stats_dev", "raftk_response_stats_host",
+    "raftk_channel_stats_dev", "raftk_channel_stats_host", "raftk_host_alloc", "raftk_host_free",
     "raftk_fp64_peak_gflops",
 ]
 
@@ -92,6 +93,10 @@ def _load():
     lib.raftk_system_solve_host.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.raftk_response_stats_dev.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.raftk_response_stats_host.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.raftk_channel_stats_dev.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 6
+    lib.raftk_channel_stats_host.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 5
+    lib.raftk_channel_stats_dev.restype = C.c_int
+    lib.raftk_channel_stats_host.restype = C.c_int
     lib.raftk_response_stats_dev.restype = C.c_int
     lib.raftk_response_stats_host.restype = C.c_int
     lib.raftk_host_alloc.restype = C.c_void_p

@@ -794,6 +794,43 @@ extern "C" int raftk_response_stats_host(int32_t n_units, int32_t nw, double dw,
     return rc;
 }
 
+extern "C" int raftk_channel_stats_dev(int32_t n_designs, int32_t n_cases, int32_t n_ch, int32_t nw, double dw, const double *coef,
+                                       const double *Xi, double *sd, double *psd, double *amp, void *stream)
+{
+    if (n_designs <= 0 || n_cases <= 0 || n_ch <= 0 || nw <= 0 || !coef || !Xi || !sd || !(dw > 0.0))
+        return set_err(RAFTK_EINVAL, "bad channel-stats arguments");
+    const size_t rows = (size_t)n_designs * n_cases * n_ch;
+    if (rows > 2147483647u) return set_err(RAFTK_EINVAL, "channel-stats: too many (design, case, channel) rows");
+    k_channel_stats<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(n_cases, n_ch, nw, dw, reinterpret_cast<const double2 *>(coef),
+                                                                    reinterpret_cast<const double2 *>(Xi), sd, psd, reinterpret_cast<double2 *>(amp));
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RAFTK_OK;
+}
+
+extern "C" int raftk_channel_stats_host(int32_t n_designs, int32_t n_cases, int32_t n_ch, int32_t nw, double dw, const double *coef,
+                                        const double *Xi, double *sd, double *psd, double *amp)
+{
+    if (n_designs <= 0 || n_cases <= 0 || n_ch <= 0 || nw <= 0 || !coef || !Xi || !sd || !(dw > 0.0))
+        return set_err(RAFTK_EINVAL, "bad channel-stats arguments");
+    const size_t rows = (size_t)n_designs * n_cases * n_ch;
+    const size_t cb = (size_t)n_designs * n_ch * 6 * nw * 16, xb = (size_t)n_designs * n_cases * 6 * nw * 16;
+    const size_t sb = rows * 8, pb = rows * nw * 8, ab = rows * nw * 16;
+    double *dC = nullptr, *dX = nullptr, *dS = nullptr, *dP = nullptr, *dA = nullptr;
+    CUDA_TRY(cudaMalloc(&dC, cb)); CUDA_TRY(cudaMalloc(&dX, xb)); CUDA_TRY(cudaMalloc(&dS, sb));
+    if (psd) CUDA_TRY(cudaMalloc(&dP, pb));
+    if (amp) CUDA_TRY(cudaMalloc(&dA, ab));
+    CUDA_TRY(cudaMemcpy(dC, coef, cb, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dX, Xi, xb, cudaMemcpyHostToDevice));
+    int rc = raftk_channel_stats_dev(n_designs, n_cases, n_ch, nw, dw, dC, dX, dS, dP, dA, nullptr);
+    if (!rc) {
+        CUDA_TRY(cudaMemcpy(sd, dS, sb, cudaMemcpyDeviceToHost));
+        if (psd) CUDA_TRY(cudaMemcpy(psd, dP, pb, cudaMemcpyDeviceToHost));
+        if (amp) CUDA_TRY(cudaMemcpy(amp, dA, ab, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(dC); cudaFree(dX); cudaFree(dS); if (dP) cudaFree(dP); if (dA) cudaFree(dA);
+    return rc;
+}
+
 extern "C" void *raftk_host_alloc(size_t bytes)
 {
     void *p = nullptr;

@@ -98,6 +98,37 @@ __global__ void __launch_bounds__(128) k_response_stats(int nw, double dw, int r
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5: output-channel statistics -- every channel of saveTurbineOutputs beyond the platform DOFs (nacelle accelerations,
+// tower-base moment, raft_fowt.py:2401-2444, 2504-2538) is a linear functional of the response:
+// Y(w) = sum_dof coef[design][ch][dof][w] * Xi[design][case][dof][w].  One CTA per (design, case, channel).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_channel_stats(int nC, int nch, int nw, double dw, const double2 *coef, const double2 *Xi,
+                                                       double *sd, double *psd, double2 *amp)
+{
+    __shared__ double part[4];
+    const int row = blockIdx.x, ch = row % nch, unit = row / nch, d = unit / nC, tid = threadIdx.x;
+    const double2 *cf = coef + ((size_t)d * nch + ch) * 6 * nw;
+    const double2 *x = Xi + (size_t)unit * 6 * nw;
+    double s = 0.0;
+    for (int i = tid; i < nw; i += 128) {
+        double yr = 0.0, yi = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            const double2 c = cf[(size_t)a * nw + i], v = x[(size_t)a * nw + i];
+            yr += c.x * v.x - c.y * v.y; yi += c.x * v.y + c.y * v.x;
+        }
+        const double a2 = yr * yr + yi * yi;
+        s += a2;
+        if (psd) psd[(size_t)row * nw + i] = 0.5 * a2 / dw;
+        if (amp) amp[(size_t)row * nw + i] = make_double2(yr, yi);
+    }
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) part[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) sd[row] = sqrt(0.5 * (((part[0] + part[1]) + part[2]) + part[3]));
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 FMA peak micro-kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters)

@@ -13,7 +13,9 @@ from .fowt import FOWT
 
 
 class Model:
-    def __init__(self, design, matrices=None, array_stiffness=None):
+    def __init__(self, design, matrices=None, array_stiffness=None, channels=None):
+        """``channels``: optional turbine output channels per FOWT (``packer.pack_turbine_channels`` dicts: nacelle
+        accelerations, tower-base moment) -- the turbine itself is outside this path, its constants enter here."""
         s = design.setdefault("settings", {})
         min_freq, max_freq = float(s.get("min_freq", 0.01)), float(s.get("max_freq", 1.00))
         self.XiStart = float(s.get("XiStart", 0.1))
@@ -40,6 +42,7 @@ class Model:
         self.nDOF = 6 * self.nFOWT
         self.C_array = None if array_stiffness is None else np.array(array_stiffness, dtype=float)   # stands in for ms.getCoupledStiffnessA
         self.results = {}
+        self.channels = list(channels) if isinstance(channels, (list, tuple)) else [channels] * self.nFOWT
         for f in self.fowtList:
             f.calcHydroConstants()
 
@@ -77,6 +80,8 @@ class Model:
         Xi_units = out["Xi_all"].reshape(len(owner), self.nFOWT, 6, self.nw)                  # [nTrains, nFOWT, 6, nw]
         sd_t, psd_t = solver.response_stats(Xi_units, self.w[1] - self.w[0])
         names = ("surge", "sway", "heave", "roll", "pitch", "yaw")
+        ch_stats = [None if ch is None else solver.channel_stats(ch["coef"], Xi_units[:, i], self.w[1] - self.w[0])
+                    for i, ch in enumerate(self.channels)]                                     # (std [nT,nch], PSD [nT,nch,nw], -)
         self.results["case_metrics"] = {}
         for ic in range(nC):
             idx = np.nonzero(owner == ic)[0]
@@ -92,6 +97,18 @@ class Model:
                     ra = np.zeros([len(idx) + 1, self.nw], dtype=complex)                     # all trains + the zero row (:1195)
                     ra[:-1] = Xi_units[idx, i, k_] * (57.29577951308232 if k_ >= 3 else 1.0)
                     m[nm + "_RA"] = ra
+                if ch_stats[i] is not None:                                                   # raft_fowt.py:2401-2444, 2504-2538
+                    ch = self.channels[i]
+                    nrot = 1 + max(ir for _, ir in ch["names"])
+                    sd_c = np.sqrt((ch_stats[i][0][idx] ** 2).sum(axis=0))
+                    psd_c = ch_stats[i][1][idx].sum(axis=0)
+                    for k_, (nm, ir) in enumerate(ch["names"]):
+                        for suffix in ("_avg", "_std", "_max", "_min"):
+                            m.setdefault(nm + suffix, np.zeros(nrot))
+                        m.setdefault(nm + "_PSD", np.zeros([self.nw, nrot]))
+                        m[nm + "_avg"][ir], m[nm + "_std"][ir] = ch["avg"][k_], sd_c[k_]
+                        m[nm + "_max"][ir], m[nm + "_min"][ir] = ch["avg"][k_] + 3 * sd_c[k_], ch["avg"][k_] - 3 * sd_c[k_]
+                        m[nm + "_PSD"][:, ir] = psd_c[k_]
                 self.results["case_metrics"][ic][i] = m
         return self.results
 

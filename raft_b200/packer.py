@@ -226,6 +226,62 @@ def pack_qtf(fowt):
                 qtf_heads=np.asarray(fowt.heads_2nd, dtype=float))
 
 
+def pack_turbine_channels(fowt):
+    """Turbine output channels of ``FOWT.saveTurbineOutputs`` as linear functionals of the 6-DOF response, for
+    ``solver.channel_stats`` (C ABI ``raftk_channel_stats_*``).  Duck-typed on a live FOWT with rotors and RIGID towers:
+
+      AxRNA, AyRNA, AzRNA  hub acceleration  w^2 (T_hub Xi)[0..2]                       raft_fowt.py:2422-2444
+      Mbase                tower-base fore-aft bending moment  M_I + M_w + M_X_aero       raft_fowt.py:2504-2538
+
+    Returns dict(names [(name, rotor index)], coef complex [nch,6,nw], avg [nch]) or None without rotors.
+    ``avg`` follows the reference's mean values (:2428, :2435, :2442, :2533; the Mbase mean needs the statics results
+    ``fowt.Xi0`` / ``fowt.f_aero0`` and is 0 when they are absent)."""
+    from .bem import translate_matrix_6to6
+    rotors = list(getattr(fowt, "rotorList", []) or [])
+    if not rotors:
+        return None
+    w = np.asarray(fowt.w, dtype=float)
+    nw, g = len(w), float(fowt.g)
+    T_full = np.asarray(fowt.T, dtype=float)
+    if T_full.shape[1] != 6:
+        raise NotImplementedError("turbine channels: only rigid 6-DOF FOWTs (fowt.T must be [nFullDOF, 6])")
+    names, coef, avg = [], [], []
+    for ir, rotor in enumerate(rotors):
+        node = rotor.nodeList[0]
+        T = T_full[node.id * 6:(node.id + 1) * 6, :]                     # hub motion = T Xi (raft_model.py:1255)
+        means = (abs(np.sin(node.r[4]) * g), abs(np.sin(node.r[3]) * g), abs(g))
+        for ax, nm in enumerate(("AxRNA", "AyRNA", "AzRNA")):
+            names.append((nm, ir))
+            coef.append(T[ax][:, None] * (w ** 2)[None, :] + 0j)
+            avg.append(means[ax])
+        mem_tower = fowt.memberList[fowt.nplatmems + ir]
+        if getattr(mem_tower, "type", "rigid") != "rigid":
+            raise NotImplementedError("turbine channels: flexible towers (finite-element internal loads, raft_fowt.py:2541) are outside the B200 path")
+        mRNA, IrRNA, zRNA = float(rotor.mRNA), float(rotor.IrRNA), float(rotor.r_rel[2])
+        mtow = float(fowt.mtower[ir])
+        m_turb = mtow + mRNA                                              # :2509
+        zCG = (float(fowt.rCG_tow[ir][2]) * mtow + zRNA * mRNA) / m_turb  # :2510
+        zBase = float(mem_tower.rA[2])
+        hArm = zCG - zBase
+        r_shift = np.asarray(mem_tower.nodeList[0].r0[:3], dtype=float) - np.array([0.0, 0.0, zCG])
+        ICG = translate_matrix_6to6(np.asarray(mem_tower.M_struc, dtype=float), r_shift)[4, 4] + mRNA * (zRNA - zCG) ** 2 + IrRNA   # :2518
+        A00 = np.asarray(fowt.A_aero, dtype=float)[0, 0, :, ir] if np.ndim(getattr(fowt, "A_aero", 0)) == 4 else np.zeros(nw)
+        B00 = np.asarray(fowt.B_aero, dtype=float)[0, 0, :, ir] if np.ndim(getattr(fowt, "B_aero", 0)) == 4 else np.zeros(nw)
+        c = np.zeros([6, nw], dtype=complex)
+        c[0] = m_turb * hArm * w ** 2                                     # -m aCG hArm, aCG = -w^2 (Xi_0 + zCG Xi_4)  (:2515, :2521)
+        c[4] = (m_turb * hArm * zCG * w ** 2 + ICG * w ** 2               # ... and -ICG (-w^2 Xi_4)
+                + m_turb * g * hArm                                       # weight moment (:2522)
+                - (-w ** 2 * A00 + 1j * w * B00) * (zRNA - zBase) ** 2)   # aero reaction moment (:2526)
+        names.append(("Mbase", ir))
+        coef.append(c)
+        mean = 0.0
+        if hasattr(fowt, "Xi0") and hasattr(fowt, "f_aero0"):
+            F6 = np.asarray(rotors[0].nodeList[0].T, dtype=float) @ np.asarray(fowt.f_aero0, dtype=float)[:, ir]
+            mean = m_turb * g * hArm * np.sin(fowt.Xi0[4]) + (F6[4] - hArm * F6[0])     # transformForce(.., offset=[0,0,-hArm])[4]  (:2533)
+        avg.append(float(mean))
+    return dict(names=names, coef=np.array(coef), avg=np.array(avg, dtype=float))
+
+
 SPECTRUM_IDS = {"JONSWAP": 0, "unit": 1, "constant": 2, "none": 3, "still": 3}
 
 

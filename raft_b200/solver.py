@@ -316,6 +316,30 @@ def response_stats(Xi, dw, psd=True, rot_deg=True):
     return sd, P
 
 
+def channel_stats(coef, Xi, dw, psd=True, amp=False):
+    """Statistics of linear output channels Y = sum_dof coef * Xi (nacelle accelerations, tower-base moment;
+    raft_fowt.py:2401-2444, 2504-2538; coefficients from ``packer.pack_turbine_channels``).
+    ``coef`` complex [nD,nch,6,nw] (or [nch,6,nw]); ``Xi`` complex [nD,nC,6,nw] (or [nC,6,nw])
+    -> (std [nD,nC,nch], PSD [nD,nC,nch,nw] or None, amplitudes complex [nD,nC,nch,nw] or None)."""
+    coef = np.ascontiguousarray(coef, dtype=np.complex128)
+    Xi = np.ascontiguousarray(Xi, dtype=np.complex128)
+    squeeze = coef.ndim == 3
+    if squeeze:
+        coef, Xi = coef[None], Xi[None]
+    nD, nch, _, nw = coef.shape
+    if Xi.ndim != 4 or Xi.shape[0] != nD or Xi.shape[2:] != (6, nw) or coef.shape[2] != 6:
+        raise ValueError("coef must be [nD,nch,6,nw] and Xi [nD,nC,6,nw]")
+    nC = Xi.shape[1]
+    sd = np.zeros([nD, nC, nch])
+    P = np.zeros([nD, nC, nch, nw]) if psd else None
+    A = np.zeros([nD, nC, nch, nw], dtype=np.complex128) if amp else None
+    check(lib.raftk_channel_stats_host(nD, nC, nch, nw, float(dw), coef.ctypes.data, Xi.ctypes.data, sd.ctypes.data,
+                                       P.ctypes.data if psd else None, A.ctypes.data if amp else None))
+    if squeeze:
+        sd, P, A = sd[0], (P[0] if psd else None), (A[0] if amp else None)
+    return sd, P, A
+
+
 def pinned_empty(shape, dtype):
     """NumPy array backed by page-locked host memory (cudaHostAlloc) for the e2e path."""
     dtype = np.dtype(dtype)

@@ -202,6 +202,45 @@ def fixture_qtf(name, yaml_path, nw, max_freq, solve_cases, trains):
     print("%-28s nw=%4d cases=%2d  %.1f s  %.0f KB" % (name, nw, len(solve_cases), time.time() - t0, os.path.getsize(path) / 1024))
 
 
+def fixture_turbine(name, yaml_path):
+    """A design WITH its turbine (rotor + rigid tower; CCBlade stubbed, turbine off, mooring stripped): the turbine
+    channels of FOWT.saveTurbineOutputs -- nacelle accelerations and tower-base moment (raft_fowt.py:2401-2444,
+    2504-2538) -- from the unmodified reference, for single- and multi-train cases."""
+    import contextlib
+    import io
+    t0 = time.time()
+    design = rh.load_design(yaml_path, strip=False)
+    design.pop("mooring", None)
+    design["platform"]["potSecOrder"] = 0
+    model = rh.build_model(design)
+    fowt = model.fowtList[0]
+    fowt.Xi0 = np.array([0.0, 0.0, 0.0, 0.0, 0.02, 0.0])      # mean pitch of a statics solve (out of scope), for Mbase_avg
+    P = packer.pack_fowt(fowt)
+    ch = packer.pack_turbine_channels(fowt)
+    out = {"P_" + k: np.asarray(v) for k, v in P.items()}
+    out["n_iter"], out["xi_start"] = np.int32(int(model.nIter)), np.float64(model.XiStart)
+    out["ch_names"] = np.array(["%s:%d" % nm for nm in ch["names"]])
+    out["ch_coef"], out["ch_avg"] = ch["coef"], ch["avg"]
+    cases = [rh.make_case(6.0, 12.0, 30.0), rh.make_case(2.0, 7.5, -75.0)]
+    c3 = rh.make_case()
+    c3.update(wave_heading=[0.0, 60.0], wave_period=[10.0, 14.0], wave_height=[4.0, 2.0], wave_spectrum=["JONSWAP"] * 2, wave_gamma=[0.0, 0.0])
+    cases.append(c3)
+    keys = [d + s for d in ("surge", "sway", "heave", "roll", "pitch", "yaw", "AxRNA", "AyRNA", "AzRNA", "Mbase")
+            for s in ("_avg", "_std", "_max", "_min", "_PSD")]
+    for ic, case in enumerate(cases):
+        x = rh.solve_dynamics(model, case)
+        res = {}
+        with contextlib.redirect_stdout(io.StringIO()):
+            fowt.saveTurbineOutputs(res, case)
+        out["ref_run_case%d_Xi" % ic] = np.array(x)                      # [nWaves+1, 6, nw]
+        out["ref_run_case%d_trains" % ic] = np.array([np.atleast_1d(case[k]) for k in ("wave_height", "wave_period", "wave_heading")], dtype=float).T
+        for k in keys:
+            out["ref_run_case%d_%s" % (ic, k)] = np.array(res[k])
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-28s nw=%4d cases=%2d  %.1f s  %.0f KB" % (name, len(P["w"]), len(cases), time.time() - t0, os.path.getsize(path) / 1024))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -231,6 +270,8 @@ def main():
         Hs, Tp, beta = seeded_cases(5, 3)
         fixture_qtf("cfg3q_OC4semi-QTF_nw96", os.path.join(REF, "examples", "OC4semi-WAMIT_Coefs.yaml"), nw=96, max_freq=0.256,
                     solve_cases=list(zip(Hs, Tp, beta)) + [(6.0, 12.0, 30.0)], trains=[(6.0, 12.0, 30.0), (2.5, 7.0, -100.0)])
+    if not args.only or args.only in "turb_VolturnUS-S":
+        fixture_turbine("turb_VolturnUS-S", os.path.join(td, "VolturnUS-S.yaml"))
     if not args.only:
         # raw WAMIT tables of the OC4 semi (reference data files examples/OC4semi-WAMIT_Coefs/marin_semi.1/.3),
         # read with the product reader, so that readHydro can be exercised at any grid size off the build box

@@ -115,3 +115,21 @@ def test_all_gather_blocks_gloo_world2(n_items):
     for rank, full, st in got:
         assert full.shape == (n_items, 3, 2) and np.array_equal(full, want)
         assert np.array_equal(st[:, 0], np.arange(n_items))
+
+
+def test_turbine_channel_coefficients_vs_reference_saveTurbineOutputs():
+    """packer.pack_turbine_channels (packed from the live reference FOWT when the fixture was made) reproduces the
+    reference's nacelle-acceleration and tower-base-moment metrics as plain linear functionals of its own Xi."""
+    z = np.load(os.path.join(GOLDEN, "turb_VolturnUS-S.npz"))
+    coef, names, dw = z["ch_coef"], [n.split(":")[0] for n in z["ch_names"]], float(z["P_dw"])
+    assert names == ["AxRNA", "AyRNA", "AzRNA", "Mbase"]
+    for ic in range(3):
+        Xi = z["ref_run_case%d_Xi" % ic]                                   # [nWaves+1, 6, nw]
+        Y = np.einsum("kaw,taw->tkw", coef, Xi)
+        sd = np.sqrt(0.5 * np.sum(np.abs(Y) ** 2, axis=(0, 2)))            # helpers.getRMS over trains and frequencies
+        psd = np.sum(0.5 * np.abs(Y) ** 2 / dw, axis=0)                    # helpers.getPSD
+        for k, nm in enumerate(names):
+            assert abs(sd[k] - z["ref_run_case%d_%s_std" % (ic, nm)][0]) <= 1e-13 * sd[k]
+            ref = z["ref_run_case%d_%s_PSD" % (ic, nm)][:, 0]
+            assert np.abs(psd[k] - ref).max() <= 1e-13 * ref.max()
+            assert abs(z["ch_avg"][k] - z["ref_run_case%d_%s_avg" % (ic, nm)][0]) <= 1e-13 * max(1.0, abs(z["ch_avg"][k]))

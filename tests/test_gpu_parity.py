@@ -605,3 +605,74 @@ def test_second_order_force_full_grid_properties(solver, oracle):
     span = P["qtf_w"][-1] - P["qtf_w"][0]
     mu = np.arange(1, nw + 1) * (w[1] - w[0])              # bin m holds difference frequency (m+1) dw
     assert np.all(fz["F_2nd"][0, 0][:, mu > span * (1 + 1e-12)] == 0.0)
+
+
+# ---- turbine output channels (nacelle accelerations, tower-base moment): raft_fowt.py:2401-2444, 2504-2538 --------
+
+def test_channel_stats_vs_reference_saveTurbineOutputs(solver):
+    """Design WITH its turbine (mass matrices incl. tower + RNA packed from the live reference): GPU solve of every
+    train, then k_channel_stats, against the metrics the unmodified reference's saveTurbineOutputs produced."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "turb_VolturnUS-S.npz"))
+    P = {k[2:]: z[k] for k in z.files if k.startswith("P_")}
+    names = [n.split(":")[0] for n in z["ch_names"]]
+    b = solver.DesignBatch(P)
+    dw = float(P["dw"])
+    from raft_b200 import packer
+    for ic in range(3):
+        tr = z["ref_run_case%d_trains" % ic]
+        case = dict(wave_spectrum=["JONSWAP"] * len(tr), wave_height=list(tr[:, 0]), wave_period=list(tr[:, 1]),
+                    wave_heading=list(tr[:, 2]), wave_gamma=[0.0] * len(tr))
+        table, owner, first = packer.pack_case_trains([case])
+        out = solver.solve_dynamics(b, solver.CaseTable(table), n_iter=int(z["n_iter"]), xi_start=float(z["xi_start"]))
+        ref = z["ref_run_case%d_Xi" % ic]
+        assert response_err(out["Xi"][0], ref[:-1]) < RTOL
+        sd, psd, amp = solver.channel_stats(z["ch_coef"], out["Xi"][0], dw, amp=True)     # [nT,nch], [nT,nch,nw]
+        sd_c, psd_c = np.sqrt((sd ** 2).sum(axis=0)), psd.sum(axis=0)
+        for k, nm in enumerate(names):
+            r = z["ref_run_case%d_%s_std" % (ic, nm)][0]
+            assert abs(sd_c[k] - r) < 1e-9 * r, (ic, nm)
+            assert relerr(psd_c[k], z["ref_run_case%d_%s_PSD" % (ic, nm)][:, 0]) < 1e-9, (ic, nm)
+        assert relerr(amp, np.einsum("kaw,taw->tkw", z["ch_coef"], out["Xi"][0])) < 1e-14
+    # design axis: two designs with different coefficient sets in one call
+    rng = np.random.default_rng(4)
+    coef = rng.normal(size=(2, 3, 6, 77)) + 1j * rng.normal(size=(2, 3, 6, 77))
+    Xi = rng.normal(size=(2, 5, 6, 77)) + 1j * rng.normal(size=(2, 5, 6, 77))
+    sd, psd, amp = solver.channel_stats(coef, Xi, 0.05, amp=True)
+    Y = np.einsum("dkaw,dcaw->dckw", coef, Xi)
+    assert relerr(amp, Y) < 1e-14 and relerr(sd, np.sqrt(0.5 * np.sum(np.abs(Y) ** 2, axis=-1))) < 1e-14
+    assert relerr(psd, 0.5 * np.abs(Y) ** 2 / 0.05) < 1e-14
+
+
+def test_model_api_turbine_channels(solver):
+    """Model(..., channels=...) fills AxRNA/AyRNA/AzRNA/Mbase metrics like saveTurbineOutputs; platform built by the
+    own builder, turbine mass/inertia injected through M_struc (statics are out of scope)."""
+    import json, os
+    from conftest import GOLDEN
+    from raft_b200.model import Model
+    z = np.load(os.path.join(GOLDEN, "turb_VolturnUS-S.npz"))
+    P = {k[2:]: z[k] for k in z.files if k.startswith("P_")}
+    G0, _ = load_golden("test_VolturnUS-S")
+    D = json.load(open(os.path.join(GOLDEN, "designs.json")))["test_VolturnUS-S"]
+    design = dict(D, site=dict(D["site"], water_depth=float(P["depth"])))
+    mats = dict(M_struc=P["M0"] - G0["A_hydro_morison"], C_struc=P["C0"] - G0["C_moor"], C_moor=G0["C_moor"], B_struc=P["B0"])
+    ch = dict(names=[(n.split(":")[0], int(n.split(":")[1])) for n in z["ch_names"]], coef=z["ch_coef"], avg=z["ch_avg"])
+    model = Model(design, matrices=mats, channels=ch)
+    cases = []
+    for ic in range(3):
+        tr = z["ref_run_case%d_trains" % ic]
+        cases.append(dict(wave_spectrum=["JONSWAP"] * len(tr), wave_height=list(tr[:, 0]), wave_period=list(tr[:, 1]),
+                          wave_heading=list(tr[:, 2]), wave_gamma=[0.0] * len(tr)))
+    res = model.analyzeCases(cases)
+    for ic in range(3):
+        m = res["case_metrics"][ic][0]
+        for nm in ("surge", "pitch", "yaw", "AxRNA", "AyRNA", "AzRNA", "Mbase"):
+            for suffix in ("_std", "_avg", "_max", "_min"):
+                ref = np.ravel(z["ref_run_case%d_%s%s" % (ic, nm, suffix)])[0]
+                mine = np.ravel(m[nm + suffix])[0]
+                if nm in ("surge", "pitch", "yaw") and suffix != "_std":
+                    continue                                 # platform means come from the statics solve (out of scope)
+                assert abs(mine - ref) <= 1e-8 * max(abs(ref), 1e-12), (ic, nm, suffix)
+            refp = z["ref_run_case%d_%s_PSD" % (ic, nm)]
+            assert relerr(np.ravel(m[nm + "_PSD"]), np.ravel(refp)) < 1e-8, (ic, nm)
