@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- RAO solves/s of the B200-native hot path (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|sweep]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|cfg3|cfg3q|sweep]
 
 A "step" is one pass of the hot path (Model.solveDynamics for every (design, case) unit of the batch:
 excitation tables, drag-linearisation fixed-point loop, 6x6 complex impedance solve per frequency).
@@ -57,7 +57,7 @@ def build_workload(args, rank, world):
                             "%d freq bins x %d sea states per GPU, fp64, nIter=10, tol=0.01" % (len(P["w"]), nC),
                    designs_per_gpu=1, cases_per_gpu=nC, nw=len(P["w"]), submerged_nodes=int(len(P["node_ls"])))
         return [P], cs, cfg
-    elif args.workload == "cfg3":
+    elif args.workload in ("cfg3", "cfg3q"):
         # BASELINE.json configs[2]: OC4semi with WAMIT added-mass/damping/excitation tables, 2048 bins x 256 sea states
         from raft_b200 import bem, packer
         from raft_b200.fowt import FOWT
@@ -68,12 +68,19 @@ def build_workload(args, rank, world):
         w = grid.make_w(0.256 / nw, 0.256)
         H = bem.read_hydro(t["A"], t["B"], t["w1"], t["Re"], t["Im"], t["w3"], t["heads"], w, rho=float(z["P_rho"]), g=float(z["P_g"]))
         mats = dict(M_struc=z["P_M0"] - z["A_hydro_morison"], C_struc=z["P_C0"] - z["C_moor"], C_moor=z["C_moor"], **H)
+        second = ""
+        if args.workload == "cfg3q":
+            # as shipped: potSecOrder 2 -- difference-frequency forces from marin_semi.12d (k_qtf_force before the solve)
+            q = np.load(os.path.join(ROOT, "tests", "golden", "cfg3q_OC4semi-QTF_nw96.npz"))
+            mats.update(qtf=q["P_qtf"], qtf_w=q["P_qtf_w"], qtf_heads=q["P_qtf_heads"])
+            D = dict(D, platform=dict(D["platform"], potSecOrder=2))
+            second = " + second-order forces from marin_semi.12d (potSecOrder 2)"
         f = FOWT(D, w, depth=float(z["P_depth"]), matrices=mats)
         f.calcHydroConstants()
         cs_all = sea_states(3, nC * world)
         cs = {k: v[rank * nC:(rank + 1) * nC] for k, v in cs_all.items()}
         cfg = dict(workload="cfg3: examples/OC4semi-WAMIT_Coefs.yaml (potModMaster 3: BEM A/B/X tables via readHydro of marin_semi.1/.3, "
-                            "drag-only strips), %d freq bins x %d sea states per GPU, fp64" % (nw, nC),
+                            "drag-only strips)%s, %d freq bins x %d sea states per GPU, fp64" % (second, nw, nC),
                    designs_per_gpu=1, cases_per_gpu=nC, nw=nw)
         return [f.pack()], cs, cfg
     else:
@@ -232,7 +239,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "sweep"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg3q", "sweep"])
     ap.add_argument("--nw", type=int, default=0)
     ap.add_argument("--cases", type=int, default=0)
     ap.add_argument("--designs", type=int, default=0)
