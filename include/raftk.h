@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RAFTK_VERSION 110 /* 0.1.1: + external-QTF second-order forces */
+#define RAFTK_VERSION 120 /* 0.1.2: + external-QTF and slender-body second-order forces, output channels */
 
 enum {
     RAFTK_OK = 0,
@@ -105,11 +105,12 @@ typedef struct raftk_designs {
        raft_fowt.py:2081-2128), or n_qtf_w = 0 */
     int32_t n_qtf_w;            /* QTF frequencies (w1_2nd == w2_2nd, raft_fowt.py:2105-2110)   */
     int32_t n_qtf_head;         /* unidirectional QTF headings (heads_2nd)                      */
-    int32_t qtf_shared;         /* 1: qtf holds ONE table used by every design (no design axis) */
+    int32_t qtf_shared;         /* 0: one table per design; 1: ONE table used by every design (no design axis);
+                                   2: one table per (design, case) -- the slender-body QTF depends on the body motions */
     int32_t _pad2;
     const double *qtf_w;        /* [n_qtf_w] rad/s, ascending                                   */
     const double *qtf_heads;    /* [n_qtf_head] rad, ascending                                  */
-    const double *qtf;          /* complex [nD or 1, n_qtf_w, n_qtf_w, n_qtf_head, 6]: fowt.qtf, dimensional,
+    const double *qtf;          /* complex [nD or 1 or nD*nC, n_qtf_w, n_qtf_w, n_qtf_head, 6]: fowt.qtf, dimensional,
                                    Hermitian-filled (raft_fowt.py:2112-2128)                     */
 } raftk_designs;
 
@@ -132,6 +133,9 @@ typedef struct raftk_cases {
     const double *F_2nd;     /* optional real [nD,nC,6,nw]: second-order force amplitudes (fowt.Fhydro_2nd, from
                                 raftk_second_order_force_*) added to the linear excitation F_BEM + F_iner of every
                                 unit (raft_model.py:1048, :1212).  NULL: none, or computed by the solve (see below). */
+    const double *Xi_init;   /* optional complex [nD,nC,6,nw]: start the fixed-point loop from this iterate instead of the
+                                constant opts.xi_start (the loop that continues after the slender-body QTF has been
+                                added, raft_model.py:1106-1131).  Fused solver only. */
 } raftk_cases;
 
 /* Fixed-point loop controls (raft_model.py:966 tol, :977 nIter, :978 XiStart, :1133 relaxation) */
@@ -153,6 +157,8 @@ typedef struct raftk_outputs {
     double *zeta;     /* [nC,nw] wave amplitudes (fowt.zeta[0])                                 */
     double *F_2nd;    /* real [nD,nC,6,nw] difference-frequency force amplitudes (fowt.Fhydro_2nd)  */
     double *F_2nd_mean; /* [nD,nC,6] mean drift force (fowt.Fhydro_2nd_mean)                        */
+    double *Xi_last;  /* complex [nD,nC,6,nw] the iterate the LAST pass linearised about (XiLast at raft_model.py:1063
+                         when the loop stopped).  Fused solver only. */
 } raftk_outputs;
 
 int raftk_version(void);
@@ -221,6 +227,43 @@ int raftk_solve_dynamics_dev(const raftk_designs *d, const raftk_cases *c, const
  */
 int raftk_second_order_force_dev(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out, void *stream);
 int raftk_second_order_force_host(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out);
+
+/*
+ * Slender-body difference-frequency QTF (potSecOrder 1): FOWT.calcQTF_slenderBody (raft_fowt.py:1988-2078) with
+ * Member.calcQTF_slenderBody + correction_KAY (raft_member.py:1488-1792) and the second-order wave kinematics of
+ * helpers.py:239-373, for ONE design and n_cases (heading, motion RAO) pairs.  Tables: the submerged strip nodes of the
+ * design (same nodes and order as raftk_designs) with the volumes / coefficients the reference evaluates inside its
+ * frequency-pair loop, per-member waterline data, and the integration segments of the Kim & Yue correction
+ * (raft_b200.packer.pack_qtf_members).  Xi_rao complex [n_cases,6,nw]: motion RAOs on the second-order grid
+ * (raft_fowt.py:2021-2023; zeros = fixed body).  qtf complex [n_cases,nw,nw,6], Hermitian-filled (:2068-2070) --
+ * the layout raftk_designs.qtf takes with qtf_shared = 2 and one heading.
+ */
+typedef struct raftk_slender {
+    int32_t n_nodes, n_members, n_seg, nw;   /* nw: second-order frequencies (w1_2nd)                      */
+    double depth, rho, g;
+    const double *w, *k;            /* [nw] w1_2nd, k1_2nd (raft_fowt.py:419-426)                           */
+    const double *mem_q, *mem_p1, *mem_p2;   /* [n_members,3]                                               */
+    const int32_t *mem_mcf;         /* [n_members] 1: Kim & Yue correction applies (mem.MCF, crosses z = 0)  */
+    const int32_t *mem_wl;          /* [n_members] 1: the member crosses the mean waterline                  */
+    const double *mem_r_int;        /* [n_members,3] intersection with z = 0        raft_member.py:1528      */
+    const double *mem_a_wl;         /* [n_members] cross-section area at the waterline      :1660-1674       */
+    const double *mem_rwl;          /* [n_members,3] Kim & Yue: waterline point from rA, rB :1723            */
+    const double *mem_R_wl;         /* [n_members] Kim & Yue: radius at z = 0               :1725            */
+    const int32_t *mem_node_start;  /* [n_members+1]                                                         */
+    const double *node_r;           /* [n_nodes,3] global node positions                                     */
+    const double *node_v_side;      /* [n_nodes] strip volume, waterline-scaled             :1565-1571       */
+    const double *node_Ca_p1, *node_Ca_p2, *node_Ca_End;  /* [n_nodes] interpolated coefficients :1560-1562  */
+    const double *node_v_end;       /* [n_nodes] end volume                                 :1620-1625       */
+    const double *node_a_i;         /* [n_nodes] signed end area (mem.a_i)                                   */
+    const int32_t *seg_mem;         /* [n_seg] Kim & Yue integration segments               :1741-1760       */
+    const double *seg_z1, *seg_z2, *seg_R, *seg_rmid;     /* [n_seg], [n_seg], [n_seg], [n_seg,3]            */
+    const double *M_struc;          /* [36] fowt.M_struc (Pinkster IV term, raft_fowt.py:2044)               */
+} raftk_slender;
+
+size_t raftk_qtf_slender_workspace_bytes(const raftk_slender *s, int32_t n_cases);
+int raftk_qtf_slender_dev(const raftk_slender *s, int32_t n_cases, const double *beta_rad, const double *Xi_rao, double *qtf,
+                          void *workspace, size_t workspace_bytes, void *stream);
+int raftk_qtf_slender_host(const raftk_slender *s, int32_t n_cases, const double *beta_rad, const double *Xi_rao, double *qtf);
 
 /* Same three operations with HOST pointers everywhere (tables, cases, outputs). */
 int raftk_hydro_excitation_host(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out);

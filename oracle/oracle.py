@@ -33,7 +33,34 @@ class RoDesign(C.Structure):
         ("X_BEM", C.c_void_p), ("bem_headings", c_double_p), ("node_Imat_w", C.c_void_p),
         ("n_qtf_w", C.c_int), ("n_qtf_head", C.c_int),
         ("qtf_w", c_double_p), ("qtf_heads", c_double_p), ("qtf", C.c_void_p),
+        ("qs", C.c_void_p), ("qs_nw", C.c_int), ("qs_w", c_double_p), ("qs_k", c_double_p),
     ]
+
+
+_QS_ARRAYS = ("mem_q", "mem_p1", "mem_p2", "mem_mcf", "mem_wl", "mem_r_int", "mem_a_wl", "mem_rwl", "mem_R_wl", "node_mem", "node_r",
+              "node_v_side", "node_Ca_p1", "node_Ca_p2", "node_Ca_End", "node_v_end", "node_a_i", "seg_mem", "seg_z1", "seg_z2", "seg_R",
+              "seg_rmid", "M_struc")
+
+
+class RoQtfDesign(C.Structure):
+    """ro_qtf_design: member tables of the slender-body QTF (raft_b200.packer.pack_qtf_members, keys qs_*)."""
+    _fields_ = [("n_nodes", C.c_int), ("n_members", C.c_int), ("n_seg", C.c_int),
+                ("depth", C.c_double), ("rho", C.c_double), ("g", C.c_double)] + [(n, C.c_void_p) for n in _QS_ARRAYS]
+
+
+def _qs_struct(P, keep):
+    q = RoQtfDesign()
+    q.n_nodes, q.n_members, q.n_seg = len(P["qs_node_mem"]), len(P["qs_mem_mcf"]), len(P["qs_seg_mem"])
+    q.depth, q.rho, q.g = float(P["qs_depth"]), float(P["qs_rho"]), float(P["qs_g"])
+    for n in _QS_ARRAYS:
+        a = np.ascontiguousarray(P["qs_" + n])
+        if a.dtype.kind == "i":
+            a = np.ascontiguousarray(a, dtype=np.int32)
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+        keep["qs_" + n] = a
+        setattr(q, n, a.ctypes.data)
+    return q
 
 
 def build(force=False):
@@ -112,6 +139,12 @@ class OracleDesign:
             assert k["qtf"].shape == (d.n_qtf_w, d.n_qtf_w, d.n_qtf_head, 6)
             d.qtf_w, d.qtf_heads = _dp(k["qtf_w"]), _dp(k["qtf_heads"])
             d.qtf = k["qtf"].ctypes.data_as(C.c_void_p)
+        if P.get("qs_w") is not None:
+            # slender-body QTF (potSecOrder 1): member tables + second-order grid
+            self.qs = _qs_struct(P, k)
+            k["qs_w"], k["qs_k"] = f8(P["qs_w"]), f8(P["qs_k"])
+            d.qs = C.addressof(self.qs)
+            d.qs_nw, d.qs_w, d.qs_k = len(k["qs_w"]), _dp(k["qs_w"]), _dp(k["qs_k"])
         self.c = d
 
 
@@ -197,6 +230,18 @@ def hydro_force_2nd(od, beta, S0):
     fm, f = np.zeros(6), np.zeros([6, od.nw])
     lib().ro_hydro_force_2nd(C.byref(od.c), C.c_double(float(beta)), _dp(S0), _dp(fm), _dp(f))
     return fm, f
+
+
+def qtf_slender(od, beta, Xi):
+    """FOWT.calcQTF_slenderBody: heading ``beta`` [rad], motion RAOs ``Xi`` [6, nw2] on the second-order grid
+    -> qtf [nw2, nw2, 6] complex, Hermitian-filled (fowt.qtf[:, :, 0, :])."""
+    n2 = od.c.qs_nw
+    Xi = np.ascontiguousarray(Xi, dtype=np.complex128)
+    assert Xi.shape == (6, n2)
+    out = np.zeros([n2, n2, 6], dtype=np.complex128)
+    lib().ro_qtf_slender(C.byref(od.qs), C.c_int(n2), od.c.qs_w, od.c.qs_k, C.c_double(float(beta)),
+                         Xi.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def solve_dynamics(od, spec, Hs, Tp, gamma, beta_deg, nIter=10, tol=0.01, XiStart=0.0, want_Z=False):

@@ -17,8 +17,9 @@
  * the reference are kept on purpose: this is the checker for the restructured CUDA kernels.
  *
  * Scope: rigid 6-DOF FOWT (MacCamy-Fuchs Imat as an input table), no underwater rotor; second-order forces only
- * from an external QTF table (potSecOrder 2; raft_fowt.py:2158-2253), not the slender-body QTF (potSecOrder 1)
- * (BASELINE.json configs 1-4; SURVEY.md section 8a rows a1-a11 + 8f row 3).
+ * from an external QTF table (potSecOrder 2; raft_fowt.py:2158-2253) or the slender-body QTF (potSecOrder 1;
+ * raft_fowt.py:1988-2078, raft_member.py:1488-1792, helpers.py:239-373), single wave train for the latter
+ * (BASELINE.json configs 1-4; SURVEY.md section 8a rows a1-a11 + 8f rows 3-4).
  */
 #include <complex.h>
 #include <math.h>
@@ -54,6 +55,10 @@ typedef struct {
     const double *qtf_w;                           /* [n_qtf_w] rad/s ascending (w1_2nd == w2_2nd)   */
     const double *qtf_heads;                       /* [n_qtf_head] rad ascending (heads_2nd)        */
     const cplx *qtf;                               /* [n_qtf_w,n_qtf_w,n_qtf_head,6] (reference layout) */
+    /* slender-body QTF (potSecOrder 1): member tables + second-order grid, or qs == NULL */
+    const struct ro_qtf_design_s *qs;
+    int qs_nw;
+    const double *qs_w, *qs_k;                     /* [qs_nw] w1_2nd, k1_2nd                              */
 } ro_design;
 
 /* helpers.py:377-392 waveNumber(omega, h, e=0.001) */
@@ -424,6 +429,389 @@ int ro_zinv(int n, cplx *A, cplx *Ainv)
     return info;
 }
 
+
+/* ======================================================================================================
+ * Slender-body QTF (potSecOrder 1): FOWT.calcQTF_slenderBody (raft_fowt.py:1988-2078),
+ * Member.calcQTF_slenderBody + correction_KAY (raft_member.py:1488-1792) and the second-order wave kinematics
+ * helpers (helpers.py:239-373).  Loop order and the reference's quirks are kept:
+ *   - getWaveKin_grad_u1 / grad_pres1st / pot2ndOrd apply deg2rad to a heading that is already in radians for the
+ *     amplitude factors (cosBeta, sinBeta) while the phase of grad_u1 uses the heading itself (helpers.py:244-245, 262);
+ *   - getWaveKin_axdivAcc removes the axial component of the node velocities IN PLACE (helpers.py:320-321, the
+ *     arguments are views of nodeV), so every later use of nodeV in the pair loop sees the transverse part only,
+ *     while nodeV_axial_rel was computed before from the full velocity (raft_member.py:1517).
+ * ====================================================================================================== */
+typedef struct ro_qtf_design_s {
+    int n_nodes, n_members, n_seg;
+    double depth, rho, g;
+    const double *mem_q, *mem_p1, *mem_p2;   /* [Nm,3]                                                      */
+    const int *mem_mcf;                      /* [Nm] 1: Kim & Yue correction applies (mem.MCF and rA_z * rB_z < 0) */
+    const int *mem_wl;                       /* [Nm] 1: the member crosses the mean waterline                */
+    const double *mem_r_int;                 /* [Nm,3] intersection with z = 0 (raft_member.py:1528)         */
+    const double *mem_a_wl;                  /* [Nm] cross-section area at the waterline (:1660-1674)        */
+    const double *mem_rwl;                   /* [Nm,3] KAY: waterline point from rA, rB (:1723)              */
+    const double *mem_R_wl;                  /* [Nm] KAY: radius at z = 0 (:1725)                            */
+    const int *node_mem;                     /* [Ns] submerged strip nodes (r_z < 0), grouped by member      */
+    const double *node_r;                    /* [Ns,3]                                                       */
+    const double *node_v_side, *node_Ca_p1, *node_Ca_p2, *node_Ca_End, *node_v_end, *node_a_i;   /* [Ns]   */
+    const int *seg_mem;                      /* [n_seg] KAY integration segments (:1741-1760)                */
+    const double *seg_z1, *seg_z2, *seg_R, *seg_rmid;  /* [n_seg], [n_seg], [n_seg], [n_seg,3]               */
+    const double *M_struc;                   /* [6,6] fowt.M_struc (Pinkster IV term, raft_fowt.py:2044)     */
+} ro_qtf_design;
+
+typedef struct { cplx v[3]; } c3;
+
+static c3 c3_zero(void) { c3 r; r.v[0] = r.v[1] = r.v[2] = 0; return r; }
+static c3 c3_add(c3 a, c3 b) { c3 r; for (int i = 0; i < 3; i++) r.v[i] = a.v[i] + b.v[i]; return r; }
+static c3 c3_sub(c3 a, c3 b) { c3 r; for (int i = 0; i < 3; i++) r.v[i] = a.v[i] - b.v[i]; return r; }
+static c3 c3_scale(c3 a, cplx s) { c3 r; for (int i = 0; i < 3; i++) r.v[i] = a.v[i] * s; return r; }
+static c3 c3_conj(c3 a) { c3 r; for (int i = 0; i < 3; i++) r.v[i] = conj(a.v[i]); return r; }
+static cplx c3_dotr(c3 a, const double *d) { return a.v[0] * d[0] + a.v[1] * d[1] + a.v[2] * d[2]; }
+static cplx c3_dot(c3 a, c3 b) { return a.v[0] * b.v[0] + a.v[1] * b.v[1] + a.v[2] * b.v[2]; }   /* np.dot: no conjugation */
+static c3 c3_vecr(const double *d, cplx s) { c3 r; for (int i = 0; i < 3; i++) r.v[i] = d[i] * s; return r; }
+static c3 m33_mul(cplx M[3][3], c3 x) { c3 r; for (int i = 0; i < 3; i++) r.v[i] = M[i][0] * x.v[0] + M[i][1] * x.v[1] + M[i][2] * x.v[2]; return r; }
+static c3 m33c_mul(cplx M[3][3], c3 x) { c3 r; for (int i = 0; i < 3; i++) r.v[i] = conj(M[i][0]) * x.v[0] + conj(M[i][1]) * x.v[1] + conj(M[i][2]) * x.v[2]; return r; }
+/* (a p1 p1' + b p2 p2') v */
+static c3 proj_p(const double *p1, const double *p2, double a, double b, c3 v)
+{
+    return c3_add(c3_vecr(p1, a * c3_dotr(v, p1)), c3_vecr(p2, b * c3_dotr(v, p2)));
+}
+static c3 proj_q(const double *q, c3 v) { return c3_vecr(q, c3_dotr(v, q)); }
+
+/* helpers.py:239-278 getWaveKin_grad_u1 (beta in radians, see the quirk note above) */
+static void grad_u1(double w, double k, double beta, double h, const double *r, cplx G[3][3])
+{
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) G[i][j] = 0;
+    double z = r[2];
+    double cosBeta = cos(beta * 0.017453292519943295), sinBeta = sin(beta * 0.017453292519943295);
+    if (z <= 0 && k > 0) {
+        double khz_xy, khz_z;
+        if (k * h >= 10) { khz_xy = exp(k * z); khz_z = khz_xy; }
+        else { khz_xy = cosh(k * (z + h)) / sinh(k * h); khz_z = sinh(k * (z + h)) / sinh(k * h); }
+        cplx ph = cexp(-I * (k * (cos(beta) * r[0] + sin(beta) * r[1])));
+        cplx aux = w * cosBeta * ph;
+        G[0][0] = -I * aux * khz_xy * k * cosBeta;
+        G[0][1] = -I * aux * khz_xy * k * sinBeta;
+        G[0][2] = aux * k * khz_z;
+        aux = w * sinBeta * ph;
+        G[1][0] = G[0][1];
+        G[1][1] = -I * aux * khz_xy * k * sinBeta;
+        G[1][2] = aux * k * khz_z;
+        aux = I * w * ph;
+        G[2][0] = G[0][2];
+        G[2][1] = G[0][1];
+        G[2][2] = aux * k * khz_xy;
+    }
+}
+
+/* helpers.py:285-308 getWaveKin_grad_pres1st */
+static c3 grad_pres1st(double k, double beta, double h, const double *r, double rho, double g)
+{
+    c3 gr = c3_zero();
+    double z = r[2];
+    double cosBeta = cos(beta * 0.017453292519943295), sinBeta = sin(beta * 0.017453292519943295);
+    if (z <= 0 && k > 0) {
+        double khz_xy, khz_z;
+        if (k * h >= 10) { khz_xy = exp(k * z); khz_z = khz_xy; }
+        else { khz_xy = cosh(k * (z + h)) / cosh(k * h); khz_z = sinh(k * (z + h)) / cosh(k * h); }
+        cplx ph = cexp(-I * (k * (cosBeta * r[0] + sinBeta * r[1])));
+        gr.v[0] = rho * g * khz_xy * ph * (-I * k * cosBeta);
+        gr.v[1] = rho * g * khz_xy * ph * (-I * k * sinBeta);
+        gr.v[2] = rho * g * khz_z * ph * k;
+    }
+    return gr;
+}
+
+/* getWaveKin for one frequency and unit amplitude -> u, ud, pDyn (helpers.py:188-236) */
+static void wave_kin1(double beta, double w, double k, double h, const double *r, double rho, double g, c3 *u, c3 *ud, cplx *pDyn)
+{
+    double one = 1.0;
+    cplx uu[3], uud[3], p;
+    ro_wave_kin(&one, beta, &w, &k, h, r, 1, rho, g, uu, uud, &p);
+    for (int i = 0; i < 3; i++) { if (u) u->v[i] = uu[i]; if (ud) ud->v[i] = uud[i]; }
+    if (pDyn) *pDyn = p;
+}
+
+/* helpers.py:311-334 getWaveKin_axdivAcc; vel1/vel2 are already the transverse node velocities */
+static c3 axdiv_acc(double w1, double w2, double k1, double k2, double beta, double h, const double *r, c3 vel1, c3 vel2,
+                    const double *q, double g)
+{
+    cplx G[3][3];
+    c3 qv = c3_vecr(q, 1.0);
+    grad_u1(w1, k1, beta, h, r, G);
+    cplx dwdz1 = c3_dotr(m33_mul(G, qv), q);
+    c3 u1, u2;
+    wave_kin1(beta, w1, k1, h, r, 1025.0, g, &u1, NULL, NULL);
+    grad_u1(w2, k2, beta, h, r, G);
+    cplx dwdz2 = c3_dotr(m33_mul(G, qv), q);
+    wave_kin1(beta, w2, k2, h, r, 1025.0, g, &u2, NULL, NULL);
+    vel1 = c3_sub(vel1, proj_q(q, vel1));
+    vel2 = c3_sub(vel2, proj_q(q, vel2));
+    u1 = c3_sub(u1, proj_q(q, u1));
+    u2 = c3_sub(u2, proj_q(q, u2));
+    c3 acc = c3_add(c3_scale(c3_conj(c3_sub(u2, vel2)), 0.25 * dwdz1), c3_scale(c3_sub(u1, vel1), 0.25 * conj(dwdz2)));
+    acc = c3_sub(acc, proj_q(q, acc));
+    return acc;
+}
+
+/* helpers.py:337-373 getWaveKin_pot2ndOrd (beta1 == beta2 == beta) */
+static void pot_2nd(double w1, double w2, double k1, double k2, double beta, double h, const double *r, double g, double rho,
+                    c3 *acc, cplx *p)
+{
+    *acc = c3_zero(); *p = 0;
+    if (w1 == w2) return;
+    double b = beta * 0.017453292519943295, cosB = cos(b), sinB = sin(b), z = r[2];
+    if (z <= 0 && k1 > 0 && k2 > 0) {
+        double kk[3] = { k1 * cosB - k2 * cosB, k1 * sinB - k2 * sinB, 0 };
+        double nk = sqrt(kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2]);
+        double t1 = tanh(k1 * h), t2 = tanh(k2 * h);
+        cplx g12 = (-I * g / (2 * w1)) * ((k1 * k1) * (1 - t1 * t1) - 2 * k1 * k2 * (1 + t1 * t2)) / ((w1 - w2) * (w1 - w2) / g - nk * tanh(nk * h));
+        cplx g21 = (-I * g / (2 * w2)) * ((k2 * k2) * (1 - t2 * t2) - 2 * k2 * k1 * (1 + t2 * t1)) / ((w2 - w1) * (w2 - w1) / g - nk * tanh(nk * h));
+        cplx aux = 0.5 * (g21 + conj(g12));
+        double khz_xy = cosh(nk * (z + h)) / cosh(nk * h), khz_z = sinh(nk * (z + h)) / cosh(nk * h);
+        cplx ph = cexp(-I * (kk[0] * r[0] + kk[1] * r[1] + kk[2] * r[2]));
+        acc->v[0] = aux * khz_xy * ph; acc->v[1] = acc->v[0];
+        acc->v[0] *= (w1 - w2) * (k1 * cosB - k2 * cosB);
+        acc->v[1] *= (w1 - w2) * (k1 * sinB - k2 * sinB);
+        acc->v[2] = aux * khz_z * ph;
+        acc->v[2] *= I * (w1 - w2) * nk;
+        *p = aux * khz_xy * ph;
+        *p *= -I * rho * (w1 - w2);
+    }
+}
+
+static cplx hankel1(int n, double x)
+{
+    if (n < 0) { cplx hv = jn(-n, x) + I * yn(-n, x); return ((-n) & 1) ? -hv : hv; }   /* H_{-n} = (-1)^n H_n */
+    return jn(n, x) + I * yn(n, x);
+}
+static cplx kay_omega(double k1R, double k2R, int n)
+{
+    cplx H_N_ii = 0.5 * (hankel1(n - 1, k1R) - hankel1(n + 1, k1R));
+    cplx H_N_jj = 0.5 * conj(hankel1(n - 1, k2R) - hankel1(n + 1, k2R));
+    cplx H_Nm1_ii = 0.5 * (hankel1(n, k1R) - hankel1(n + 2, k1R));
+    cplx H_Nm1_jj = 0.5 * conj(hankel1(n, k2R) - hankel1(n + 2, k2R));
+    return 1 / (H_Nm1_ii * H_N_jj) - 1 / (H_N_ii * H_Nm1_jj);
+}
+
+/* raft_member.py:1680-1792 correction_KAY for member m, Nm = 10 */
+static void correction_kay(const ro_qtf_design *d, int m, double w1, double w2, double k1, double k2, double beta, cplx F[6])
+{
+    for (int a = 0; a < 6; a++) F[a] = 0;
+    if (!d->mem_mcf[m]) return;
+    double h = d->depth, rho = d->rho, g = d->g;
+    const double *p1 = d->mem_p1 + 3 * m, *p2 = d->mem_p2 + 3 * m;
+    double cosB = cos(beta), sinB = sin(beta);
+    double kk[3] = { k1 * cosB - k2 * cosB, k1 * sinB - k2 * sinB, 0 };
+    double bv[3] = { cosB, sinB, 0 };
+    double d1 = bv[0] * p1[0] + bv[1] * p1[1] + bv[2] * p1[2], d2 = bv[0] * p2[0] + bv[1] * p2[1] + bv[2] * p2[2];
+    double pf[3] = { d1 * p1[0] + d2 * p2[0], d1 * p1[1] + d2 * p2[1], d1 * p1[2] + d2 * p2[2] };
+    double nrm = sqrt(pf[0] * pf[0] + pf[1] * pf[1] + pf[2] * pf[2]);
+    for (int i = 0; i < 3; i++) pf[i] /= nrm;
+    {   /* mem_mcf already folds in rA_z * rB_z < 0 (:1721, :1741): without a waterline crossing the correction is zero */
+        const double *rwl = d->mem_rwl + 3 * m;
+        double R = d->mem_R_wl[m], k1R = k1 * R, k2R = k2 * R;
+        cplx Fwl = 0;
+        for (int nn = 0; nn <= 10; nn++) Fwl += -rho * g * R * 2 * I / M_PI / (k1R * k2R) * kay_omega(k1R, k2R, nn);
+        cplx ph = cexp(-I * (kk[0] * rwl[0] + kk[1] * rwl[1] + kk[2] * rwl[2]));
+        cplx Fs = creal(Fwl) * ph;
+        cplx f3[3] = { Fs * pf[0], Fs * pf[1], Fs * pf[2] }, f6[6];
+        translate_force(f3, rwl, f6);
+        for (int a = 0; a < 6; a++) F[a] += f6[a];
+        for (int s = 0; s < d->n_seg; s++) {
+            if (d->seg_mem[s] != m) continue;
+            double z1 = d->seg_z1[s], z2 = d->seg_z2[s];
+            R = d->seg_R[s]; k1R = k1 * R; k2R = k2 * R;
+            double H = h / R, k1h = k1R * H, k2h = k2R * H, Im, Ip;
+            if (w1 == w2) {
+                Im = 0.5 * (sinh((k1 + k2) * (z2 + h)) / (k1h + k2h) - (z2 + h) / h - sinh((k1 + k2) * (z1 + h)) / (k1h + k2h) + (z1 + h) / h);
+                Ip = 0.5 * (sinh((k1 + k2) * (z2 + h)) / (k1h + k2h) + (z2 + h) / h - sinh((k1 + k2) * (z1 + h)) / (k1h + k2h) - (z1 + h) / h);
+            } else {
+                Im = 0.5 * (sinh((k1 + k2) * (z2 + h)) / (k1h + k2h) - sinh((k1 - k2) * (z2 + h)) / (k1h - k2h) - sinh((k1 + k2) * (z1 + h)) / (k1h + k2h) + sinh((k1 - k2) * (z1 + h)) / (k1h - k2h));
+                Ip = 0.5 * (sinh((k1 + k2) * (z2 + h)) / (k1h + k2h) + sinh((k1 - k2) * (z2 + h)) / (k1h - k2h) - sinh((k1 + k2) * (z1 + h)) / (k1h + k2h) - sinh((k1 - k2) * (z1 + h)) / (k1h - k2h));
+            }
+            double c1 = cosh(k1h), c2 = cosh(k2h);
+            cplx dF = 0;
+            for (int nn = 0; nn <= 10; nn++)
+                dF += rho * g * R * 2 * I / M_PI / (k1R * k2R) * kay_omega(k1R, k2R, nn)
+                      * (k1h * k2h / sqrt(k1h * tanh(k1h)) / sqrt(k2h * tanh(k2h)) * (Im + Ip * nn * (nn + 1) / k1R / k2R) / c1 / c2);
+            cplx dFs = creal(dF) * ph;
+            cplx g3[3] = { dFs * pf[0], dFs * pf[1], dFs * pf[2] }, g6[6];
+            translate_force(g3, d->seg_rmid + 3 * s, g6);
+            for (int a = 0; a < 6; a++) F[a] += g6[a];
+        }
+    }
+    if (k1 < k2) for (int a = 0; a < 6; a++) F[a] = conj(F[a]);
+}
+
+/* Member.calcQTF_slenderBody for member m, accumulated into qtf [nw][nw][6] (upper triangle w2 >= w1) */
+static void member_qtf(const ro_qtf_design *d, int m, int nw, const double *w, const double *k, double beta, const cplx *Xi, cplx *qtf)
+{
+    double h = d->depth, rho = d->rho, g = d->g;
+    const double *q = d->mem_q + 3 * m, *p1 = d->mem_p1 + 3 * m, *p2 = d->mem_p2 + 3 * m;
+    int j0 = -1, j1 = -1;
+    for (int j = 0; j < d->n_nodes; j++) if (d->node_mem[j] == m) { if (j0 < 0) j0 = j; j1 = j + 1; }
+    int ns = j0 < 0 ? 0 : j1 - j0;
+    /* per node, per frequency kinematics (raft_member.py:1501-1521) */
+    c3 *dr = malloc(sizeof(c3) * (size_t)(ns + 1) * nw), *nodeV = malloc(sizeof(c3) * (size_t)(ns + 1) * nw), *u = malloc(sizeof(c3) * (size_t)(ns + 1) * nw);
+    c3 *gp = malloc(sizeof(c3) * (size_t)(ns + 1) * nw);
+    cplx (*G)[3][3] = malloc(sizeof(cplx[3][3]) * (size_t)(ns + 1) * nw), (*Gd)[3][3] = malloc(sizeof(cplx[3][3]) * (size_t)(ns + 1) * nw);
+    cplx *vax = malloc(sizeof(cplx) * (size_t)(ns + 1) * nw);
+    cplx *t3 = malloc(sizeof(cplx) * 3 * nw), *t3b = malloc(sizeof(cplx) * 3 * nw), *t3c = malloc(sizeof(cplx) * 3 * nw);
+    for (int n = 0; n < ns; n++) {
+        const double *r = d->node_r + 3 * (j0 + n);
+        ro_get_kinematics(r, Xi, w, nw, t3, t3b, t3c);
+        for (int i = 0; i < nw; i++) {
+            size_t e = (size_t)n * nw + i;
+            for (int a = 0; a < 3; a++) { dr[e].v[a] = t3[a * nw + i]; nodeV[e].v[a] = t3b[a * nw + i]; }
+            wave_kin1(beta, w[i], k[i], h, r, rho, g, &u[e], NULL, NULL);
+            grad_u1(w[i], k[i], beta, h, r, G[e]);
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Gd[e][a][b] = I * w[i] * G[e][a][b];
+            vax[e] = c3_dotr(c3_sub(u[e], nodeV[e]), q);
+            gp[e] = grad_pres1st(k[i], beta, h, r, rho, g);
+            nodeV[e] = c3_sub(nodeV[e], proj_q(q, nodeV[e]));        /* the in-place side effect of getWaveKin_axdivAcc */
+        }
+    }
+    /* waterline quantities (:1524-1539) */
+    cplx *eta_r = calloc(nw, sizeof(cplx));
+    c3 *ud_wl = calloc(nw, sizeof(c3)), *a_wl = calloc(nw, sizeof(c3)), *g_e1 = calloc(nw, sizeof(c3));
+    const double *r_int = d->mem_r_int + 3 * m;
+    if (d->mem_wl[m]) {
+        ro_get_kinematics(r_int, Xi, w, nw, t3, t3b, t3c);
+        for (int i = 0; i < nw; i++) {
+            cplx eta;
+            wave_kin1(beta, w[i], k[i], h, r_int, 1.0, 1.0, NULL, &ud_wl[i], &eta);
+            for (int a = 0; a < 3; a++) a_wl[i].v[a] = t3c[a * nw + i];
+            eta_r[i] = eta - t3[2 * nw + i];
+        }
+    }
+    for (int i = 0; i < nw; i++) {
+        const cplx *th = Xi + 3 * nw;      /* Xi[3:, i] = th[0*nw+i], th[nw+i], th[2nw+i] */
+        cplx a = th[i], b = th[nw + i];
+        cplx c1z = a * p1[1] - b * p1[0], c2z = a * p2[1] - b * p2[0];       /* cross(theta, p)[2] */
+        for (int x = 0; x < 3; x++) g_e1[i].v[x] = -g * (c1z * p1[x] + c2z * p2[x]);
+    }
+    for (int i1 = 0; i1 < nw; i1++) {
+        for (int i2 = 0; i2 < nw; i2++) {
+            double w1 = w[i1], w2 = w[i2], k1 = k[i1], k2 = k[i2];
+            if (w2 < w1) continue;
+            cplx F[6] = {0, 0, 0, 0, 0, 0};
+            cplx O1[3][3], O2[3][3];
+            {   /* OMEGA = -getH(1j w Xi[3:]) */
+                cplx a1[3] = { I * w1 * Xi[3 * nw + i1], I * w1 * Xi[4 * nw + i1], I * w1 * Xi[5 * nw + i1] };
+                cplx a2[3] = { I * w2 * Xi[3 * nw + i2], I * w2 * Xi[4 * nw + i2], I * w2 * Xi[5 * nw + i2] };
+                cplx H1[3][3] = { { 0, a1[2], -a1[1] }, { -a1[2], 0, a1[0] }, { a1[1], -a1[0], 0 } };
+                cplx H2[3][3] = { { 0, a2[2], -a2[1] }, { -a2[2], 0, a2[0] }, { a2[1], -a2[0], 0 } };
+                for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { O1[a][b] = -H1[a][b]; O2[a][b] = -H2[a][b]; }
+            }
+            for (int n = 0; n < ns; n++) {
+                int jg = j0 + n;
+                const double *r = d->node_r + 3 * jg;
+                size_t e1 = (size_t)n * nw + i1, e2 = (size_t)n * nw + i2;
+                double Ca1 = d->node_Ca_p1[jg], Ca2 = d->node_Ca_p2[jg], CaE = d->node_Ca_End[jg];
+                double v_i = d->node_v_side[jg], v_e = d->node_v_end[jg], a_i = d->node_a_i[jg];
+                c3 acc2; cplx p2nd;
+                pot_2nd(w1, w2, k1, k2, beta, h, r, g, rho, &acc2, &p2nd);
+                c3 f_2ndPot = c3_scale(proj_p(p1, p2, 1. + Ca1, 1. + Ca2, acc2), rho * v_i);
+                c3 conv_acc = c3_scale(c3_add(m33_mul(G[e1], c3_conj(u[e2])), m33c_mul(G[e2], u[e1])), 0.25);
+                c3 f_conv = c3_scale(proj_p(p1, p2, 1. + Ca1, 1. + Ca2, conv_acc), rho * v_i);
+                c3 f_axdv = c3_scale(proj_p(p1, p2, Ca1, Ca2, axdiv_acc(w1, w2, k1, k2, beta, h, r, nodeV[e1], nodeV[e2], q, g)), rho * v_i);
+                c3 acc_nabla = c3_add(c3_scale(m33_mul(Gd[e1], c3_conj(dr[e2])), 0.25), c3_scale(m33c_mul(Gd[e2], dr[e1]), 0.25));
+                c3 f_nabla = c3_scale(proj_p(p1, p2, 1. + Ca1, 1. + Ca2, acc_nabla), rho * v_i);
+                c3 t = c3_add(m33_mul(O1, c3_conj(c3_vecr(q, vax[e2]))), m33c_mul(O2, c3_vecr(q, vax[e1])));
+                c3 f_rslb = c3_scale(proj_p(p1, p2, Ca1, Ca2, t), -0.25 * 2);
+                f_rslb = c3_scale(f_rslb, rho * v_i);
+                c3 u1a = c3_sub(u[e1], nodeV[e1]), u2a = c3_sub(u[e2], nodeV[e2]);
+                cplx V1[3][3], V2[3][3];
+                for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { V1[a][b] = G[e1][a][b] + O1[a][b]; V2[a][b] = G[e2][a][b] + O2[a][b]; }
+                c3 aux = c3_scale(c3_add(m33_mul(V1, c3_conj(proj_p(p1, p2, Ca1, Ca2, u2a))), m33c_mul(V2, proj_p(p1, p2, Ca1, Ca2, u1a))), 0.25);
+                aux = c3_sub(aux, proj_q(q, aux));
+                f_rslb = c3_add(f_rslb, c3_scale(aux, rho * v_i));
+                u1a = c3_sub(u1a, proj_q(q, u1a));
+                u2a = c3_sub(u2a, proj_q(q, u2a));
+                aux = c3_scale(c3_add(proj_p(p1, p2, Ca1, Ca2, m33_mul(V1, c3_conj(u2a))), proj_p(p1, p2, Ca1, Ca2, m33c_mul(V2, u1a))), 0.25);
+                f_rslb = c3_add(f_rslb, c3_scale(aux, -rho * v_i));
+                /* axial / end effects */
+                f_2ndPot = c3_add(f_2ndPot, c3_vecr(q, a_i * p2nd));
+                f_2ndPot = c3_add(f_2ndPot, c3_scale(proj_q(q, acc2), rho * v_e * CaE));
+                f_conv = c3_add(f_conv, c3_scale(proj_q(q, conv_acc), rho * v_e * CaE));
+                f_nabla = c3_add(f_nabla, c3_scale(proj_q(q, acc_nabla), rho * v_e * CaE));
+                cplx p_nabla = 0.25 * c3_dot(gp[e1], c3_conj(dr[e2])) + 0.25 * c3_dot(c3_conj(gp[e2]), dr[e1]);
+                f_nabla = c3_add(f_nabla, c3_vecr(q, a_i * p_nabla));
+                cplx p_drop = -2 * 0.25 * 0.5 * rho * c3_dot(proj_p(p1, p2, 1.0, 1.0, c3_sub(u[e1], nodeV[e1])),
+                                                               c3_conj(proj_p(p1, p2, Ca1, Ca2, c3_sub(u[e2], nodeV[e2]))));
+                f_conv = c3_add(f_conv, c3_vecr(q, a_i * p_drop));
+                u1a = proj_p(p1, p2, Ca1, Ca2, u1a);
+                u2a = proj_p(p1, p2, Ca1, Ca2, u2a);
+                c3 f_transv = c3_scale(c3_add(c3_scale(c3_conj(u1a), vax[e2]), c3_scale(u2a, conj(vax[e1]))), 0.25 * a_i * rho);
+                f_conv = c3_add(f_conv, f_transv);
+                c3 parts[5] = { f_2ndPot, f_conv, f_axdv, f_nabla, f_rslb };
+                for (int pz = 0; pz < 5; pz++) {
+                    cplx f6[6];
+                    translate_force(parts[pz].v, r, f6);
+                    for (int a = 0; a < 6; a++) F[a] += f6[a];
+                }
+            }
+            if (d->mem_wl[m]) {          /* relative-wave-elevation force at the waterline (:1655-1683) */
+                double a_i = d->mem_a_wl[m];
+                double Ca1 = 0, Ca2 = 0;
+                if (ns > 0) { Ca1 = d->node_Ca_p1[j1 - 1]; Ca2 = d->node_Ca_p2[j1 - 1]; }   /* the loop variables keep the last submerged node's values */
+                c3 fe = c3_scale(c3_add(c3_scale(ud_wl[i1], conj(eta_r[i2])), c3_scale(c3_conj(ud_wl[i2]), eta_r[i1])), 0.25);
+                fe = c3_scale(proj_p(p1, p2, 1. + Ca1, 1. + Ca2, fe), rho * a_i);
+                c3 ae = c3_scale(c3_add(c3_scale(a_wl[i1], conj(eta_r[i2])), c3_scale(c3_conj(a_wl[i2]), eta_r[i1])), 0.25);
+                fe = c3_sub(fe, c3_scale(proj_p(p1, p2, Ca1, Ca2, ae), rho * a_i));
+                fe = c3_sub(fe, c3_scale(c3_add(c3_scale(g_e1[i1], conj(eta_r[i2])), c3_scale(c3_conj(g_e1[i2]), eta_r[i1])), 0.25 * rho * a_i));
+                cplx f6[6];
+                translate_force(fe.v, r_int, f6);
+                for (int a = 0; a < 6; a++) F[a] += f6[a];
+            }
+            cplx K[6];
+            correction_kay(d, m, w1, w2, k1, k2, beta, K);
+            for (int a = 0; a < 6; a++) qtf[((size_t)i1 * nw + i2) * 6 + a] += F[a] + K[a];
+        }
+    }
+    free(dr); free(nodeV); free(u); free(gp); free(G); free(Gd); free(vax); free(t3); free(t3b); free(t3c);
+    free(eta_r); free(ud_wl); free(a_wl); free(g_e1);
+}
+
+/* FOWT.calcQTF_slenderBody (raft_fowt.py:1988-2078): Xi [6][nw] RAOs already on the second-order grid w (:2021-2023).
+ * qtf [nw][nw][6], Hermitian-filled (:2068-2070). */
+void ro_qtf_slender(const ro_qtf_design *d, int nw, const double *w, const double *k, double beta, const cplx *Xi, cplx *qtf)
+{
+    for (size_t e = 0; e < (size_t)nw * nw * 6; e++) qtf[e] = 0;
+    /* Pinkster IV: rotation of the first-order forces, F1st = M_struc (-w^2 Xi) (:2044-2058) */
+    cplx *F1 = malloc(sizeof(cplx) * 6 * nw);
+    for (int a = 0; a < 6; a++)
+        for (int i = 0; i < nw; i++) {
+            cplx s = 0;
+            for (int b = 0; b < 6; b++) s += d->M_struc[6 * a + b] * (-w[i] * w[i] * Xi[b * nw + i]);
+            F1[a * nw + i] = s;
+        }
+#define CROSS(o, a0, a1, a2, b0, b1, b2) do { o[0] = (a1) * (b2) - (a2) * (b1); o[1] = (a2) * (b0) - (a0) * (b2); o[2] = (a0) * (b1) - (a1) * (b0); } while (0)
+    for (int i1 = 0; i1 < nw; i1++)
+        for (int i2 = i1; i2 < nw; i2++) {
+            if (w[i2] < w[i1]) continue;
+            cplx t1[3], t2[3], x1[3] = { Xi[3 * nw + i1], Xi[4 * nw + i1], Xi[5 * nw + i1] };
+            cplx x2c[3] = { conj(Xi[3 * nw + i2]), conj(Xi[4 * nw + i2]), conj(Xi[5 * nw + i2]) };
+            cplx *o = qtf + ((size_t)i1 * nw + i2) * 6;
+            CROSS(t1, x1[0], x1[1], x1[2], conj(F1[0 * nw + i2]), conj(F1[1 * nw + i2]), conj(F1[2 * nw + i2]));
+            CROSS(t2, x2c[0], x2c[1], x2c[2], F1[0 * nw + i1], F1[1 * nw + i1], F1[2 * nw + i1]);
+            for (int a = 0; a < 3; a++) o[a] = 0.25 * (t1[a] + t2[a]);
+            CROSS(t1, x1[0], x1[1], x1[2], conj(F1[3 * nw + i2]), conj(F1[4 * nw + i2]), conj(F1[5 * nw + i2]));
+            CROSS(t2, x2c[0], x2c[1], x2c[2], F1[3 * nw + i1], F1[4 * nw + i1], F1[5 * nw + i1]);
+            for (int a = 0; a < 3; a++) o[3 + a] = 0.25 * (t1[a] + t2[a]);
+        }
+#undef CROSS
+    free(F1);
+    for (int m = 0; m < d->n_members; m++) member_qtf(d, m, nw, w, k, beta, Xi, qtf);
+    for (int i1 = 0; i1 < nw; i1++)
+        for (int i2 = i1 + 1; i2 < nw; i2++)
+            for (int a = 0; a < 6; a++) {
+                cplx up = qtf[((size_t)i1 * nw + i2) * 6 + a], lo = qtf[((size_t)i2 * nw + i1) * 6 + a];
+                qtf[((size_t)i1 * nw + i2) * 6 + a] = up + conj(lo);
+                qtf[((size_t)i2 * nw + i1) * 6 + a] = lo + conj(up);
+            }
+}
+
 /* ---- public entry points --------------------------------------------------------------- */
 
 /* FOWT.calcHydroForce_2ndOrd(beta, S0), interpMode 'qtf' (raft_fowt.py:2158-2253): difference-frequency force
@@ -565,7 +953,7 @@ int ro_solve_dynamics(const ro_design *d, int spec, double Hs, double Tp, double
     if (rc) goto done;
     second_order_force(d, spec, Hs, Tp, gamma, beta_deg, F2, NULL);             /* :1035-1038 */
     for (int i = 0; i < 6 * nw; i++) XiLast[i] = XiStart;
-    int passes = 0, conv = 0;
+    int passes = 0, conv = 0, flagQTF = 0;
     for (int iiter = 0; iiter < nIter + 1; iiter++) {                        /* :977, :1052 */
         hydro_linearization(d, u, XiLast, Bmat, B_drag, F_drag);             /* :1063-1064 */
         passes++;
@@ -593,7 +981,42 @@ int ro_solve_dynamics(const ro_design *d, int spec, double Hs, double Tp, double
             double tc = cabs(Xi[i] - XiLast[i]) / (cabs(Xi[i]) + tol);
             if (!(tc < tol)) { all = 0; break; }
         }
-        if (all) { conv = 1; break; }
+        if (all) {
+            if (!d->qs || flagQTF) { conv = 1; break; }                       /* :1106-1107 */
+            /* potSecOrder 1 (:1108-1131): QTF from the motions just found, second-order force added to the excitation,
+               and the loop goes on from the SAME XiLast with its counter reset (iiter = 0, then += 1) */
+            iiter = 0;
+            int n2 = d->qs_nw;
+            cplx *rao = malloc(sizeof(cplx) * 6 * nw), *Xi2 = malloc(sizeof(cplx) * 6 * n2), *qtf = malloc(sizeof(cplx) * (size_t)n2 * n2 * 6);
+            for (int a = 0; a < 6; a++)
+                for (int i = 0; i < nw; i++) rao[a * nw + i] = (fabs(zeta[i]) > 1e-6) ? Xi[a * nw + i] / zeta[i] : 0;   /* helpers.getRAO */
+            for (int a = 0; a < 6; a++)                                      /* np.interp(w1_2nd, w, Xi0, left=0, right=0)  raft_fowt.py:2021-2023 */
+                for (int j = 0; j < n2; j++) {
+                    double x = d->qs_w[j];
+                    cplx v = 0;
+                    if (x >= d->w[0] && x <= d->w[nw - 1]) {
+                        if (x == d->w[nw - 1]) v = rao[a * nw + nw - 1];
+                        else {
+                            int i0 = 0;
+                            while (i0 < nw - 2 && d->w[i0 + 1] <= x) i0++;
+                            cplx y0 = rao[a * nw + i0], y1 = rao[a * nw + i0 + 1];
+                            cplx slope = (y1 - y0) / (d->w[i0 + 1] - d->w[i0]);
+                            v = slope * (x - d->w[i0]) + y0;
+                        }
+                    }
+                    Xi2[a * n2 + j] = v;
+                }
+            ro_qtf_slender(d->qs, n2, d->qs_w, d->qs_k, beta_deg * 0.017453292519943295, Xi2, qtf);
+            ro_design dq = *d;                                                /* calcHydroForce_2ndOrd with fowt.qtf, heads_2nd = [beta] */
+            double head = beta_deg * 0.017453292519943295;
+            dq.n_qtf_w = n2; dq.n_qtf_head = 1; dq.qtf_w = d->qs_w; dq.qtf_heads = &head; dq.qtf = qtf;
+            double *S = malloc(sizeof(double) * nw), *zz = malloc(sizeof(double) * nw), fm[6];
+            ro_sea_state(d->w, nw, d->dw, spec, Hs, Tp, gamma, S, zz);
+            ro_hydro_force_2nd(&dq, head, S, fm, F2);                         /* F_lin += Fhydro_2nd  (:1129-1130) */
+            free(rao); free(Xi2); free(qtf); free(S); free(zz);
+            flagQTF = 1;
+            continue;
+        }
         for (int i = 0; i < 6 * nw; i++) XiLast[i] = 0.2 * XiLast[i] + 0.8 * Xi[i];   /* :1133 */
     }
     status[0] = passes; status[1] = conv;

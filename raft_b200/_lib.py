@@ -33,7 +33,7 @@ class RaftkCases(C.Structure):
     _fields_ = [
         ("n_cases", C.c_int32), ("_pad0", C.c_int32),
         ("Hs", C.c_void_p), ("Tp", C.c_void_p), ("gamma", C.c_void_p), ("beta_deg", C.c_void_p),
-        ("spec", C.c_void_p), ("zeta", C.c_void_p), ("primary", C.c_void_p), ("F_2nd", C.c_void_p),
+        ("spec", C.c_void_p), ("zeta", C.c_void_p), ("primary", C.c_void_p), ("F_2nd", C.c_void_p), ("Xi_init", C.c_void_p),
     ]
 
 
@@ -44,7 +44,17 @@ class RaftkSolveOpts(C.Structure):
 class RaftkOutputs(C.Structure):
     _fields_ = [("Xi", C.c_void_p), ("status", C.c_void_p), ("B_drag", C.c_void_p), ("F_drag", C.c_void_p),
                 ("F_iner", C.c_void_p), ("F_BEM", C.c_void_p), ("zeta", C.c_void_p),
-                ("F_2nd", C.c_void_p), ("F_2nd_mean", C.c_void_p)]
+                ("F_2nd", C.c_void_p), ("F_2nd_mean", C.c_void_p), ("Xi_last", C.c_void_p)]
+
+
+SLENDER_ARRAYS = ("w", "k", "mem_q", "mem_p1", "mem_p2", "mem_mcf", "mem_wl", "mem_r_int", "mem_a_wl", "mem_rwl", "mem_R_wl", "mem_node_start",
+                  "node_r", "node_v_side", "node_Ca_p1", "node_Ca_p2", "node_Ca_End", "node_v_end", "node_a_i",
+                  "seg_mem", "seg_z1", "seg_z2", "seg_R", "seg_rmid", "M_struc")
+
+
+class RaftkSlender(C.Structure):
+    _fields_ = ([("n_nodes", C.c_int32), ("n_members", C.c_int32), ("n_seg", C.c_int32), ("nw", C.c_int32),
+                 ("depth", C.c_double), ("rho", C.c_double), ("g", C.c_double)] + [(n, C.c_void_p) for n in SLENDER_ARRAYS])
 
 
 # every symbol include/raftk.h declares (tests/test_abi.py checks the header against this list)
@@ -54,6 +64,7 @@ SYMBOLS = [
     "raftk_hydro_excitation_dev", "raftk_hydro_linearization_dev", "raftk_solve_dynamics_dev",
     "raftk_hydro_excitation_host", "raftk_hydro_linearization_host", "raftk_solve_dynamics_host",
     "raftk_second_order_force_dev", "raftk_second_order_force_host",
+    "raftk_qtf_slender_workspace_bytes", "raftk_qtf_slender_dev", "raftk_qtf_slender_host",
     "raftk_system_solve_dev", "raftk_system_solve_host", "raftk_response_stats_dev", "raftk_response_stats_host",
     "raftk_channel_stats_dev", "raftk_channel_stats_host", "raftk_host_alloc", "raftk_host_free",
     "raftk_fp64_peak_gflops",
@@ -89,6 +100,12 @@ def _load():
     lib.raftk_solve_dynamics_host.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkSolveOpts), P(RaftkOutputs)]
     lib.raftk_second_order_force_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkOutputs), C.c_void_p]
     lib.raftk_second_order_force_host.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkOutputs)]
+    lib.raftk_qtf_slender_workspace_bytes.restype = C.c_size_t
+    lib.raftk_qtf_slender_workspace_bytes.argtypes = [P(RaftkSlender), C.c_int32]
+    lib.raftk_qtf_slender_dev.argtypes = [P(RaftkSlender), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.raftk_qtf_slender_host.argtypes = [P(RaftkSlender), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.raftk_qtf_slender_dev.restype = C.c_int
+    lib.raftk_qtf_slender_host.restype = C.c_int
     lib.raftk_system_solve_dev.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.raftk_system_solve_host.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.raftk_response_stats_dev.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -105,6 +105,7 @@ extern "C" long long raftk_launch_count(void) { return g_launches; }
 #include "raftk_tables.cuh"
 #include "raftk_fused.cuh"
 #include "raftk_qtf.cuh"
+#include "raftk_slender.cuh"
 #include "raftk_misc.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -177,6 +178,7 @@ static int validate_qtf(const raftk_designs *d, const raftk_cases *c)
     if (d->n_designs <= 0 || d->nw <= 0 || c->n_cases <= 0) return set_err(RAFTK_EINVAL, "empty batch (n_designs, nw, n_cases must be > 0)");
     if (d->n_qtf_w < 2 || d->n_qtf_head < 1 || !d->qtf || !d->qtf_w || !d->qtf_heads)
         return set_err(RAFTK_EINVAL, "designs carry no QTF table (n_qtf_w >= 2, n_qtf_head >= 1, qtf, qtf_w, qtf_heads)");
+    if (d->qtf_shared < 0 || d->qtf_shared > 2) return set_err(RAFTK_EINVAL, "qtf_shared must be 0, 1 or 2");
     if ((size_t)d->nw * 20 > 227 * 1024) return set_err(RAFTK_EINVAL, "nw too large for the second-order force kernel's shared-memory tables");
     return 0;
 }
@@ -188,7 +190,7 @@ static int run_qtf(const raftk_designs *d, const raftk_cases *c, double *F2, dou
     if (!F2) return set_err(RAFTK_EINVAL, "second-order force needs the F_2nd buffer");
     CasesDev C = to_dev(c);
     QtfParams P;
-    P.nD = d->n_designs; P.shared = d->qtf_shared ? 1 : 0;
+    P.nD = d->n_designs; P.shared = d->qtf_shared;
     P.n2 = d->n_qtf_w; P.nh = d->n_qtf_head; P.nw = d->nw; P.dw = d->dw;
     P.w = d->w; P.qw = d->qtf_w; P.qh = d->qtf_heads;
     P.qtf = reinterpret_cast<const double2 *>(d->qtf);
@@ -205,7 +207,7 @@ static int run_qtf(const raftk_designs *d, const raftk_cases *c, double *F2, dou
         }
     }
     const int ntasks = d->nw / 2 + 1, per_cta = (QTF_THREADS / 32) * QTF_TASKS_PER_WARP;
-    dim3 grid((ntasks + per_cta - 1) / per_cta, c->n_cases, P.shared ? 1 : d->n_designs);
+    dim3 grid((ntasks + per_cta - 1) / per_cta, c->n_cases, P.shared == 1 ? 1 : d->n_designs);
     if (grid.y > 65535u || grid.z > 65535u) return set_err(RAFTK_EINVAL, "second-order force: more than 65535 cases or designs per call");
     if (P.nh > 1) k_qtf_force<true><<<grid, QTF_THREADS, smem, st>>>(C, P);
     else k_qtf_force<false><<<grid, QTF_THREADS, smem, st>>>(C, P);
@@ -343,6 +345,8 @@ static int run_fused(const raftk_designs *d, const raftk_cases *c, const raftk_s
     P.Finer_out = reinterpret_cast<double2 *>(out->F_iner);
     P.Fbem_out = reinterpret_cast<double2 *>(out->F_BEM);
     P.Bdrag_out = out->B_drag; P.zeta_out = out->zeta; P.status = out->status;
+    P.Xilast_out = reinterpret_cast<double2 *>(out->Xi_last);
+    P.Xi_init = reinterpret_cast<const double2 *>(c->Xi_init);
     P.F0g = pl.f0_global ? reinterpret_cast<double2 *>(workspace) : nullptr;
     const int units = d->n_designs * c->n_cases;
     P.lin_g = nullptr; P.phase = -1;
@@ -374,6 +378,7 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
         const bool have_ws = workspace && wbytes >= (size_t)nD * nC * 6 * nw * sizeof(double2);
         if (fused_plan(d, nD * nC, o ? o->cluster_size : 0, have_ws, fp)) return run_fused(d, c, o, out, fp, workspace, wbytes, st);
         if (c->primary) return set_err(RAFTK_EINVAL, "wave-train cases (cases.primary) need the fused solver; the design's frequency slice does not fit on chip");
+        if (c->Xi_init || out->Xi_last) return set_err(RAFTK_EINVAL, "cases.Xi_init / outputs.Xi_last need the fused solver; the design's frequency slice does not fit on chip");
     }
     if (c->primary && mode != 2) return set_err(RAFTK_EINVAL, "cases.primary is only supported by raftk_solve_dynamics_*");
     if (do_excitation) prof_begin_call();
@@ -591,9 +596,10 @@ static size_t in_bytes(const raftk_designs *d, const raftk_cases *c)
     add(nC * 4); add(nC * 4);
     if (c->zeta) add(nC * nw * 8);
     if (c->F_2nd) add(nD * nC * 6 * nw * 8);
+    if (c->Xi_init) add(nD * nC * 6 * nw * 16);
     if (d->n_qtf_w > 0) {
         add((size_t)d->n_qtf_w * 8); add((size_t)d->n_qtf_head * 8);
-        add((d->qtf_shared ? 1 : nD) * (size_t)d->n_qtf_w * d->n_qtf_w * d->n_qtf_head * 96);
+        add((d->qtf_shared == 1 ? 1 : (d->qtf_shared == 2 ? nD * nC : nD)) * (size_t)d->n_qtf_w * d->n_qtf_w * d->n_qtf_head * 96);
     }
     return b;
 }
@@ -610,7 +616,7 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     size_t obytes = 0;
     auto oadd = [&](const void *p, size_t n) { if (p) obytes += align_up(n, 256); };
     oadd(out->Xi, resp); oadd(out->status, nD * nC * 16); oadd(out->B_drag, nD * nC * 288); oadd(out->F_drag, resp);
-    oadd(out->F_iner, resp); oadd(out->F_BEM, resp); oadd(out->zeta, nC * nw * 8);
+    oadd(out->F_iner, resp); oadd(out->F_BEM, resp); oadd(out->zeta, nC * nw * 8); oadd(out->Xi_last, resp);
     const bool qtf_solve = (mode == 0 && d->n_qtf_w > 0 && !c->F_2nd);   // potSecOrder 2: compute the force on the device first
     if (qtf_solve) obytes += align_up(resp / 2, 256) + align_up(nD * nC * 48, 256);
     if (Xi_in) obytes += align_up(resp, 256);
@@ -650,10 +656,11 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     cc.zeta = up(A, c->zeta, nC * nw, st, e);
     cc.primary = up(A, c->primary, c->primary ? nC : 0, st, e);
     cc.F_2nd = up(A, c->F_2nd, c->F_2nd ? nD * nC * 6 * nw : 0, st, e);
+    cc.Xi_init = up(A, c->Xi_init, c->Xi_init ? nD * nC * 6 * nw * 2 : 0, st, e);
     if (d->n_qtf_w > 0) {
         dd.qtf_w = up(A, d->qtf_w, (size_t)d->n_qtf_w, st, e);
         dd.qtf_heads = up(A, d->qtf_heads, (size_t)d->n_qtf_head, st, e);
-        dd.qtf = up(A, d->qtf, (d->qtf_shared ? 1 : nD) * (size_t)d->n_qtf_w * d->n_qtf_w * d->n_qtf_head * 12, st, e);
+        dd.qtf = up(A, d->qtf, (d->qtf_shared == 1 ? 1 : (d->qtf_shared == 2 ? nD * nC : nD)) * (size_t)d->n_qtf_w * d->n_qtf_w * d->n_qtf_head * 12, st, e);
     }
     const double *Xi_in_d = up(A, Xi_in, Xi_in ? nD * nC * 6 * nw * 2 : 0, st, e);
     {
@@ -670,6 +677,7 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     if (out->F_iner) od.F_iner = static_cast<double *>(A.take(resp));
     if (out->F_BEM) od.F_BEM = static_cast<double *>(A.take(resp));
     if (out->zeta) od.zeta = static_cast<double *>(A.take(nC * nw * 8));
+    if (out->Xi_last) od.Xi_last = static_cast<double *>(A.take(resp));
     if (qtf_solve) {
         od.F_2nd = static_cast<double *>(A.take(resp / 2));
         od.F_2nd_mean = static_cast<double *>(A.take(nD * nC * 48));
@@ -689,7 +697,7 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     down(out->Xi, od.Xi, resp); down(out->status, od.status, nD * nC * 16); down(out->B_drag, od.B_drag, nD * nC * 288);
     down(out->F_drag, od.F_drag, resp); down(out->F_iner, od.F_iner, resp); down(out->F_BEM, od.F_BEM, resp);
     down(out->zeta, od.zeta, nC * nw * 8);
-    down(out->F_2nd, od.F_2nd, resp / 2); down(out->F_2nd_mean, od.F_2nd_mean, nD * nC * 48);
+    down(out->F_2nd, od.F_2nd, resp / 2); down(out->F_2nd_mean, od.F_2nd_mean, nD * nC * 48); down(out->Xi_last, od.Xi_last, resp);
     cudaError_t se = cudaStreamSynchronize(st);
     if (e != cudaSuccess || se != cudaSuccess)
         return set_err(RAFTK_ECUDA, "kernel/D2H: %s", cudaGetErrorString(se != cudaSuccess ? se : e));
@@ -717,7 +725,7 @@ extern "C" int raftk_second_order_force_host(const raftk_designs *d, const raftk
     int rc = validate_qtf(d, c);
     if (rc) return rc;
     const size_t nD = d->n_designs, nw = d->nw, nC = c->n_cases, n2 = d->n_qtf_w, nh = d->n_qtf_head;
-    const size_t qb = (d->qtf_shared ? 1 : nD) * n2 * n2 * nh * 96, fb = nD * nC * 6 * nw * 8, mb = nD * nC * 48;
+    const size_t qb = (d->qtf_shared == 1 ? 1 : (d->qtf_shared == 2 ? nD * nC : nD)) * n2 * n2 * nh * 96, fb = nD * nC * 6 * nw * 8, mb = nD * nC * 48;
     // one temporary block: grid, table axes, table, case columns, (zeta), outputs
     size_t total = 0;
     auto take = [&](size_t n) { size_t o = total; total += align_up(n, 256); return o; };
@@ -747,6 +755,98 @@ extern "C" int raftk_second_order_force_host(const raftk_designs *d, const raftk
     }
     cudaFree(base);
     if (e != cudaSuccess) return set_err(RAFTK_ECUDA, "second-order force: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+// ---- slender-body QTF ----------------------------------------------------------------------------------
+static int validate_slender(const raftk_slender *s, int32_t n_cases)
+{
+    if (!s || n_cases <= 0 || s->nw <= 0 || s->n_members <= 0 || s->n_nodes < 0 || s->n_seg < 0)
+        return set_err(RAFTK_EINVAL, "bad slender-body QTF arguments (n_cases, nw, n_members must be > 0)");
+    if (n_cases > 65535) return set_err(RAFTK_EINVAL, "slender-body QTF: more than 65535 cases per call");
+    return 0;
+}
+
+extern "C" size_t raftk_qtf_slender_workspace_bytes(const raftk_slender *s, int32_t n_cases)
+{
+    if (!s || n_cases <= 0) return 0;
+    return align_up((size_t)n_cases * std::max(s->n_nodes, 1) * s->nw * SL_NODE_C * sizeof(cx), 256)
+           + align_up((size_t)n_cases * s->n_members * s->nw * SL_MEM_C * sizeof(cx), 256);
+}
+
+extern "C" int raftk_qtf_slender_dev(const raftk_slender *s, int32_t n_cases, const double *beta_rad, const double *Xi_rao, double *qtf,
+                                     void *workspace, size_t workspace_bytes, void *stream)
+{
+    int rc = validate_slender(s, n_cases);
+    if (rc) return rc;
+    if (!beta_rad || !Xi_rao || !qtf) return set_err(RAFTK_EINVAL, "slender-body QTF: null beta / Xi_rao / qtf");
+    if (!workspace || workspace_bytes < raftk_qtf_slender_workspace_bytes(s, n_cases)) return set_err(RAFTK_ENOMEM, "slender-body QTF: workspace too small");
+    SlenderDev D;
+    D.n_nodes = s->n_nodes; D.n_members = s->n_members; D.n_seg = s->n_seg; D.nw = s->nw;
+    D.depth = s->depth; D.rho = s->rho; D.g = s->g;
+    D.mem_q = s->mem_q; D.mem_p1 = s->mem_p1; D.mem_p2 = s->mem_p2; D.mem_mcf = s->mem_mcf; D.mem_wl = s->mem_wl;
+    D.mem_r_int = s->mem_r_int; D.mem_a_wl = s->mem_a_wl; D.mem_rwl = s->mem_rwl; D.mem_R_wl = s->mem_R_wl;
+    D.mem_node_start = s->mem_node_start; D.node_r = s->node_r; D.node_v_side = s->node_v_side;
+    D.node_Ca_p1 = s->node_Ca_p1; D.node_Ca_p2 = s->node_Ca_p2; D.node_Ca_End = s->node_Ca_End; D.node_v_end = s->node_v_end; D.node_a_i = s->node_a_i;
+    D.seg_mem = s->seg_mem; D.seg_z1 = s->seg_z1; D.seg_z2 = s->seg_z2; D.seg_R = s->seg_R; D.seg_rmid = s->seg_rmid;
+    D.M_struc = s->M_struc; D.w = s->w; D.k = s->k;
+    cudaStream_t st = (cudaStream_t)stream;
+    cx *Tn = static_cast<cx *>(workspace);
+    cx *Tm = reinterpret_cast<cx *>(static_cast<char *>(workspace) + align_up((size_t)n_cases * std::max(s->n_nodes, 1) * s->nw * SL_NODE_C * sizeof(cx), 256));
+    const cx *X = reinterpret_cast<const cx *>(Xi_rao);
+    cx *Q = reinterpret_cast<cx *>(qtf);
+    k_slender_tables<<<dim3(s->n_nodes + s->n_members, n_cases), SL_THREADS, 0, st>>>(D, beta_rad, X, Tn, Tm);
+    const unsigned npairs = (unsigned)((size_t)s->nw * (s->nw + 1) / 2);
+    k_slender_pairs<<<dim3(npairs, n_cases), SL_THREADS, 0, st>>>(D, beta_rad, X, Tn, Tm, Q);
+    k_slender_fill<<<dim3(s->nw, n_cases), 64, 0, st>>>(s->nw, Q);
+    g_launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return RAFTK_OK;
+}
+
+extern "C" int raftk_qtf_slender_host(const raftk_slender *s, int32_t n_cases, const double *beta_rad, const double *Xi_rao, double *qtf)
+{
+    int rc = validate_slender(s, n_cases);
+    if (rc) return rc;
+    if (!beta_rad || !Xi_rao || !qtf) return set_err(RAFTK_EINVAL, "slender-body QTF: null beta / Xi_rao / qtf");
+    const size_t Nm = s->n_members, Ns = s->n_nodes, Ng = s->n_seg, nw = s->nw, nC = n_cases;
+    size_t total = 0;
+    auto take = [&](size_t n) { size_t o = total; total += align_up(std::max<size_t>(n, 8), 256); return o; };
+    struct Item { size_t off; const void *h; size_t n; const void **slot; };
+    raftk_slender dd = *s;
+    std::vector<Item> items;
+    auto add = [&](const void *h, size_t n, const void **slot) { items.push_back({take(n), h, n, slot}); };
+    add(s->w, nw * 8, (const void **)&dd.w); add(s->k, nw * 8, (const void **)&dd.k);
+    add(s->mem_q, Nm * 24, (const void **)&dd.mem_q); add(s->mem_p1, Nm * 24, (const void **)&dd.mem_p1); add(s->mem_p2, Nm * 24, (const void **)&dd.mem_p2);
+    add(s->mem_mcf, Nm * 4, (const void **)&dd.mem_mcf); add(s->mem_wl, Nm * 4, (const void **)&dd.mem_wl);
+    add(s->mem_r_int, Nm * 24, (const void **)&dd.mem_r_int); add(s->mem_a_wl, Nm * 8, (const void **)&dd.mem_a_wl);
+    add(s->mem_rwl, Nm * 24, (const void **)&dd.mem_rwl); add(s->mem_R_wl, Nm * 8, (const void **)&dd.mem_R_wl);
+    add(s->mem_node_start, (Nm + 1) * 4, (const void **)&dd.mem_node_start);
+    add(s->node_r, Ns * 24, (const void **)&dd.node_r); add(s->node_v_side, Ns * 8, (const void **)&dd.node_v_side);
+    add(s->node_Ca_p1, Ns * 8, (const void **)&dd.node_Ca_p1); add(s->node_Ca_p2, Ns * 8, (const void **)&dd.node_Ca_p2);
+    add(s->node_Ca_End, Ns * 8, (const void **)&dd.node_Ca_End); add(s->node_v_end, Ns * 8, (const void **)&dd.node_v_end);
+    add(s->node_a_i, Ns * 8, (const void **)&dd.node_a_i);
+    add(s->seg_mem, Ng * 4, (const void **)&dd.seg_mem); add(s->seg_z1, Ng * 8, (const void **)&dd.seg_z1); add(s->seg_z2, Ng * 8, (const void **)&dd.seg_z2);
+    add(s->seg_R, Ng * 8, (const void **)&dd.seg_R); add(s->seg_rmid, Ng * 24, (const void **)&dd.seg_rmid);
+    add(s->M_struc, 288, (const void **)&dd.M_struc);
+    const size_t o_beta = take(nC * 8), o_xi = take(nC * 6 * nw * 16), o_q = take(nC * nw * nw * 6 * 16);
+    const size_t wb = raftk_qtf_slender_workspace_bytes(s, n_cases), o_ws = take(wb);
+    char *base = nullptr;
+    CUDA_TRY(cudaMalloc(&base, total));
+    cudaError_t e = cudaSuccess;
+    for (auto &it : items) {
+        if (it.h && it.n) { cudaError_t r = cudaMemcpy(base + it.off, it.h, it.n, cudaMemcpyHostToDevice); if (r != cudaSuccess) e = r; }
+        *it.slot = base + it.off;
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(base + o_beta, beta_rad, nC * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(base + o_xi, Xi_rao, nC * 6 * nw * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = raftk_qtf_slender_dev(&dd, n_cases, reinterpret_cast<double *>(base + o_beta), reinterpret_cast<double *>(base + o_xi),
+                                   reinterpret_cast<double *>(base + o_q), base + o_ws, wb, nullptr);
+        if (!rc) e = cudaMemcpy(qtf, base + o_q, nC * nw * nw * 6 * 16, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(base);
+    if (e != cudaSuccess) return set_err(RAFTK_ECUDA, "slender-body QTF: %s", cudaGetErrorString(e));
     return rc;
 }
 

@@ -20,6 +20,8 @@ struct FusedParams {
     int n_iter, CS, nwl, maxW, maxH, maxZ;
     double tol, xi_start;
     double2 *Xi_out, *Fdrag_out, *Finer_out, *Fbem_out;
+    double2 *Xilast_out;     // [units][6][nw] iterate each pass linearised about (last write = XiLast of the final pass), or NULL
+    const double2 *Xi_init;  // [units][6][nw] starting iterate instead of xi_start, or NULL
     double *Bdrag_out, *zeta_out;
     int *status;
     double2 *F0g;            // [units][6][nw] linear excitation kept in global memory (frees 96 B/bin of smem), or NULL
@@ -327,7 +329,8 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
         for (int a = 0; a < 6; a++) {
             if (P.F0g) P.F0g[ogl + (size_t)a * nw + i] = make_double2(Fr[a], Fi[a]);
             else { S.f0[(2 * a) * nwl + t] = Fr[a]; S.f0[(2 * a + 1) * nwl + t] = Fi[a]; }
-            S.xi[(2 * a) * nwl + t] = P.xi_start; S.xi[(2 * a + 1) * nwl + t] = 0.0;
+            if (P.Xi_init) { const double2 x0 = P.Xi_init[ogl + (size_t)a * nw + i]; S.xi[(2 * a) * nwl + t] = x0.x; S.xi[(2 * a + 1) * nwl + t] = x0.y; }
+            else { S.xi[(2 * a) * nwl + t] = P.xi_start; S.xi[(2 * a + 1) * nwl + t] = 0.0; }
         }
     }
     __syncthreads();
@@ -608,6 +611,7 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
                 S.xi[(2 * a) * nwl + t] = 0.2 * lr + 0.8 * br[a];
                 S.xi[(2 * a + 1) * nwl + t] = 0.2 * li + 0.8 * bi[a];
                 P.Xi_out[ogl + (size_t)a * nw + i] = make_double2(br[a], bi[a]);
+                if (P.Xilast_out) P.Xilast_out[ogl + (size_t)a * nw + i] = make_double2(lr, li);
             }
         }
         passes++;

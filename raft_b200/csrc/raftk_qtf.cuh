@@ -20,7 +20,8 @@
 
 struct QtfParams {
     int nD;                 // designs written (F_2nd has a design axis)
-    int shared;             // 1: one table for all designs (computed once per case, stored nD times)
+    int shared;             // 0: table per design; 1: one table for all designs (computed once per case, stored nD times);
+                            // 2: table per (design, case)
     int n2, nh, nw;
     double dw;
     const double *w;        // [nw] model grid
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(QTF_THREADS, QTF_MIN_CTAS) k_qtf_force(CasesDe
     }
     __syncthreads();
 
-    const double2 *Q = P.qtf + (P.shared ? (size_t)0 : (size_t)dz * n2 * n2 * nh * 6) + (size_t)hl * 6;
+    const size_t tab = (P.shared == 1) ? (size_t)0 : (P.shared == 2 ? (size_t)dz * Cs.nC + c : (size_t)dz);
+    const double2 *Q = P.qtf + tab * n2 * n2 * nh * 6 + (size_t)hl * 6;
     const size_t sj = (size_t)nh * 6, si = (size_t)n2 * nh * 6;      // strides of the w2 / w1 axes (double2 units)
     const int dh = (hh - hl) * 6;                                    // 0 outside the table's heading range: blend of a table with itself
     const int ntasks = nw / 2 + 1;
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(QTF_THREADS, QTF_MIN_CTAS) k_qtf_force(CasesDe
                 for (int a = 1; a < 6; a++) if (lane == a) v = acc[a];
                 // f[mu] lands in bin mu - 1 (the reference shifts by one bin, :2244) and the last bin is zero (:2245)
                 const double outv = (mu == 0) ? 2.0 * v * P.dw : 4.0 * sqrt(v) * P.dw;
-                const int d_lo = P.shared ? 0 : dz, d_hi = P.shared ? P.nD : dz + 1;
+                const int d_lo = (P.shared == 1) ? 0 : dz, d_hi = (P.shared == 1) ? P.nD : dz + 1;
                 for (int d = d_lo; d < d_hi; d++) {
                     const size_t unit = (size_t)d * Cs.nC + c;
                     if (mu == 0) {

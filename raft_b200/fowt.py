@@ -62,8 +62,15 @@ class FOWT:
         # table matrices['qtf'], ['qtf_w'], ['qtf_heads']); 1 (slender-body QTF) is outside the B200 path
         self.potSecOrder = int(plat.get("potSecOrder", 0) or 0)
         self.outFolderQTF = None
-        if self.potSecOrder == 1:
-            raise NotImplementedError("potSecOrder 1 (slender-body QTF, raft_fowt.py:1988) is outside the B200 path")
+        if self.potSecOrder == 1:                                      # slender-body QTF on its own frequency grid (:411-426)
+            if "min_freq2nd" not in plat or "max_freq2nd" not in plat:
+                raise Exception("If potSecOrder==1, then both min_freq2nd and max_freq2nd must be specified in the platform input.")
+            lo, hi = plat["min_freq2nd"], plat["max_freq2nd"]
+            df = plat.get("df_freq2nd", lo)
+            self.w1_2nd = np.arange(lo, hi + 0.5 * lo, df) * 2 * np.pi
+            self.w2_2nd = self.w1_2nd.copy()
+            self.k1_2nd = np.array([grid.wave_number(np.array([w_]), self.depth)[0] for w_ in self.w1_2nd])
+            self.k2_2nd = self.k1_2nd.copy()
         if self.potSecOrder == 2:
             if "qtf" in mats:
                 self.qtf = np.array(mats["qtf"], dtype=complex)
@@ -141,6 +148,29 @@ class FOWT:
         self.w2_2nd = self.w1_2nd.copy()
         self._batch = None
 
+    # raft_fowt.py:1988-2078 -------------------------------------------------------------------------------
+    def calcQTF_slenderBody(self, waveHeadInd, Xi0=None, verbose=False, iCase=None, iWT=None):
+        """Slender-body difference-frequency QTF on the GPU for wave train ``waveHeadInd`` of the last
+        calcHydroExcitation; ``Xi0`` [6,nw] motion RAOs on self.w (None: fixed body).  Leaves self.qtf
+        [nw2,nw2,1,6] and self.heads_2nd = [beta] like the reference."""
+        if self.potSecOrder != 1:
+            raise RuntimeError("calcQTF_slenderBody needs potSecOrder 1 (min_freq2nd / max_freq2nd in the platform input)")
+        if Xi0 is None:
+            Xi0 = np.zeros([6, self.nw], dtype=complex)
+        beta = float(self.beta[waveHeadInd])
+        self.heads_2nd = [beta]
+        Xi = np.array([np.interp(self.w1_2nd, self.w, np.asarray(Xi0)[a], left=0, right=0) for a in range(6)])   # :2021-2023
+        q = solver.qtf_slender(self.pack(), [beta], Xi[None])
+        self.qtf = np.ascontiguousarray(q[0][:, :, None, :])
+        return self.qtf
+
+    def _qtf_batch(self):
+        """DesignBatch carrying self.qtf (read from a file, injected, or left by calcQTF_slenderBody)."""
+        P = {k: v for k, v in self.pack().items() if not k.startswith(("qs_", "qtf"))}
+        P.update(qtf=np.asarray(self.qtf, dtype=complex), qtf_w=np.asarray(self.w1_2nd, dtype=float),
+                 qtf_heads=np.asarray(self.heads_2nd, dtype=float))
+        return solver.DesignBatch(P)
+
     # raft_fowt.py:2158-2253 -------------------------------------------------------------------------------
     def calcHydroForce_2ndOrd(self, beta, S0, iCase=None, iWT=None, interpMode="qtf"):
         """Difference-frequency force amplitudes from the QTF table on the GPU: ``beta`` [rad], ``S0`` [nw] wave
@@ -150,7 +180,7 @@ class FOWT:
         S0 = np.asarray(S0, dtype=float)
         one = solver.CaseTable(dict(Hs=[0.0], Tp=[1.0], gamma=[0.0], beta_deg=[float(beta) * 57.29577951308232], spec=[0]),
                                zeta=np.sqrt(2.0 * S0 * self.dw)[None, :])
-        out = solver.second_order_force(self._get_batch(), one)
+        out = solver.second_order_force(self._qtf_batch(), one)
         return out["F_2nd_mean"][0, 0], out["F_2nd"][0, 0]
 
     # raft_fowt.py:1891-1957 -------------------------------------------------------------------------------

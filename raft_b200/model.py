@@ -116,11 +116,21 @@ class Model:
         table, owner, first = packer.pack_case_trains(cases)
         ct = solver.CaseTable(table)
         nC = len(cases)
-        batch = solver.DesignBatch([f.pack() for f in self.fowtList])
+        packs = [f.pack() for f in self.fowtList]
+        batch = solver.DesignBatch([{k: v for k, v in P.items() if not k.startswith("qs_")} for P in packs])
         want = ("Xi", "status", "B_drag", "F_drag", "F_iner", "F_BEM", "zeta")
-        if batch.n_qtf_w:                                                   # potSecOrder 2 (raft_model.py:1035-1038)
-            want += ("F_2nd", "F_2nd_mean")
-        o = solver.solve_dynamics(batch, ct, n_iter=self.nIter, tol=tol, xi_start=self.XiStart, want=want)
+        sec = [int(getattr(f, "potSecOrder", 0)) for f in self.fowtList]
+        if any(s_ == 1 for s_ in sec):                                      # slender-body QTF inside the loop (raft_model.py:1106-1131)
+            if not all(s_ == 1 for s_ in sec):
+                raise NotImplementedError("mixing potSecOrder 1 with other settings in one array is not supported")
+            o = solver.solve_dynamics_slender(packs, ct, n_iter=self.nIter, tol=tol, xi_start=self.XiStart, want=want)
+            for i, f in enumerate(self.fowtList):
+                f.qtf = np.ascontiguousarray(o["qtf"][i, -1][:, :, None, :])
+                f.heads_2nd = [float(ct.arrays["beta_deg"][-1]) * 0.017453292519943295]
+        else:
+            if batch.n_qtf_w:                                               # potSecOrder 2 (raft_model.py:1035-1038)
+                want += ("F_2nd", "F_2nd_mean")
+            o = solver.solve_dynamics(batch, ct, n_iter=self.nIter, tol=tol, xi_start=self.XiStart, want=want)
         if "primary" in table:                                              # secondary trains share their primary's B_drag
             o["B_drag"] = o["B_drag"][:, table["primary"]]
         st = o["status"][:, first]                                          # [nFOWT, nC, 4] (train 0 of every case)

@@ -213,17 +213,101 @@ def pack_fowt(fowt, w=None, k=None):
 def pack_qtf(fowt):
     """External difference-frequency QTF of a FOWT (state left by FOWT.readQTF, raft_fowt.py:2081-2128):
     ``qtf`` complex [nw1, nw2, nheads, 6] (dimensional, Hermitian-filled), ``qtf_w`` [nw1] rad/s, ``qtf_heads``
-    [nheads] rad.  Empty dict for potSecOrder 0; the slender-body QTF (potSecOrder 1) is not on this path."""
+    [nheads] rad.  Empty dict for potSecOrder 0; for potSecOrder 1 the member tables of the slender-body QTF
+    (``pack_qtf_members``, keys ``qs_*``)."""
     sec = int(getattr(fowt, "potSecOrder", 0) or 0)
     if sec == 0:
         return {}
-    if sec != 2:
-        raise NotImplementedError("potSecOrder 1 (slender-body QTF, raft_fowt.py:1988) is outside the B200 path")
+    if sec == 1:                                   # slender-body QTF, computed on the GPU from the member tables
+        if int(getattr(fowt, "nDOF", 6)) != 6:
+            raise NotImplementedError("slender-body QTF: rigid 6-DOF FOWTs only (the reference returns null QTFs otherwise, raft_fowt.py:2014)")
+        return pack_qtf_members(fowt)
     w1, w2 = np.asarray(fowt.w1_2nd, dtype=float), np.asarray(fowt.w2_2nd, dtype=float)
     if w1.shape != w2.shape or not (w1 == w2).all():
         raise ValueError("Both frequency columns in the input QTF must contain the same values.")   # raft_fowt.py:2109
     return dict(qtf=np.ascontiguousarray(fowt.qtf, dtype=np.complex128), qtf_w=w1,
                 qtf_heads=np.asarray(fowt.heads_2nd, dtype=float))
+
+
+def pack_qtf_members(fowt):
+    """Tables of the slender-body QTF (potSecOrder 1; C ABI ``raftk_slender``), duck-typed on the reference's FOWT / Member
+    objects.  Hoists what Member.calcQTF_slenderBody / correction_KAY evaluate inside their frequency-pair loops
+    (raft_member.py:1560-1571 strip volume and coefficients, :1620-1625 end volume, :1528 waterline intersection,
+    :1660-1674 waterline area, :1721-1760 Kim & Yue waterline point and integration segments).  Keys ``qs_*``; the
+    submerged nodes and their order are those of ``pack_members``."""
+    rho, g = float(fowt.rho_water), float(fowt.g)
+    mq, mp1, mp2, mmcf, mwl, mrint, mawl, mrwl, mRwl = [], [], [], [], [], [], [], [], []
+    cols = {k: [] for k in ("mem", "r", "v_side", "Ca_p1", "Ca_p2", "Ca_End", "v_end", "a_i")}
+    seg = {k: [] for k in ("mem", "z1", "z2", "R", "rmid")}
+    for mem in fowt.memberList:
+        sub = np.where(mem.r[:, 2] < 0)[0]
+        if len(sub) == 0:
+            continue
+        im = len(mq)
+        circ = mem.shape == "circular"
+        mq.append(np.array(mem.q, dtype=float)), mp1.append(np.array(mem.p1, dtype=float)), mp2.append(np.array(mem.p2, dtype=float))
+        for il in sub:
+            ls = float(mem.ls[il])
+            if circ:
+                v_i = 0.25 * np.pi * mem.ds[il] ** 2 * mem.dls[il]
+            else:
+                v_i = mem.ds[il, 0] * mem.ds[il, 1] * mem.dls[il]
+            if mem.r[il, 2] + 0.5 * mem.dls[il] > 0:
+                v_i = v_i * (0.5 * mem.dls[il] - mem.r[il, 2]) / mem.dls[il]
+            if circ:
+                v_e = np.pi / 12.0 * abs((mem.ds[il] + mem.drs[il]) ** 3 - (mem.ds[il] - mem.drs[il]) ** 3)
+            else:
+                v_e = np.pi / 12.0 * ((np.mean(mem.ds[il] + mem.drs[il])) ** 3 - (np.mean(mem.ds[il] - mem.drs[il])) ** 3)
+            cols["mem"].append(im), cols["r"].append(np.array(mem.r[il], dtype=float))
+            cols["v_side"].append(v_i), cols["v_end"].append(v_e), cols["a_i"].append(float(mem.a_i[il]))
+            cols["Ca_p1"].append(np.interp(ls, mem.stations, mem.Ca_p1)), cols["Ca_p2"].append(np.interp(ls, mem.stations, mem.Ca_p2))
+            cols["Ca_End"].append(np.interp(ls, mem.stations, mem.Ca_End))
+        wl = bool(mem.r[-1, 2] * mem.r[0, 2] < 0)
+        r_int, a_wl = np.zeros(3), 0.0
+        if wl:
+            r_int = mem.r[0, :] + (mem.r[-1, :] - mem.r[0, :]) * (0. - mem.r[0, 2]) / (mem.r[-1, 2] - mem.r[0, 2])
+            i_wl = np.where(mem.r[:, 2] < 0)[0][-1]
+            if circ:
+                d_wl = 0.5 * (mem.ds[i_wl] + mem.ds[i_wl + 1]) if i_wl != len(mem.ds) - 1 else mem.ds[i_wl]
+                a_wl = 0.25 * np.pi * d_wl ** 2
+            else:
+                if i_wl != len(mem.ds) - 1:
+                    d1, d2 = 0.5 * (mem.ds[i_wl, 0] + mem.ds[i_wl + 1, 0]), 0.5 * (mem.ds[i_wl, 1] + mem.ds[i_wl + 1, 1])
+                else:
+                    d1, d2 = mem.ds[i_wl, 0], mem.ds[i_wl, 1]
+                a_wl = d1 * d2
+        kay = bool(getattr(mem, "MCF", False)) and bool(mem.rA[2] * mem.rB[2] < 0)
+        rwl, Rwl = np.zeros(3), 1.0
+        if kay:
+            rwl = mem.rA + (mem.rB - mem.rA) * (0 - mem.rA[2]) / (mem.rB[2] - mem.rA[2])
+            Rwl = float(np.interp(0, mem.r[:, 2], 0.5 * np.array(mem.ds)))
+            for il, r1 in enumerate(mem.r[:-1]):
+                z1 = r1[2]
+                if z1 > 0:
+                    continue
+                r2 = mem.r[il + 1]
+                z2 = 0 if r2[2] > 0 else r2[2]
+                R1 = mem.ds[il] / 2
+                if mem.dls[il] == 0:
+                    R1 = mem.ds[il]
+                R2 = mem.ds[il + 1] / 2
+                if mem.dls[il + 1] == 0:
+                    R2 = mem.ds[il]
+                seg["mem"].append(im), seg["z1"].append(z1), seg["z2"].append(z2), seg["R"].append(0.5 * (R1 + R2)), seg["rmid"].append(0.5 * (r1 + r2))
+        mmcf.append(1 if kay else 0), mwl.append(1 if wl else 0), mrint.append(r_int), mawl.append(a_wl), mrwl.append(rwl), mRwl.append(Rwl)
+    ns, nm, nsg = len(cols["mem"]), len(mq), len(seg["mem"])
+    out = dict(qs_mem_q=np.array(mq).reshape(nm, 3), qs_mem_p1=np.array(mp1).reshape(nm, 3), qs_mem_p2=np.array(mp2).reshape(nm, 3),
+               qs_mem_mcf=np.array(mmcf, dtype=np.int32), qs_mem_wl=np.array(mwl, dtype=np.int32),
+               qs_mem_r_int=np.array(mrint, dtype=float).reshape(nm, 3), qs_mem_a_wl=np.array(mawl, dtype=float),
+               qs_mem_rwl=np.array(mrwl, dtype=float).reshape(nm, 3), qs_mem_R_wl=np.array(mRwl, dtype=float),
+               qs_node_mem=np.array(cols["mem"], dtype=np.int32), qs_node_r=np.array(cols["r"], dtype=float).reshape(ns, 3),
+               qs_seg_mem=np.array(seg["mem"], dtype=np.int32), qs_seg_z1=np.array(seg["z1"], dtype=float), qs_seg_z2=np.array(seg["z2"], dtype=float),
+               qs_seg_R=np.array(seg["R"], dtype=float), qs_seg_rmid=np.array(seg["rmid"], dtype=float).reshape(nsg, 3),
+               qs_M_struc=np.array(fowt.M_struc, dtype=float), qs_w=np.array(fowt.w1_2nd, dtype=float), qs_k=np.array(fowt.k1_2nd, dtype=float),
+               qs_depth=np.float64(fowt.depth), qs_rho=np.float64(rho), qs_g=np.float64(g))
+    for k in ("v_side", "Ca_p1", "Ca_p2", "Ca_End", "v_end", "a_i"):
+        out["qs_node_" + k] = np.array(cols[k], dtype=float)
+    return out
 
 
 def pack_turbine_channels(fowt):

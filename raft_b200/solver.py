@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import RaftkCases, RaftkDesigns, RaftkOutputs, RaftkSolveOpts, check, lib
+from ._lib import RaftkCases, RaftkDesigns, RaftkOutputs, RaftkSlender, RaftkSolveOpts, check, lib
 
 _F8 = np.float64
 _I4 = np.int32
@@ -173,8 +173,9 @@ class DesignBatch:
 class CaseTable:
     """SoA case table (``packer.pack_cases`` dict, or keyword arrays)."""
 
-    def __init__(self, cases, zeta=None, F_2nd=None):
-        """``F_2nd``: optional real [nD,nC,6,nw] second-order force amplitudes added to the linear excitation."""
+    def __init__(self, cases, zeta=None, F_2nd=None, Xi_init=None):
+        """``F_2nd``: optional real [nD,nC,6,nw] second-order force amplitudes added to the linear excitation.
+        ``Xi_init``: optional complex [nD,nC,6,nw] starting iterate of the fixed-point loop (instead of xi_start)."""
         self.arrays = a = {}
         for kname in ("Hs", "Tp", "gamma", "beta_deg"):
             a[kname] = np.ascontiguousarray(cases[kname], dtype=_F8)
@@ -191,6 +192,8 @@ class CaseTable:
             a["primary"] = pr
         if F_2nd is not None:
             a["F_2nd"] = np.ascontiguousarray(F_2nd, dtype=_F8)
+        if Xi_init is not None:
+            a["Xi_init"] = np.ascontiguousarray(Xi_init, dtype=np.complex128)
 
     def input_bytes(self):
         return int(sum(v.nbytes for v in self.arrays.values()))
@@ -198,7 +201,7 @@ class CaseTable:
     def struct(self, ptr):
         s = RaftkCases()
         s.n_cases = self.n_cases
-        for name in ("Hs", "Tp", "gamma", "beta_deg", "spec", "zeta", "primary", "F_2nd"):
+        for name in ("Hs", "Tp", "gamma", "beta_deg", "spec", "zeta", "primary", "F_2nd", "Xi_init"):
             setattr(s, name, ptr(name) if name in self.arrays else None)
         return s
 
@@ -211,13 +214,13 @@ def _alloc_outputs(nD, nC, nw, want, alloc=np.zeros):
     shapes = dict(Xi=([nD, nC, 6, nw], np.complex128), status=([nD, nC, 4], _I4), B_drag=([nD, nC, 6, 6], _F8),
                   F_drag=([nD, nC, 6, nw], np.complex128), F_iner=([nD, nC, 6, nw], np.complex128),
                   F_BEM=([nD, nC, 6, nw], np.complex128), zeta=([nC, nw], _F8),
-                  F_2nd=([nD, nC, 6, nw], _F8), F_2nd_mean=([nD, nC, 6], _F8))
+                  F_2nd=([nD, nC, 6, nw], _F8), F_2nd_mean=([nD, nC, 6], _F8), Xi_last=([nD, nC, 6, nw], np.complex128))
     return {k: alloc(shapes[k][0], dtype=shapes[k][1]) for k in want}
 
 
 def _out_struct(outs, ptr):
     o = RaftkOutputs()
-    for k in ("Xi", "status", "B_drag", "F_drag", "F_iner", "F_BEM", "zeta", "F_2nd", "F_2nd_mean"):
+    for k in ("Xi", "status", "B_drag", "F_drag", "F_iner", "F_BEM", "zeta", "F_2nd", "F_2nd_mean", "Xi_last"):
         setattr(o, k, ptr(outs[k]) if k in outs else None)
     return o
 
@@ -249,6 +252,95 @@ def hydro_excitation(batch, cases, want=("F_iner", "F_BEM", "zeta")):
     os_ = _out_struct(outs, lambda a: a.ctypes.data)
     check(lib.raftk_hydro_excitation_host(C.byref(d), C.byref(c), C.byref(os_)))
     return outs
+
+
+def qtf_slender(P, beta_rad, Xi_rao):
+    """FOWT.calcQTF_slenderBody on the GPU (raft_fowt.py:1988-2078) for one design and n (heading, motion RAO) pairs.
+    ``P``: packed design with the ``qs_*`` tables (``packer.pack_qtf_members``); ``beta_rad`` [n]; ``Xi_rao`` complex
+    [n,6,nw2] motion RAOs on the second-order grid (zeros = fixed body) -> qtf complex [n,nw2,nw2,6], Hermitian-filled."""
+    beta = np.ascontiguousarray(np.atleast_1d(beta_rad), dtype=_F8)
+    Xi = np.ascontiguousarray(Xi_rao, dtype=np.complex128)
+    n, nw2 = len(beta), len(P["qs_w"])
+    if Xi.shape != (n, 6, nw2):
+        raise ValueError("Xi_rao must be [n,6,nw2] on the second-order grid")
+    keep = {}
+    s = RaftkSlender()
+    nm = len(P["qs_mem_mcf"])
+    s.n_nodes, s.n_members, s.n_seg, s.nw = len(P["qs_node_mem"]), nm, len(P["qs_seg_mem"]), nw2
+    s.depth, s.rho, s.g = float(P["qs_depth"]), float(P["qs_rho"]), float(P["qs_g"])
+    start = np.concatenate([[0], np.cumsum(np.bincount(np.asarray(P["qs_node_mem"], dtype=np.int64), minlength=nm))])
+    for name in _lib.SLENDER_ARRAYS:
+        a = start if name == "mem_node_start" else np.asarray(P["qs_" + name])
+        a = np.ascontiguousarray(a, dtype=_I4 if name in ("mem_mcf", "mem_wl", "mem_node_start", "seg_mem") else _F8)
+        keep[name] = a
+        setattr(s, name, a.ctypes.data)
+    out = np.zeros([n, nw2, nw2, 6], dtype=np.complex128)
+    check(lib.raftk_qtf_slender_host(C.byref(s), n, beta.ctypes.data, Xi.ctypes.data, out.ctypes.data))
+    return out
+
+
+def get_rao(Xi, zeta):
+    """helpers.getRAO (helpers.py:762-784): response per unit wave amplitude, zero where |zeta| <= 1e-6."""
+    Xi, zeta = np.asarray(Xi), np.asarray(zeta)
+    ok = np.abs(zeta) > 1e-6
+    out = np.zeros_like(Xi, dtype=complex)
+    out[..., ok] = Xi[..., ok] / zeta[ok]
+    return out
+
+
+def solve_dynamics_slender(packed, cases, n_iter=10, tol=0.01, xi_start=0.0, cluster_size=0, want=("Xi", "status", "B_drag")):
+    """Model.solveDynamics with potSecOrder 1 (raft_model.py:1052-1142) for every (design, case): (A) the drag-linearisation
+    loop without second-order forces; (B) where it converged: motion RAOs -> slender-body QTF on the second-order grid ->
+    difference-frequency force -> the loop continues from the SAME iterate with the force added and its counter reset
+    (at most n_iter more passes).  Units whose loop (A) did not converge keep its result, like the reference.
+    ``packed``: list of packed designs carrying ``qs_*`` tables on one second-order grid; ``cases``: CaseTable (single
+    wave train per case).  Extra outputs: F_2nd, F_2nd_mean, qtf [nD,nC,nw2,nw2,6]."""
+    if isinstance(packed, dict):
+        packed = [packed]
+    if "primary" in cases.arrays:
+        raise NotImplementedError("potSecOrder 1 with several wave trains fails in the reference itself (raft_model.py:1229 rebinds Fhydro_2nd)")
+    if n_iter < 1:
+        raise ValueError("potSecOrder 1 needs nIter >= 1")
+    plain = [{k: v for k, v in P.items() if not k.startswith(("qtf", "qs_"))} for P in packed]
+    batch = DesignBatch(plain)
+    nD, nC, nw = batch.n_designs, cases.n_cases, batch.nw
+    base = {k: v for k, v in cases.arrays.items() if k not in ("F_2nd", "Xi_init")}
+    wantA = tuple(dict.fromkeys(tuple(want) + ("Xi", "status", "zeta", "Xi_last")))
+    A = solve_dynamics(batch, CaseTable(base, zeta=base.get("zeta")), n_iter=n_iter, tol=tol, xi_start=xi_start, cluster_size=cluster_size, want=wantA)
+    qw = np.ascontiguousarray(packed[0]["qs_w"], dtype=_F8)
+    beta_rad = cases.arrays["beta_deg"] * 0.017453292519943295
+    qtf = np.zeros([nD, nC, len(qw), len(qw), 6], dtype=np.complex128)
+    for d, P in enumerate(packed):
+        if not np.array_equal(P["qs_w"], qw):
+            raise ValueError("all designs of a batch must share the second-order frequency grid")
+        Xi2 = np.zeros([nC, 6, len(qw)], dtype=np.complex128)
+        for c in range(nC):
+            r = get_rao(A["Xi"][d, c], A["zeta"][c])
+            for a in range(6):
+                Xi2[c, a] = np.interp(qw, batch.w, r[a], left=0, right=0)          # raft_fowt.py:2021-2023
+        qtf[d] = qtf_slender(P, beta_rad, Xi2)
+    qb = DesignBatch(plain)
+    qb.arrays["qtf_w"], qb.arrays["qtf_heads"] = qw, np.zeros(1)
+    qb.arrays["qtf"] = np.ascontiguousarray(qtf.reshape(nD, nC, len(qw), len(qw), 1, 6))
+    qb.n_qtf_w, qb.n_qtf_head, qb.qtf_shared = len(qw), 1, 2
+    F2 = second_order_force(qb, CaseTable(base, zeta=base.get("zeta")))
+    B = solve_dynamics(batch, CaseTable(base, zeta=base.get("zeta"), F_2nd=F2["F_2nd"], Xi_init=A["Xi_last"]), n_iter=n_iter - 1, tol=tol,
+                       xi_start=xi_start, cluster_size=cluster_size, want=wantA)
+    ok = A["status"][:, :, 1] == 1                                                   # units whose first loop converged
+    out = {}
+    for k in wantA:
+        if k == "zeta":
+            out[k] = A[k]
+            continue
+        sel = ok.reshape(ok.shape + (1,) * (A[k].ndim - 2))
+        out[k] = np.where(sel, B[k], A[k])
+    out["status"][:, :, 0] = A["status"][:, :, 0] + np.where(ok, B["status"][:, :, 0], 0)
+    out["status"][:, :, 2] = A["status"][:, :, 2] | np.where(ok, B["status"][:, :, 2], 0)
+    okf = ok[:, :, None, None]
+    out["F_2nd"] = np.where(okf, F2["F_2nd"], 0.0)
+    out["F_2nd_mean"] = np.where(ok[:, :, None], F2["F_2nd_mean"], 0.0)
+    out["qtf"] = qtf
+    return out
 
 
 def second_order_force(batch, cases):

@@ -241,6 +241,51 @@ def fixture_turbine(name, yaml_path):
     print("%-28s nw=%4d cases=%2d  %.1f s  %.0f KB" % (name, len(P["w"]), len(cases), time.time() - t0, os.path.getsize(path) / 1024))
 
 
+def fixture_slender(name, yaml_path, pickle_path, solve_cases):
+    """potSecOrder 1 (slender-body QTF): the reference's OWN golden QTF (tests/test_data/*_true_calcQTF_slenderBody.pkl,
+    fixed body, reference test test_fowt.py:192-216), plus reference runs of Model.solveDynamics with the QTF computed
+    inside the loop (raft_model.py:1106-1131): recorded motion RAOs, QTF with motions, second-order force, response, passes."""
+    t0 = time.time()
+    design = rh.load_design(yaml_path, sec_order=True)
+    assert int(design["platform"]["potSecOrder"]) == 1
+    model = rh.build_model(design)
+    fowt = model.fowtList[0]
+    P = packer.pack_fowt(fowt)
+    out = {"P_" + k: np.asarray(v) for k, v in P.items()}
+    out["n_iter"], out["xi_start"] = np.int32(int(model.nIter)), np.float64(model.XiStart)
+    out["C_moor"], out["A_hydro_morison"] = np.array(fowt.C_moor), np.array(fowt.A_hydro_morison)
+    with open(pickle_path, "rb") as f:
+        tv = pickle.load(f)
+    out["ref_pickle_qtf"] = np.array(tv["qtf"])                                          # [nw2, nw2, 1, 6]
+    out["ref_pickle_case"] = np.array([float(np.ravel(tv["case"][k])[0]) for k in ("wave_height", "wave_period", "wave_heading")])
+    rec = {}
+    orig = fowt.calcQTF_slenderBody
+
+    def wrapped(waveHeadInd, Xi0=None, **kw):
+        rec["Xi0"] = np.array(Xi0)
+        kw.pop("verbose", None)
+        r = orig(waveHeadInd, Xi0=Xi0, **kw)
+        rec["qtf"] = np.array(fowt.qtf)
+        return r
+    fowt.calcQTF_slenderBody = wrapped
+    cnt, orig_lin = count_passes(fowt)
+    keys = ("Xi", "passes", "Xi0", "qtf", "F2nd", "F2nd_mean")
+    acc = {k: [] for k in keys}
+    for (Hs, Tp, beta) in solve_cases:
+        cnt[0] = 0
+        x = rh.solve_dynamics(model, rh.make_case(Hs, Tp, beta))
+        acc["Xi"].append(np.array(x[0])), acc["passes"].append(cnt[0]), acc["Xi0"].append(rec["Xi0"]), acc["qtf"].append(rec["qtf"][:, :, 0, :])
+        acc["F2nd"].append(np.array(fowt.Fhydro_2nd[0].real)), acc["F2nd_mean"].append(np.array(fowt.Fhydro_2nd_mean[0]))
+    fowt.calcHydroLinearization = orig_lin
+    out["ref_run_solve_cases"] = np.array(solve_cases, dtype=float)
+    for k in keys:
+        out["ref_run_solve_" + k] = np.array(acc[k])
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-28s nw=%4d nw2=%3d cases=%2d  %.1f s  %.0f KB" % (name, len(P["w"]), len(P["qs_w"]), len(solve_cases), time.time() - t0,
+                                                             os.path.getsize(path) / 1024))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -270,6 +315,9 @@ def main():
         Hs, Tp, beta = seeded_cases(5, 3)
         fixture_qtf("cfg3q_OC4semi-QTF_nw96", os.path.join(REF, "examples", "OC4semi-WAMIT_Coefs.yaml"), nw=96, max_freq=0.256,
                     solve_cases=list(zip(Hs, Tp, beta)) + [(6.0, 12.0, 30.0)], trains=[(6.0, 12.0, 30.0), (2.5, 7.0, -100.0)])
+    if not args.only or args.only in "slender_VolturnUS-S":
+        fixture_slender("slender_VolturnUS-S", os.path.join(td, "VolturnUS-S.yaml"), os.path.join(td, "VolturnUS-S_true_calcQTF_slenderBody.pkl"),
+                        solve_cases=[(6.0, 12.0, 30.0), (2.0, 7.5, -75.0), (9.0, 15.0, 160.0)])
     if not args.only or args.only in "turb_VolturnUS-S":
         fixture_turbine("turb_VolturnUS-S", os.path.join(td, "VolturnUS-S.yaml"))
     if not args.only:

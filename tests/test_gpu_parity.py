@@ -676,3 +676,95 @@ def test_model_api_turbine_channels(solver):
                 assert abs(mine - ref) <= 1e-8 * max(abs(ref), 1e-12), (ic, nm, suffix)
             refp = z["ref_run_case%d_%s_PSD" % (ic, nm)]
             assert relerr(np.ravel(m[nm + "_PSD"]), np.ravel(refp)) < 1e-8, (ic, nm)
+
+
+# ---- slender-body QTF (potSecOrder 1): raft_fowt.py:1988-2078, raft_member.py:1488-1792 ---------------------------
+
+def _slender_golden():
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "slender_VolturnUS-S.npz"))
+    return z, {k[2:]: z[k] for k in z.files if k.startswith("P_")}
+
+
+def test_slender_qtf_vs_reference_pickle_and_run(solver, oracle):
+    """k_slender_tables / k_slender_pairs: fixed body vs the reference's own golden pickle; moving body vs the QTFs the
+    reference computed inside solveDynamics; random motions and headings vs the oracle (all pairs in one call)."""
+    z, P = _slender_golden()
+    n2 = len(P["qs_w"])
+    deg = 0.017453292519943295
+    q = solver.qtf_slender(P, [z["ref_pickle_case"][2] * deg], np.zeros([1, 6, n2], dtype=complex))
+    for a in range(6):
+        assert relerr(q[0][..., a], z["ref_pickle_qtf"][:, :, 0, a]) < RTOL, a
+    cases = z["ref_run_solve_cases"]
+    Xi2 = np.array([[np.interp(P["qs_w"], P["w"], z["ref_run_solve_Xi0"][i][a], left=0, right=0) for a in range(6)] for i in range(len(cases))])
+    q = solver.qtf_slender(P, cases[:, 2] * deg, Xi2)
+    for i in range(len(cases)):
+        for a in range(6):
+            assert relerr(q[i][..., a], z["ref_run_solve_qtf"][i][..., a]) < RTOL, (i, a)
+    rng = np.random.default_rng(5)
+    Xr = (rng.normal(size=(4, 6, n2)) + 1j * rng.normal(size=(4, 6, n2))) * np.array([1, 1, 1, 0.03, 0.03, 0.03])[None, :, None]
+    betas = rng.uniform(-np.pi, np.pi, 4)
+    q = solver.qtf_slender(P, betas, Xr)
+    od = oracle.OracleDesign(P)
+    for c in range(4):
+        qo = oracle.qtf_slender(od, betas[c], Xr[c])
+        for a in range(6):
+            assert relerr(q[c][..., a], qo[..., a]) < RTOL, (c, a)
+        off = ~np.eye(n2, dtype=bool)
+        assert np.array_equal(q[c][off], np.conj(np.swapaxes(q[c], 0, 1))[off])          # Hermitian fill
+
+
+def test_slender_solve_flow_vs_reference_run(solver, oracle):
+    """Model.solveDynamics with potSecOrder 1: loop, QTF from the motions, second-order force, loop continued from the
+    same iterate -- responses, pass counts, force and QTF against the unmodified reference; Xi_init / Xi_last plumbing."""
+    z, P = _slender_golden()
+    cs = z["ref_run_solve_cases"]
+    n = len(cs)
+    table = dict(Hs=cs[:, 0], Tp=cs[:, 1], gamma=np.zeros(n), beta_deg=cs[:, 2], spec=np.zeros(n, dtype=np.int32))
+    out = solver.solve_dynamics_slender(P, solver.CaseTable(table), n_iter=int(z["n_iter"]), xi_start=float(z["xi_start"]))
+    assert np.array_equal(out["status"][0, :, 0], z["ref_run_solve_passes"])
+    assert response_err(out["Xi"][0], z["ref_run_solve_Xi"]) < RTOL
+    assert relerr(out["F_2nd"][0], z["ref_run_solve_F2nd"]) < RTOL and relerr(out["F_2nd_mean"][0], z["ref_run_solve_F2nd_mean"]) < RTOL
+    for i in range(n):
+        assert relerr(out["qtf"][0, i], z["ref_run_solve_qtf"][i]) < RTOL
+    # oracle agrees on the converged flag as well
+    od = oracle.OracleDesign(P)
+    for i in range(n):
+        _, st = oracle.solve_dynamics(od, 0, cs[i, 0], cs[i, 1], 0.0, cs[i, 2], nIter=int(z["n_iter"]), XiStart=float(z["xi_start"]))
+        assert out["status"][0, i, 1] == st[1]
+    # Xi_last of a converged solve is the iterate of its last pass: restarting from it with no extra force reproduces Xi in one pass
+    plain = solver.DesignBatch({k: v for k, v in P.items() if not k.startswith("qs_")})
+    A = solver.solve_dynamics(plain, solver.CaseTable(table), n_iter=int(z["n_iter"]), xi_start=float(z["xi_start"]), cluster_size=2, want=("Xi", "status", "Xi_last"))
+    Bq = solver.solve_dynamics(plain, solver.CaseTable(table, Xi_init=A["Xi_last"]), n_iter=int(z["n_iter"]), cluster_size=2)
+    conv = A["status"][0, :, 1] == 1
+    assert conv.any() and np.all(Bq["status"][0, conv, 0] == 1)
+    assert np.array_equal(Bq["Xi"][0, conv], A["Xi"][0, conv])
+
+
+def test_slender_model_api(solver):
+    """raft_b200.Model / FOWT with potSecOrder 1 from the design dict: calcQTF_slenderBody mirror (fixed body, golden
+    pickle) and solveDynamics / analyzeCases against the reference run."""
+    import json, os
+    from conftest import GOLDEN
+    from raft_b200.model import Model
+    z, P = _slender_golden()
+    D = json.load(open(os.path.join(GOLDEN, "designs.json")))["test_VolturnUS-S"]
+    design = dict(D, platform=dict(D["platform"], potSecOrder=1), site=dict(D["site"], water_depth=float(P["depth"])))
+    mats = dict(M_struc=P["M0"] - z["A_hydro_morison"], C_struc=P["C0"] - z["C_moor"], C_moor=z["C_moor"])
+    model = Model(design, matrices=mats)
+    f = model.fowtList[0]
+    assert f.potSecOrder == 1 and np.array_equal(f.w1_2nd, P["qs_w"]) and relerr(f.k1_2nd, P["qs_k"]) < 1e-15
+    h, t, b = z["ref_pickle_case"]
+    f.calcHydroExcitation(dict(wave_spectrum="JONSWAP", wave_height=h, wave_period=t, wave_heading=b, wave_gamma=0))
+    q = f.calcQTF_slenderBody(0)
+    assert q.shape == z["ref_pickle_qtf"].shape
+    for a in range(6):
+        assert relerr(q[..., a], z["ref_pickle_qtf"][..., a]) < 1e-9, a
+    cases = [dict(wave_spectrum="JONSWAP", wave_height=h_, wave_period=t_, wave_heading=b_) for h_, t_, b_ in z["ref_run_solve_cases"]]
+    res = model.analyzeCases(cases)
+    assert np.array_equal(res["status"][:, 0, 0], z["ref_run_solve_passes"])
+    assert response_err(res["Xi"], z["ref_run_solve_Xi"]) < 1e-9
+    assert relerr(f.Fhydro_2nd[0].real, z["ref_run_solve_F2nd"][-1]) < 1e-9
+    with pytest.raises(NotImplementedError):
+        model.solveDynamics(dict(wave_spectrum=["JONSWAP"] * 2, wave_height=[2.0, 1.0], wave_period=[8.0, 12.0], wave_heading=[0.0, 40.0], wave_gamma=[0.0, 0.0]))

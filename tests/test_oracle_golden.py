@@ -176,3 +176,29 @@ def test_second_order_heading_interpolation_vs_reference_run(oracle):
         fm, f = oracle.hydro_force_2nd(od, b * 0.017453292519943295, G["ref_run_S"][0])
         assert relerr(f, G["ref_run_mh_F2nd"][i]) < 1e-13
         assert relerr(fm, G["ref_run_mh_F2nd_mean"][i]) < 1e-13
+
+
+def test_slender_body_qtf_vs_reference_pickle_and_run(oracle):
+    """potSecOrder 1: the oracle's calcQTF_slenderBody vs the reference's OWN golden pickle (fixed body; the reference's
+    test allows rtol 1e-5) and vs QTFs the reference computed inside solveDynamics with the body moving; then the full
+    solve with the QTF inside the loop (response, pass count)."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "slender_VolturnUS-S.npz"))
+    P = {k[2:]: z[k] for k in z.files if k.startswith("P_")}
+    od = oracle.OracleDesign(P)
+    n2 = len(P["qs_w"])
+    q = oracle.qtf_slender(od, z["ref_pickle_case"][2] * 0.017453292519943295, np.zeros([6, n2], dtype=complex))
+    ref = z["ref_pickle_qtf"][:, :, 0, :]
+    for a in range(6):
+        assert relerr(q[..., a], ref[..., a]) < 1e-13, a
+    cases = z["ref_run_solve_cases"]
+    for i, (Hs, Tp, beta) in enumerate(cases):
+        Xi0 = z["ref_run_solve_Xi0"][i]
+        Xi2 = np.array([np.interp(P["qs_w"], P["w"], Xi0[a], left=0, right=0) for a in range(6)])
+        q = oracle.qtf_slender(od, beta * 0.017453292519943295, Xi2)
+        for a in range(6):
+            assert relerr(q[..., a], z["ref_run_solve_qtf"][i][..., a]) < 1e-13, (i, a)
+        Xi, st = oracle.solve_dynamics(od, 0, Hs, Tp, 0.0, beta, nIter=int(z["n_iter"]), XiStart=float(z["xi_start"]))
+        assert st[0] == z["ref_run_solve_passes"][i]
+        assert response_err(Xi, z["ref_run_solve_Xi"][i]) < 1e-11
