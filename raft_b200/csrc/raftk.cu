@@ -771,7 +771,8 @@ extern "C" size_t raftk_qtf_slender_workspace_bytes(const raftk_slender *s, int3
 {
     if (!s || n_cases <= 0) return 0;
     return align_up((size_t)n_cases * std::max(s->n_nodes, 1) * s->nw * SL_NODE_C * sizeof(cx), 256)
-           + align_up((size_t)n_cases * s->n_members * s->nw * SL_MEM_C * sizeof(cx), 256);
+           + align_up((size_t)n_cases * s->n_members * s->nw * SL_MEM_C * sizeof(cx), 256)
+           + align_up((size_t)(s->n_members + s->n_seg) * s->nw * SL_HANK * sizeof(cx), 256);
 }
 
 extern "C" int raftk_qtf_slender_dev(const raftk_slender *s, int32_t n_cases, const double *beta_rad, const double *Xi_rao, double *qtf,
@@ -793,11 +794,12 @@ extern "C" int raftk_qtf_slender_dev(const raftk_slender *s, int32_t n_cases, co
     cudaStream_t st = (cudaStream_t)stream;
     cx *Tn = static_cast<cx *>(workspace);
     cx *Tm = reinterpret_cast<cx *>(static_cast<char *>(workspace) + align_up((size_t)n_cases * std::max(s->n_nodes, 1) * s->nw * SL_NODE_C * sizeof(cx), 256));
+    cx *Th = reinterpret_cast<cx *>(reinterpret_cast<char *>(Tm) + align_up((size_t)n_cases * s->n_members * s->nw * SL_MEM_C * sizeof(cx), 256));
     const cx *X = reinterpret_cast<const cx *>(Xi_rao);
     cx *Q = reinterpret_cast<cx *>(qtf);
-    k_slender_tables<<<dim3(s->n_nodes + s->n_members, n_cases), SL_THREADS, 0, st>>>(D, beta_rad, X, Tn, Tm);
+    k_slender_tables<<<dim3(s->n_nodes + 2 * s->n_members + s->n_seg, n_cases), SL_THREADS, 0, st>>>(D, beta_rad, X, Tn, Tm, Th);
     const unsigned npairs = (unsigned)((size_t)s->nw * (s->nw + 1) / 2);
-    k_slender_pairs<<<dim3(npairs, n_cases), SL_THREADS, 0, st>>>(D, beta_rad, X, Tn, Tm, Q);
+    k_slender_pairs<<<dim3(npairs, n_cases), SL_THREADS, 0, st>>>(D, beta_rad, X, Tn, Tm, Th, Q);
     k_slender_fill<<<dim3(s->nw, n_cases), 64, 0, st>>>(s->nw, Q);
     g_launches += 3;
     CUDA_TRY(cudaGetLastError());

@@ -3,8 +3,9 @@
 // wave kinematics of helpers.py:239-373  (included by raftk.cu only).
 //
 // Two kernels per call.  k_slender_tables: per (case, node, frequency) first-order kinematics -- body displacement and
-// transverse velocity, wave velocity and its gradient, relative axial velocity, pressure gradient -- and per (case,
-// member, frequency) the waterline quantities; the reference recomputes all of these inside its frequency-pair loop.
+// transverse velocity, wave velocity and its gradient, relative axial velocity, pressure gradient --, per (case,
+// member, frequency) the waterline quantities, and per (radius, frequency) the Hankel functions of the Kim & Yue
+// correction; the reference recomputes all of these inside its frequency-pair loop.
 // k_slender_pairs: one CTA per (frequency pair w2 >= w1, case); its threads split the strip nodes (and the members'
 // waterline / Kim & Yue terms), evaluate Rainey's second-order terms and the second-order potential, and a fixed-order
 // block reduction gives the six force components.  k_slender_fill adds the conjugate triangle.
@@ -17,6 +18,7 @@
 #define SL_THREADS 64
 #define SL_NODE_C 22          // complex numbers per (case, node, frequency): dr 3, vt 3, u 3, G 9, vax 1, gp 3
 #define SL_MEM_C 10           // per (case, member, frequency): eta_r 1, ud_wl 3, a_wl 3, g_e1 3
+#define SL_HANK 14            // Hankel orders -1 .. 12 per (radius, frequency) for the Kim & Yue correction
 #define SL_DEG 0.017453292519943295
 
 struct cx { double x, y; };
@@ -166,12 +168,13 @@ __host__ __device__ inline cx sl_hankel1(int n, double x)
     cx hv = mk(jn(m, x), yn(m, x));
     return (n < 0 && (m & 1)) ? -hv : hv;
 }
-__host__ __device__ inline cx sl_kay_omega(double k1R, double k2R, int n)
+// raft_member.py:1700-1708 omega(k1R, k2R, n); h1 / h2: H_{-1..12}(k1 R), H_{-1..12}(k2 R) from the table (index order + 1)
+__host__ __device__ inline cx sl_kay_omega(const cx *h1, const cx *h2, int n)
 {
-    const cx H_N_ii = (sl_hankel1(n - 1, k1R) - sl_hankel1(n + 1, k1R)) * 0.5;
-    const cx H_N_jj = cj(sl_hankel1(n - 1, k2R) - sl_hankel1(n + 1, k2R)) * 0.5;
-    const cx H_Nm1_ii = (sl_hankel1(n, k1R) - sl_hankel1(n + 2, k1R)) * 0.5;
-    const cx H_Nm1_jj = cj(sl_hankel1(n, k2R) - sl_hankel1(n + 2, k2R)) * 0.5;
+    const cx H_N_ii = (h1[n] - h1[n + 2]) * 0.5;
+    const cx H_N_jj = cj(h2[n] - h2[n + 2]) * 0.5;
+    const cx H_Nm1_ii = (h1[n + 1] - h1[n + 3]) * 0.5;
+    const cx H_Nm1_jj = cj(h2[n + 1] - h2[n + 3]) * 0.5;
     return mk(1.0) / (H_Nm1_ii * H_N_jj) - mk(1.0) / (H_N_ii * H_Nm1_jj);
 }
 
@@ -193,9 +196,22 @@ struct SlenderDev {
 // tables: grid (n_nodes + n_members, n_cases), block SL_THREADS; thread loops over frequencies
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SL_THREADS) k_slender_tables(SlenderDev D, const double *beta_rad, const cx *Xi /*[nC][6][nw]*/,
-                                                               cx *Tn /*[nC][Ns][nw][22]*/, cx *Tm /*[nC][Nm][nw][10]*/)
+                                                               cx *Tn /*[nC][Ns][nw][22]*/, cx *Tm /*[nC][Nm][nw][10]*/,
+                                                               cx *Th /*[Nm + n_seg][nw][14]*/)
 {
     const int c = blockIdx.y, nw = D.nw;
+    if ((int)blockIdx.x >= D.n_nodes + D.n_members) {
+        // Hankel functions of the Kim & Yue correction: they depend on (radius, frequency) only, not on the pair or the case
+        if (c != 0) return;
+        const int x = blockIdx.x - D.n_nodes - D.n_members;
+        const bool live = x < D.n_members ? (D.mem_mcf[x] != 0) : (D.mem_mcf[D.seg_mem[x - D.n_members]] != 0);
+        const double R = x < D.n_members ? D.mem_R_wl[x] : D.seg_R[x - D.n_members];
+        for (int t = threadIdx.x; t < nw * SL_HANK; t += SL_THREADS) {
+            const int i = t / SL_HANK, n = t % SL_HANK - 1;
+            Th[((size_t)x * nw + i) * SL_HANK + (n + 1)] = live ? sl_hankel1(n, D.k[i] * R) : mk(0.0);
+        }
+        return;
+    }
     const double beta = beta_rad[c], h = D.depth;
     const cx *X = Xi + (size_t)c * 6 * nw;
     if ((int)blockIdx.x < D.n_nodes) {
@@ -305,8 +321,8 @@ __host__ __device__ inline void sl_node_terms(const SlenderDev &D, int m, int j,
 
 // member-level terms of the pair: relative-wave-elevation force at the waterline (raft_member.py:1655-1683) and the
 // Kim & Yue correction (:1692-1792)
-__host__ __device__ inline void sl_member_terms(const SlenderDev &D, int m, const cx *tm1, const cx *tm2, double w1, double w2, double k1,
-                                                double k2, double beta, cx (&F)[6])
+__host__ __device__ inline void sl_member_terms(const SlenderDev &D, int m, const cx *tm1, const cx *tm2, const cx *Th, int i1, int i2,
+                                                double w1, double w2, double k1, double k2, double beta, cx (&F)[6])
 {
     const double *p1 = D.mem_p1 + 3 * m, *p2 = D.mem_p2 + 3 * m;
     const double rho = D.rho, g = D.g, h = D.depth;
@@ -338,8 +354,9 @@ __host__ __device__ inline void sl_member_terms(const SlenderDev &D, int m, cons
         const cx ph = cexpi(-(kx * rwl[0] + ky * rwl[1]));
         {
             const double R = D.mem_R_wl[m], k1R = k1 * R, k2R = k2 * R;
+            const cx *h1 = Th + ((size_t)m * D.nw + i1) * SL_HANK, *h2 = Th + ((size_t)m * D.nw + i2) * SL_HANK;
             cx Fwl = mk(0.0);
-            for (int nn = 0; nn <= 10; nn++) Fwl = Fwl + mk(0.0, -rho * g * R * 2 / CUDART_PI / (k1R * k2R)) * sl_kay_omega(k1R, k2R, nn);
+            for (int nn = 0; nn <= 10; nn++) Fwl = Fwl + mk(0.0, -rho * g * R * 2 / CUDART_PI / (k1R * k2R)) * sl_kay_omega(h1, h2, nn);
             force6(vecr(pf, ph * Fwl.x), rwl, K);
         }
         for (int s = 0; s < D.n_seg; s++) {
@@ -355,9 +372,10 @@ __host__ __device__ inline void sl_member_terms(const SlenderDev &D, int m, cons
                 Ip = 0.5 * (sinh((k1 + k2) * (z2 + h)) / (k1h + k2h) + sinh((k1 - k2) * (z2 + h)) / (k1h - k2h) - sinh((k1 + k2) * (z1 + h)) / (k1h + k2h) - sinh((k1 - k2) * (z1 + h)) / (k1h - k2h));
             }
             const double c1 = cosh(k1h), c2 = cosh(k2h);
+            const cx *h1 = Th + ((size_t)(D.n_members + s) * D.nw + i1) * SL_HANK, *h2 = Th + ((size_t)(D.n_members + s) * D.nw + i2) * SL_HANK;
             cx dF = mk(0.0);
             for (int nn = 0; nn <= 10; nn++)
-                dF = dF + mk(0.0, rho * g * R * 2 / CUDART_PI / (k1R * k2R)) * sl_kay_omega(k1R, k2R, nn)
+                dF = dF + mk(0.0, rho * g * R * 2 / CUDART_PI / (k1R * k2R)) * sl_kay_omega(h1, h2, nn)
                           * (k1h * k2h / sqrt(k1h * tanh(k1h)) / sqrt(k2h * tanh(k2h)) * (Im + Ip * nn * (nn + 1) / k1R / k2R) / c1 / c2);
             force6(vecr(pf, ph * dF.x), D.seg_rmid + 3 * s, K);
         }
@@ -369,7 +387,7 @@ __host__ __device__ inline void sl_member_terms(const SlenderDev &D, int m, cons
 // pairs: grid (nw (nw + 1) / 2, n_cases), block SL_THREADS.  qtf [nC][nw][nw][6], upper triangle i2 >= i1.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SL_THREADS) k_slender_pairs(SlenderDev D, const double *beta_rad, const cx *Xi, const cx *Tn, const cx *Tm,
-                                                              cx *qtf)
+                                                              const cx *Th, cx *qtf)
 {
     __shared__ cx part[SL_THREADS][6];
     const int c = blockIdx.y, nw = D.nw, tid = threadIdx.x;
@@ -400,7 +418,7 @@ __global__ void __launch_bounds__(SL_THREADS) k_slender_pairs(SlenderDev D, cons
         for (int m = tid; m < D.n_members; m += SL_THREADS) {
             const cx *tm1 = Tm + (((size_t)c * D.n_members + m) * nw + i1) * SL_MEM_C;
             const cx *tm2 = Tm + (((size_t)c * D.n_members + m) * nw + i2) * SL_MEM_C;
-            sl_member_terms(D, m, tm1, tm2, w1, w2, k1, k2, beta, F);
+            sl_member_terms(D, m, tm1, tm2, Th, i1, i2, w1, w2, k1, k2, beta, F);
         }
         if (tid == 0) {                                           // Pinkster IV: rotation of the first-order forces (raft_fowt.py:2044-2058)
             cx F1a[6], F1b[6];
