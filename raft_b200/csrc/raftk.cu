@@ -525,6 +525,14 @@ extern "C" int raftk_system_solve_dev(int32_t n, int32_t nw, int32_t nrhs, doubl
 }
 
 // ---- host-pointer front ends -------------------------------------------------------------------------
+// temporary device allocation released on every exit path of the small *_host wrappers
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+#define DEV_ALLOC(buf, bytes) CUDA_TRY(cudaMalloc(&(buf).p, (bytes)))
+
 struct Arena {
     char *base = nullptr; size_t cap = 0, used = 0;
     int reserve(size_t bytes)
@@ -856,15 +864,14 @@ extern "C" int raftk_system_solve_host(int32_t n, int32_t nw, int32_t nrhs, doub
 {
     if (n <= 0 || nw <= 0 || nrhs <= 0 || !Z || !F) return set_err(RAFTK_EINVAL, "bad system-solve arguments");
     const size_t zb = (size_t)nw * n * n * 16, fb = (size_t)nw * n * nrhs * 16, ib = (size_t)nw * 4;
-    double *dZ = nullptr, *dF = nullptr; int32_t *dI = nullptr;
-    CUDA_TRY(cudaMalloc(&dZ, zb)); CUDA_TRY(cudaMalloc(&dF, fb)); CUDA_TRY(cudaMalloc(&dI, ib));
-    CUDA_TRY(cudaMemcpy(dZ, Z, zb, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dF, F, fb, cudaMemcpyHostToDevice));
-    int rc = raftk_system_solve_dev(n, nw, nrhs, dZ, dF, dI, nullptr);
+    DevBuf dZ, dF, dI;
+    DEV_ALLOC(dZ, zb); DEV_ALLOC(dF, fb); DEV_ALLOC(dI, ib);
+    CUDA_TRY(cudaMemcpy(dZ.p, Z, zb, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dF.p, F, fb, cudaMemcpyHostToDevice));
+    int rc = raftk_system_solve_dev(n, nw, nrhs, dZ.as<double>(), dF.as<double>(), dI.as<int32_t>(), nullptr);
     if (!rc) {
-        CUDA_TRY(cudaMemcpy(F, dF, fb, cudaMemcpyDeviceToHost));
-        if (info) CUDA_TRY(cudaMemcpy(info, dI, ib, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(F, dF.p, fb, cudaMemcpyDeviceToHost));
+        if (info) CUDA_TRY(cudaMemcpy(info, dI.p, ib, cudaMemcpyDeviceToHost));
     }
-    cudaFree(dZ); cudaFree(dF); cudaFree(dI);
     return rc;
 }
 
@@ -883,16 +890,15 @@ extern "C" int raftk_response_stats_host(int32_t n_units, int32_t nw, double dw,
 {
     if (n_units <= 0 || nw <= 0 || !Xi || !sd || !(dw > 0.0)) return set_err(RAFTK_EINVAL, "bad response-stats arguments");
     const size_t xb = (size_t)n_units * 6 * nw * 16, sb = (size_t)n_units * 6 * 8, pb = (size_t)n_units * 6 * nw * 8;
-    double *dX = nullptr, *dS = nullptr, *dP = nullptr;
-    CUDA_TRY(cudaMalloc(&dX, xb)); CUDA_TRY(cudaMalloc(&dS, sb));
-    if (psd) CUDA_TRY(cudaMalloc(&dP, pb));
-    CUDA_TRY(cudaMemcpy(dX, Xi, xb, cudaMemcpyHostToDevice));
-    int rc = raftk_response_stats_dev(n_units, nw, dw, rot_deg, dX, dS, dP, nullptr);
+    DevBuf dX, dS, dP;
+    DEV_ALLOC(dX, xb); DEV_ALLOC(dS, sb);
+    if (psd) DEV_ALLOC(dP, pb);
+    CUDA_TRY(cudaMemcpy(dX.p, Xi, xb, cudaMemcpyHostToDevice));
+    int rc = raftk_response_stats_dev(n_units, nw, dw, rot_deg, dX.as<double>(), dS.as<double>(), dP.as<double>(), nullptr);
     if (!rc) {
-        CUDA_TRY(cudaMemcpy(sd, dS, sb, cudaMemcpyDeviceToHost));
-        if (psd) CUDA_TRY(cudaMemcpy(psd, dP, pb, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(sd, dS.p, sb, cudaMemcpyDeviceToHost));
+        if (psd) CUDA_TRY(cudaMemcpy(psd, dP.p, pb, cudaMemcpyDeviceToHost));
     }
-    cudaFree(dX); cudaFree(dS); if (dP) cudaFree(dP);
     return rc;
 }
 
@@ -918,18 +924,18 @@ extern "C" int raftk_channel_stats_host(int32_t n_designs, int32_t n_cases, int3
     const size_t rows = (size_t)n_designs * n_cases * n_ch;
     const size_t cb = (size_t)n_designs * n_ch * 6 * nw * 16, xb = (size_t)n_designs * n_cases * 6 * nw * 16;
     const size_t sb = rows * 8, pb = rows * nw * 8, ab = rows * nw * 16;
-    double *dC = nullptr, *dX = nullptr, *dS = nullptr, *dP = nullptr, *dA = nullptr;
-    CUDA_TRY(cudaMalloc(&dC, cb)); CUDA_TRY(cudaMalloc(&dX, xb)); CUDA_TRY(cudaMalloc(&dS, sb));
-    if (psd) CUDA_TRY(cudaMalloc(&dP, pb));
-    if (amp) CUDA_TRY(cudaMalloc(&dA, ab));
-    CUDA_TRY(cudaMemcpy(dC, coef, cb, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dX, Xi, xb, cudaMemcpyHostToDevice));
-    int rc = raftk_channel_stats_dev(n_designs, n_cases, n_ch, nw, dw, dC, dX, dS, dP, dA, nullptr);
+    DevBuf dC, dX, dS, dP, dA;
+    DEV_ALLOC(dC, cb); DEV_ALLOC(dX, xb); DEV_ALLOC(dS, sb);
+    if (psd) DEV_ALLOC(dP, pb);
+    if (amp) DEV_ALLOC(dA, ab);
+    CUDA_TRY(cudaMemcpy(dC.p, coef, cb, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dX.p, Xi, xb, cudaMemcpyHostToDevice));
+    int rc = raftk_channel_stats_dev(n_designs, n_cases, n_ch, nw, dw, dC.as<double>(), dX.as<double>(), dS.as<double>(), dP.as<double>(),
+                                     dA.as<double>(), nullptr);
     if (!rc) {
-        CUDA_TRY(cudaMemcpy(sd, dS, sb, cudaMemcpyDeviceToHost));
-        if (psd) CUDA_TRY(cudaMemcpy(psd, dP, pb, cudaMemcpyDeviceToHost));
-        if (amp) CUDA_TRY(cudaMemcpy(amp, dA, ab, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(sd, dS.p, sb, cudaMemcpyDeviceToHost));
+        if (psd) CUDA_TRY(cudaMemcpy(psd, dP.p, pb, cudaMemcpyDeviceToHost));
+        if (amp) CUDA_TRY(cudaMemcpy(amp, dA.p, ab, cudaMemcpyDeviceToHost));
     }
-    cudaFree(dC); cudaFree(dX); cudaFree(dS); if (dP) cudaFree(dP); if (dA) cudaFree(dA);
     return rc;
 }
 
