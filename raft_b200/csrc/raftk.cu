@@ -206,9 +206,36 @@ static int run_qtf(const raftk_designs *d, const raftk_cases *c, double *F2, dou
             smem_set = smem;
         }
     }
+    if (P.shared != 1 && d->n_designs > 65535) return set_err(RAFTK_EINVAL, "second-order force: more than 65535 designs per call");
+    if (c->n_cases > 65535) return set_err(RAFTK_EINVAL, "second-order force: more than 65535 cases per call");
+    // tile variant (registers hold the table-cell corners, systolic diagonal accumulators) when its shared-memory
+    // tables fit and the frequency rows fit k_qtf_finish's register staging; RAFTK_QTF_DIAG=1 forces the diagonal kernel
+    const int ncell = d->n_qtf_w - 1;
+    const size_t tsmem = (size_t)d->nw * 68 + (size_t)ncell * 8 + 16;
+    const bool tiles = !getenv("RAFTK_QTF_DIAG") && tsmem <= 226 * 1024 && d->nw <= 4096;
+    if (tiles) {
+        static size_t tsmem_set = 48 * 1024;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (tsmem > tsmem_set) {
+                CUDA_TRY(cudaFuncSetAttribute(k_qtf_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                tsmem_set = tsmem;
+            }
+        }
+        QtfTileParams TP;
+        TP.q = P; TP.ncell = ncell;
+        const size_t rows = (size_t)((P.shared == 1) ? 1 : d->n_designs) * c->n_cases * 6 * d->nw;
+        CUDA_TRY(cudaMemsetAsync(F2, 0, rows * sizeof(double), st));
+        dim3 gt(QT_GROUPS, c->n_cases, P.shared == 1 ? 1 : d->n_designs);
+        k_qtf_tiles<<<gt, QT_THREADS, tsmem, st>>>(C, TP);
+        dim3 gf(6, c->n_cases, P.shared == 1 ? 1 : d->n_designs);
+        k_qtf_finish<<<gf, 256, 0, st>>>(C, P);
+        g_launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        return RAFTK_OK;
+    }
     const int ntasks = d->nw / 2 + 1, per_cta = (QTF_THREADS / 32) * QTF_TASKS_PER_WARP;
     dim3 grid((ntasks + per_cta - 1) / per_cta, c->n_cases, P.shared == 1 ? 1 : d->n_designs);
-    if (grid.y > 65535u || grid.z > 65535u) return set_err(RAFTK_EINVAL, "second-order force: more than 65535 cases or designs per call");
     if (P.nh > 1) k_qtf_force<true><<<grid, QTF_THREADS, smem, st>>>(C, P);
     else k_qtf_force<false><<<grid, QTF_THREADS, smem, st>>>(C, P);
     g_launches++;

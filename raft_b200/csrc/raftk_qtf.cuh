@@ -146,3 +146,229 @@ __global__ void __launch_bounds__(QTF_THREADS, QTF_MIN_CTAS) k_qtf_force(CasesDe
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Tile variant (k_qtf_tiles + k_qtf_finish).  ncu on k_qtf_force shows L1TEX at 94 % while the FP64 pipe idles at
+// 35 %: every lane re-loads the four corner values of its table cell for every element (a 128-bit load costs four
+// L1 wavefronts even when all lanes read the same address).  Here a warp works on ONE pair of table cells at a time:
+// the corners (heading-blended) sit in registers for the whole tile, lanes are 32 consecutive columns j, the rows i of
+// the cell are walked in order, and the per-diagonal accumulators are SYSTOLIC: the diagonal mu = j - i held by lane l
+// at row i continues in lane l + 1 at row i + 1, so the accumulators shift up one lane per row (6 shuffles), lane 0
+// starts a new diagonal and lane 31 retires one into the CTA's shared-memory sums.  Sums of a case are combined across
+// its CTAs with atomic adds into the (zeroed) F_2nd buffer; k_qtf_finish turns them into amplitudes, applies the
+// one-bin shift and computes the mean drift.  Floating-point addition order therefore varies run to run (1e-16).
+// ------------------------------------------------------------------------------------------------
+#define QT_THREADS 512
+#define QT_GROUPS 4             // CTAs per (case, table)
+
+struct QtfTileParams {
+    QtfParams q;
+    int ncell;                  // n2 - 1
+};
+
+__device__ __forceinline__ void qtf_heading(const CasesDev &Cs, const QtfParams &P, int c, int &hl, int &hh, double &hr)
+{
+    hl = 0; hh = 0; hr = 0.0;
+    if (P.nh > 1) {
+        const double beta = Cs.beta_deg[c] * (CUDART_PI / 180.0);
+        if (beta < P.qh[0]) { hl = hh = 0; }
+        else if (beta > P.qh[P.nh - 1]) { hl = hh = P.nh - 1; }
+        else {
+            int idx = 0;
+            while (idx < P.nh && P.qh[idx] < beta) idx++;      // searchsorted, side left
+            idx = min(max(idx, 1), P.nh - 1);
+            hl = idx - 1; hh = idx;
+            hr = (beta - P.qh[hl]) / (P.qh[hh] - P.qh[hl]);
+        }
+    }
+}
+
+__device__ __forceinline__ void qtf_bin_tables(const CasesDev &Cs, const QtfParams &P, int c, double *S0, double *tt, int *cell, int tid, int nthreads)
+{
+    for (int i = tid; i < P.nw; i += nthreads) {
+        const double x = P.w[i];
+        S0[i] = sea_state_S(Cs, c, i, P.nw, x, P.dw);
+        int ci = -1; double t = 0.0;
+        if (x >= P.qw[0] && x <= P.qw[P.n2 - 1]) {
+            int lo = 0, hi = P.n2 - 1;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.qw[mid] <= x) lo = mid; else hi = mid; }
+            ci = lo;
+            t = (x - P.qw[ci]) / (P.qw[ci + 1] - P.qw[ci]);
+        }
+        cell[i] = ci; tt[i] = t;
+    }
+}
+
+__global__ void __launch_bounds__(QT_THREADS, 1) k_qtf_tiles(CasesDev Cs, QtfTileParams TP)
+{
+    extern __shared__ __align__(16) double qsm[];
+    __shared__ int maxw_s;
+    const QtfParams &P = TP.q;
+    const int nw = P.nw, n2 = P.n2, nh = P.nh, ncell = TP.ncell;
+    double *S0 = qsm, *tt = qsm + nw, *f2s = qsm + 2 * (size_t)nw;            // f2s [6][nw]
+    int *cell = reinterpret_cast<int *>(qsm + 8 * (size_t)nw);
+    int *cstart = cell + nw, *cend = cstart + ncell;
+    const int c = blockIdx.y, dz = blockIdx.z, grp = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    qtf_bin_tables(Cs, P, c, S0, tt, cell, tid, QT_THREADS);
+    for (int t = tid; t < 6 * nw; t += QT_THREADS) f2s[t] = 0.0;
+    for (int t = tid; t < 2 * ncell; t += QT_THREADS) cstart[t] = 0;           // cstart and cend are contiguous
+    if (tid == 0) maxw_s = 0;
+    __syncthreads();
+    for (int i = tid; i < nw; i += QT_THREADS) {
+        const int ci = cell[i];
+        if (ci >= 0) {
+            if (i == 0 || cell[i - 1] != ci) cstart[ci] = i;
+            if (i == nw - 1 || cell[i + 1] != ci) cend[ci] = i + 1;
+        }
+    }
+    int hl, hh; double hr;
+    qtf_heading(Cs, P, c, hl, hh, hr);
+    __syncthreads();
+    for (int t = tid; t < ncell; t += QT_THREADS) atomicMax(&maxw_s, cend[t] - cstart[t]);
+    __syncthreads();
+    const int smax = (maxw_s + 31) / 32;                     // column strips (32 bins) of the widest cell
+
+    const size_t tab = (P.shared == 1) ? (size_t)0 : (P.shared == 2 ? (size_t)dz * Cs.nC + c : (size_t)dz);
+    const double2 *Q = P.qtf + tab * n2 * n2 * nh * 6;
+    const size_t sj = (size_t)nh * 6, si = (size_t)n2 * nh * 6;
+    const bool mix = hh != hl;
+
+    // work items: (ci <= cj, strip of 32 columns of cell cj), dealt round-robin to the warps of the case's CTAs
+    const int npair = ncell * (ncell + 1) / 2;
+    const int nitems = npair * smax;
+    const int nwarps = (QT_THREADS / 32) * QT_GROUPS;
+    for (int item = grp * (QT_THREADS / 32) + warp; item < nitems; item += nwarps) {
+        const int pr = item / smax, s = item % smax;
+        int ci = 0, rem = pr;
+        while (rem >= ncell - ci) { rem -= ncell - ci; ci++; }
+        const int cjx = ci + rem;
+        const int a0 = cstart[ci], a1 = cend[ci], b0 = cstart[cjx], b1 = cend[cjx];
+        const int jb = b0 + 32 * s;
+        if (a1 <= a0 || jb >= b1) continue;
+        if (jb + 31 <= a0) continue;                                    // every column at or below the first row: no j > i
+        const int a1e = min(a1, jb + 31);                              // rows i >= jb + 31 have no column j > i in this strip
+        const int j = jb + lane;
+        const bool jin = j < b1;
+        const double sjv = jin ? S0[j] : 0.0, tj = jin ? tt[j] : 0.0;
+        const double2 *q00 = Q + ((size_t)ci * n2 + cjx) * sj + (size_t)hl * 6;
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            double2 v00[3], v01[3], v10[3], v11[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const int ad = 3 * half + a;
+                v00[a] = __ldg(q00 + ad); v01[a] = __ldg(q00 + sj + ad); v10[a] = __ldg(q00 + si + ad); v11[a] = __ldg(q00 + si + sj + ad);
+                if (mix) {
+                    const int dh = (hh - hl) * 6;
+                    const double2 u00 = __ldg(q00 + dh + ad), u01 = __ldg(q00 + sj + dh + ad);
+                    const double2 u10 = __ldg(q00 + si + dh + ad), u11 = __ldg(q00 + si + sj + dh + ad);
+                    v00[a].x = fma(u00.x - v00[a].x, hr, v00[a].x); v00[a].y = fma(u00.y - v00[a].y, hr, v00[a].y);
+                    v01[a].x = fma(u01.x - v01[a].x, hr, v01[a].x); v01[a].y = fma(u01.y - v01[a].y, hr, v01[a].y);
+                    v10[a].x = fma(u10.x - v10[a].x, hr, v10[a].x); v10[a].y = fma(u10.y - v10[a].y, hr, v10[a].y);
+                    v11[a].x = fma(u11.x - v11[a].x, hr, v11[a].x); v11[a].y = fma(u11.y - v11[a].y, hr, v11[a].y);
+                }
+            }
+            double acc[3] = {0.0, 0.0, 0.0}, ret[3] = {0.0, 0.0, 0.0};
+            int held = 0;                                               // retired diagonals parked in lanes 0 .. held-1
+            for (int i = a0; i < a1e; i++) {
+                const double ti = tt[i];
+                const double ss = (jin && j > i) ? S0[i] * sjv : 0.0;
+                const double w00 = (1.0 - ti) * (1.0 - tj), w01 = (1.0 - ti) * tj, w10 = ti * (1.0 - tj), w11 = ti * tj;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const double re = ((v00[a].x * w00 + v01[a].x * w01) + v10[a].x * w10) + v11[a].x * w11;
+                    const double im = ((v00[a].y * w00 + v01[a].y * w01) + v10[a].y * w10) + v11[a].y * w11;
+                    acc[a] = fma(ss, fma(re, re, im * im), acc[a]);
+                }
+                // lane 31's diagonal (mu = jb + 31 - i) is complete for this tile: park it in lane `held` (a single-lane
+                // shared-memory atomic per row would serialise the warp), shift the others up one lane, open a new one in lane 0
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const double out = __shfl_sync(0xffffffffu, acc[a], 31);
+                    if (lane == held) ret[a] = out;
+                    const double up = __shfl_up_sync(0xffffffffu, acc[a], 1);
+                    acc[a] = lane == 0 ? 0.0 : up;
+                }
+                held++;
+                if (held == 32 || i == a1e - 1) {                       // lane l parked the diagonal retired at row i - held + 1 + l
+                    const int mur = jb + 31 - (i - held + 1 + lane);
+                    if (lane < held && mur >= 1 && mur < nw) {
+#pragma unroll
+                        for (int a = 0; a < 3; a++) if (ret[a] != 0.0) atomicAdd(&f2s[(size_t)(3 * half + a) * nw + mur], ret[a]);
+                    }
+                    held = 0;
+                }
+            }
+            // after the last row (a1e - 1) and one more shift, lane l holds the diagonal of lane l - 1: mu = jb + l - 1 - (a1e - 1)
+            const int mu = jb + lane - a1e;
+            if (lane >= 1 && mu >= 1 && mu < nw) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) if (acc[a] != 0.0) atomicAdd(&f2s[(size_t)(3 * half + a) * nw + mu], acc[a]);
+            }
+        }
+    }
+    __syncthreads();
+    // combine the CTAs of this (case, table): atomic adds into the zeroed F_2nd rows (design dz, or design 0 when shared)
+    const size_t unit = (size_t)((P.shared == 1) ? 0 : dz) * Cs.nC + c;
+    for (int t = tid; t < 6 * nw; t += QT_THREADS) {
+        const double v = f2s[t];
+        if (v != 0.0) atomicAdd(&P.F2[unit * 6 * nw + t], v);
+    }
+}
+
+// F_2nd rows hold sum_i S_i S_{i+mu} |Q|^2 at index mu: -> 4 sqrt(.) dw shifted by one bin (raft_fowt.py:2236, :2244-2245),
+// plus the mean drift 2 dw sum_i S_i Re Q(w_i, w_i) (:2239).  grid (6, nC, nD|1), block 256.
+__global__ void __launch_bounds__(256) k_qtf_finish(CasesDev Cs, QtfParams P)
+{
+    __shared__ double red[8];
+    const int a = blockIdx.x, c = blockIdx.y, dz = blockIdx.z, tid = threadIdx.x, nw = P.nw, n2 = P.n2, nh = P.nh;
+    const size_t unit = (size_t)((P.shared == 1) ? 0 : dz) * Cs.nC + c;
+    double *row = P.F2 + (unit * 6 + a) * nw;
+    int hl, hh; double hr;
+    qtf_heading(Cs, P, c, hl, hh, hr);
+    const size_t tab = (P.shared == 1) ? (size_t)0 : (P.shared == 2 ? (size_t)dz * Cs.nC + c : (size_t)dz);
+    const double2 *Q = P.qtf + tab * n2 * n2 * nh * 6 + (size_t)hl * 6 + a;
+    const size_t sj = (size_t)nh * 6, si = (size_t)n2 * nh * 6;
+    const int dh = (hh - hl) * 6;
+    double sm = 0.0;
+    for (int i = tid; i < nw; i += 256) {                  // mean drift: diagonal of the interpolated table
+        const double x = P.w[i];
+        if (x >= P.qw[0] && x <= P.qw[n2 - 1]) {
+            int lo = 0, hi = n2 - 1;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.qw[mid] <= x) lo = mid; else hi = mid; }
+            const double t = (x - P.qw[lo]) / (P.qw[lo + 1] - P.qw[lo]);
+            const double2 *q00 = Q + ((size_t)lo * n2 + lo) * sj;
+            double r00 = __ldg(q00).x, r01 = __ldg(q00 + sj).x, r10 = __ldg(q00 + si).x, r11 = __ldg(q00 + si + sj).x;
+            if (dh) {
+                r00 = fma(__ldg(q00 + dh).x - r00, hr, r00); r01 = fma(__ldg(q00 + sj + dh).x - r01, hr, r01);
+                r10 = fma(__ldg(q00 + si + dh).x - r10, hr, r10); r11 = fma(__ldg(q00 + si + sj + dh).x - r11, hr, r11);
+            }
+            const double re = ((r00 * ((1.0 - t) * (1.0 - t)) + r01 * ((1.0 - t) * t)) + r10 * (t * (1.0 - t))) + r11 * (t * t);
+            sm = fma(sea_state_S(Cs, c, i, nw, x, P.dw), re, sm);
+        }
+    }
+    for (int o = 16; o >= 1; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    if ((tid & 31) == 0) red[tid >> 5] = sm;
+    // amplitudes, shifted by one bin: read everything before anything is written (in-place)
+    const int per = (nw + 255) / 256;
+    double vals[16];
+    for (int e = 0; e < per && e < 16; e++) {
+        const int m = tid + 256 * e;
+        vals[e] = (m < nw - 1) ? row[m + 1] : 0.0;
+    }
+    __syncthreads();
+    double mean = 0.0;
+    if (tid == 0) { for (int t = 0; t < 8; t++) mean += red[t]; mean = 2.0 * mean * P.dw; }
+    const int d_lo = (P.shared == 1) ? 0 : dz, d_hi = (P.shared == 1) ? P.nD : dz + 1;
+    for (int d = d_lo; d < d_hi; d++) {
+        const size_t u = (size_t)d * Cs.nC + c;
+        double *orow = P.F2 + (u * 6 + a) * nw;
+        for (int e = 0; e < per && e < 16; e++) {
+            const int m = tid + 256 * e;
+            if (m < nw) orow[m] = (m < nw - 1) ? 4.0 * sqrt(vals[e]) * P.dw : 0.0;
+        }
+        if (tid == 0 && P.F2mean) P.F2mean[u * 6 + a] = mean;
+    }
+}

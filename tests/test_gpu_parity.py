@@ -491,8 +491,9 @@ def test_second_order_force_vs_reference_run(solver, oracle):
     ses = solver.DeviceSession(b, solver.CaseTable(table))
     o = ses.solve(n_iter=int(G["n_iter"]), xi_start=float(G["xi_start"]), cluster_size=2)
     torch.cuda.synchronize()
-    assert np.array_equal(o["Xi"].cpu().numpy(), out["Xi"]) and np.array_equal(o["F_2nd"].cpu().numpy(), out["F_2nd"])
-    assert np.array_equal(ses.second_order_force()["F_2nd_mean"].cpu().numpy(), out["F_2nd_mean"])
+    # (the tile kernel combines partial sums with atomic adds: equal to rounding, not bit for bit)
+    assert response_err(o["Xi"].cpu().numpy()[0], out["Xi"][0]) < 1e-13 and relerr(o["F_2nd"].cpu().numpy(), out["F_2nd"]) < 1e-13
+    assert relerr(ses.second_order_force()["F_2nd_mean"].cpu().numpy(), out["F_2nd_mean"]) < 1e-13
     # precomputed force handed in through cases.F_2nd == computed inside the solve; without it the response differs
     P0 = {k: v for k, v in P.items() if not k.startswith("qtf")}
     pre = solver.solve_dynamics(solver.DesignBatch(P0), solver.CaseTable(table, F_2nd=f2["F_2nd"]), n_iter=int(G["n_iter"]),
@@ -537,7 +538,7 @@ def test_second_order_heading_interpolation_and_design_axis(solver, oracle):
     b3 = solver.DesignBatch([Pm, Pm])
     assert b3.qtf_shared == 1
     f3 = solver.second_order_force(b3, solver.CaseTable(cs))
-    assert np.array_equal(f3["F_2nd"][0], f3["F_2nd"][1]) and np.array_equal(f3["F_2nd"][0], out["F_2nd"][0])
+    assert np.array_equal(f3["F_2nd"][0], f3["F_2nd"][1]) and relerr(f3["F_2nd"][0], out["F_2nd"][0]) < 1e-13
 
 
 def test_second_order_model_api_from_files(solver, tmp_path):
