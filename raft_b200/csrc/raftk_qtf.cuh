@@ -159,7 +159,9 @@ __global__ void __launch_bounds__(QTF_THREADS, QTF_MIN_CTAS) k_qtf_force(CasesDe
 // one-bin shift and computes the mean drift.  Floating-point addition order therefore varies run to run (1e-16).
 // ------------------------------------------------------------------------------------------------
 #define QT_THREADS 512
+#ifndef QT_GROUPS
 #define QT_GROUPS 4             // CTAs per (case, table)
+#endif
 
 struct QtfTileParams {
     QtfParams q;
