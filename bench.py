@@ -365,7 +365,10 @@ def main():
                     kernel="k_rao_fused (excitation + drag linearisation + 6x6 solves, on-chip)" if kn[1] == 0 else "k_drag_solve",
                     kernel_ms=k2_ms, share_of_step=kms[2] / max(sum(kms), 1e-30),
                     algorithmic_bytes_per_solve=b_alg, peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                    other_kernels_ms=dict(depth_table=kms[0] / max(kn[0], 1), excitation=kms[1] / max(kn[1], 1)))
+                    other_kernels_ms=dict(depth_table=kms[0] / max(kn[0], 1), excitation=kms[1] / max(kn[1], 1)),
+                    note="the contract's two bounds are hbm | tensor; this kernel is neither: ~80 kflop of dependent FP64 per 104 "
+                         "algorithmic bytes, DRAM traffic below the algorithmic bytes (tables live on chip). Its binding resource is "
+                         "the FP64 pipe: see roofline_fp64 (same kernel, same timing)")
     fp64_peak = solver.fp64_peak_gflops(20000) if rank == 0 else 0.0
     f_alg = algorithmic_flops_per_solve(Ns, mean_passes)
     fp64_ach = f_alg * units_per_launch / (k2_ms * 1e-3) / 1e9
