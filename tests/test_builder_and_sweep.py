@@ -133,3 +133,40 @@ def test_turbine_channel_coefficients_vs_reference_saveTurbineOutputs():
             ref = z["ref_run_case%d_%s_PSD" % (ic, nm)][:, 0]
             assert np.abs(psd[k] - ref).max() <= 1e-13 * ref.max()
             assert abs(z["ch_avg"][k] - z["ref_run_case%d_%s_avg" % (ic, nm)][0]) <= 1e-13 * max(1.0, abs(z["ch_avg"][k]))
+
+
+def test_slender_qtf_tables_from_own_builder_match_reference_tables():
+    """potSecOrder 1: raft_b200.FOWT builds the second-order grid (w1_2nd, k1_2nd) and, through
+    packer.pack_qtf_members, the strip / waterline / Kim & Yue tables exactly as packed from the live reference."""
+    from raft_b200.model import Model
+    z = np.load(os.path.join(GOLDEN, "slender_VolturnUS-S.npz"))
+    P = {k[2:]: z[k] for k in z.files if k.startswith("P_")}
+    D = DESIGNS["test_VolturnUS-S"]
+    design = dict(D, platform=dict(D["platform"], potSecOrder=1), site=dict(D["site"], water_depth=float(P["depth"])))
+    mats = dict(M_struc=P["M0"] - z["A_hydro_morison"], C_struc=P["C0"] - z["C_moor"], C_moor=z["C_moor"])
+    f = Model(design, matrices=mats).fowtList[0]
+    assert f.potSecOrder == 1 and len(f.w1_2nd) == 23
+    Q = f.pack()
+    keys = sorted(k for k in P if k.startswith("qs_"))
+    assert len(keys) == 28
+    for k in keys:
+        a, b = np.asarray(Q[k]), np.asarray(P[k])
+        assert a.shape == b.shape, k
+        assert np.abs(a - b).max() <= 1e-15 * max(np.abs(b).max(), 1e-300), k
+    # the two MacCamy-Fuchs columns that cross the waterline carry the Kim & Yue correction
+    assert int(Q["qs_mem_mcf"].sum()) >= 1 and len(Q["qs_seg_mem"]) > 0
+    bad = dict(design, platform={k: v for k, v in design["platform"].items() if k != "min_freq2nd"})
+    with pytest.raises(Exception, match="min_freq2nd"):
+        Model(bad, matrices=mats)
+
+
+def test_get_rao_and_second_order_case_plumbing():
+    from raft_b200 import solver
+    Xi = np.arange(12, dtype=float).reshape(2, 6) + 1j
+    zeta = np.array([0.0, 2.0, 1e-7, 4.0, 0.5, 1e-6])
+    r = solver.get_rao(Xi, zeta)                                  # helpers.getRAO: zero where |zeta| <= 1e-6
+    assert np.all(r[:, [0, 2, 5]] == 0) and np.allclose(r[:, [1, 3, 4]], Xi[:, [1, 3, 4]] / zeta[[1, 3, 4]])
+    ct = solver.CaseTable(dict(Hs=[1.0], Tp=[8.0], gamma=[0.0], beta_deg=[0.0], spec=[0]), F_2nd=np.zeros([1, 1, 6, 4]),
+                          Xi_init=np.zeros([1, 1, 6, 4], dtype=complex))
+    s = ct.struct(lambda name: ct.arrays[name].ctypes.data)
+    assert s.F_2nd == ct.arrays["F_2nd"].ctypes.data and s.Xi_init == ct.arrays["Xi_init"].ctypes.data and not s.primary
