@@ -315,6 +315,12 @@ def main():
         Hs, Tp, beta = seeded_cases(5, 3)
         fixture_qtf("cfg3q_OC4semi-QTF_nw96", os.path.join(REF, "examples", "OC4semi-WAMIT_Coefs.yaml"), nw=96, max_freq=0.256,
                     solve_cases=list(zip(Hs, Tp, beta)) + [(6.0, 12.0, 30.0)], trains=[(6.0, 12.0, 30.0), (2.5, 7.0, -100.0)])
+    if not args.only or args.only in "pin_VolturnUS-S-pointInertia":
+        # fourth rigid design of the reference's test set (point inertias in the mass matrix): oracle-only fixture, the
+        # kernels see the same member tables as test_VolturnUS-S with another M0
+        fixture(name="pin_VolturnUS-S-pointInertia", yaml_path=os.path.join(td, "VolturnUS-S-pointInertia.yaml"),
+                solve_cases=[(6.0, 12.0, 30.0), (2.0, 8.0, 0.0)], pickles=os.path.join(td, "VolturnUS-S-pointInertia"))
+        DESIGNS.pop("pin_VolturnUS-S-pointInertia", None)
     if not args.only or args.only in "slender_VolturnUS-S":
         fixture_slender("slender_VolturnUS-S", os.path.join(td, "VolturnUS-S.yaml"), os.path.join(td, "VolturnUS-S_true_calcQTF_slenderBody.pkl"),
                         solve_cases=[(6.0, 12.0, 30.0), (2.0, 7.5, -75.0), (9.0, 15.0, 160.0)])

@@ -202,3 +202,24 @@ def test_slender_body_qtf_vs_reference_pickle_and_run(oracle):
         Xi, st = oracle.solve_dynamics(od, 0, Hs, Tp, 0.0, beta, nIter=int(z["n_iter"]), XiStart=float(z["xi_start"]))
         assert st[0] == z["ref_run_solve_passes"][i]
         assert response_err(Xi, z["ref_run_solve_Xi"][i]) < 1e-11
+
+
+def test_point_inertia_design_vs_reference_pickle_and_run(oracle):
+    """Fourth rigid design of the reference's test set (VolturnUS-S-pointInertia): its golden excitation /
+    linearisation pickles and reference-run responses."""
+    G, P = load_golden("pin_VolturnUS-S-pointInertia")
+    od = oracle.OracleDesign(P)
+    ref = G["ref_pickle_exc_F_hydro_iner"]
+    sc = lambda x: float(np.ravel(x)[0])
+    worst = 0.0
+    for i in range(len(ref)):
+        _, _, F, _ = oracle.calc_hydro_excitation(od, 0, sc(G["ref_pickle_exc_height"][i]), sc(G["ref_pickle_exc_period"][i]), 0.0,
+                                                  sc(G["ref_pickle_exc_heading"][i]))
+        worst = max(worst, np.abs(F - ref[i]).max() / np.abs(ref).max())
+    assert worst < 1e-13
+    _, _, _, u = oracle.calc_hydro_excitation(od, 1, 2.0, 10.0, 0.0, 0.0)
+    _, B, F = oracle.calc_hydro_linearization(od, u, G["ref_run_lin_Xi"])
+    assert relerr(B, G["ref_pickle_lin_B_hydro_drag"]) < 1e-13 and relerr(F, G["ref_pickle_lin_F_hydro_drag"]) < 1e-13
+    for i, (Hs, Tp, beta) in enumerate(G["ref_run_solve_cases"]):
+        Xi, st = oracle.solve_dynamics(od, 0, Hs, Tp, 0.0, beta, nIter=int(G["n_iter"]), XiStart=float(G["xi_start"]))
+        assert st[0] == G["ref_run_solve_passes"][i] and response_err(Xi, G["ref_run_solve_Xi"][i]) < 1e-12
