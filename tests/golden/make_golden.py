@@ -321,6 +321,10 @@ def main():
         fixture(name="pin_VolturnUS-S-pointInertia", yaml_path=os.path.join(td, "VolturnUS-S-pointInertia.yaml"),
                 solve_cases=[(6.0, 12.0, 30.0), (2.0, 8.0, 0.0)], pickles=os.path.join(td, "VolturnUS-S-pointInertia"))
         DESIGNS.pop("pin_VolturnUS-S-pointInertia", None)
+    if not args.only or args.only in "pinq_VolturnUS-S-pointInertia":
+        # the reference's second slender-body QTF golden (oracle-only fixture: tables + its pickle, no solves)
+        fixture_slender("pinq_VolturnUS-S-pointInertia", os.path.join(td, "VolturnUS-S-pointInertia.yaml"),
+                        os.path.join(td, "VolturnUS-S-pointInertia_true_calcQTF_slenderBody.pkl"), solve_cases=[(6.0, 12.0, 30.0)])
     if not args.only or args.only in "slender_VolturnUS-S":
         fixture_slender("slender_VolturnUS-S", os.path.join(td, "VolturnUS-S.yaml"), os.path.join(td, "VolturnUS-S_true_calcQTF_slenderBody.pkl"),
                         solve_cases=[(6.0, 12.0, 30.0), (2.0, 7.5, -75.0), (9.0, 15.0, 160.0)])

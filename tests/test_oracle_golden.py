@@ -223,3 +223,18 @@ def test_point_inertia_design_vs_reference_pickle_and_run(oracle):
     for i, (Hs, Tp, beta) in enumerate(G["ref_run_solve_cases"]):
         Xi, st = oracle.solve_dynamics(od, 0, Hs, Tp, 0.0, beta, nIter=int(G["n_iter"]), XiStart=float(G["xi_start"]))
         assert st[0] == G["ref_run_solve_passes"][i] and response_err(Xi, G["ref_run_solve_Xi"][i]) < 1e-12
+
+
+def test_slender_body_qtf_second_reference_pickle(oracle):
+    """The reference's other slender-body golden (VolturnUS-S-pointInertia_true_calcQTF_slenderBody.pkl) + one solve."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "pinq_VolturnUS-S-pointInertia.npz"))
+    P = {k[2:]: z[k] for k in z.files if k.startswith("P_")}
+    od = oracle.OracleDesign(P)
+    q = oracle.qtf_slender(od, z["ref_pickle_case"][2] * 0.017453292519943295, np.zeros([6, len(P["qs_w"])], dtype=complex))
+    for a in range(6):
+        assert relerr(q[..., a], z["ref_pickle_qtf"][:, :, 0, a]) < 1e-13, a
+    Hs, Tp, beta = z["ref_run_solve_cases"][0]
+    Xi, st = oracle.solve_dynamics(od, 0, Hs, Tp, 0.0, beta, nIter=int(z["n_iter"]), XiStart=float(z["xi_start"]))
+    assert st[0] == z["ref_run_solve_passes"][0] and response_err(Xi, z["ref_run_solve_Xi"][0]) < 1e-11
