@@ -232,6 +232,47 @@ def hydro_force_2nd(od, beta, S0):
     return fm, f
 
 
+class RoGeneral(C.Structure):
+    _fields_ = [("d", C.c_void_p), ("nDOF", C.c_int), ("Tn", c_double_p), ("rr", c_double_p)]
+
+
+class GeneralDesign:
+    """Generalised-DOF design (raft_b200.packer.pack_general_dofs): node tables + per-node T blocks."""
+
+    def __init__(self, P):
+        self.od = OracleDesign(P)
+        self.n = int(P["gen_nDOF"])
+        self.Tn = np.ascontiguousarray(P["gen_Tn"], dtype=np.float64)
+        self.rr = np.ascontiguousarray(P["gen_rr"], dtype=np.float64)
+        self.c = RoGeneral(C.addressof(self.od.c), self.n, _dp(self.Tn), _dp(self.rr))
+
+
+def general_excitation(gd, spec, Hs, Tp, gamma, beta_deg):
+    """FOWT.calcHydroExcitation with nDOF reduced degrees of freedom -> zeta [nw], F_hydro_iner [nDOF,nw], u [Ns,3,nw]."""
+    nw, Ns = gd.od.nw, gd.od.Ns
+    zeta = np.zeros(nw)
+    F = np.zeros([gd.n, nw], dtype=np.complex128)
+    u = np.zeros([max(Ns, 1), 3, nw], dtype=np.complex128)
+    rc = lib().ro_general_excitation(C.byref(gd.c), C.c_int(spec), C.c_double(float(Hs)), C.c_double(float(Tp)), C.c_double(float(gamma)),
+                                     C.c_double(float(beta_deg)), _dp(zeta), F.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise ValueError("Wave spectrum input not recognized.")
+    return zeta, F, u
+
+
+def general_linearization(gd, u, Xi):
+    """FOWT.calcHydroLinearization(Xi [nDOF,nw]) + calcDragExcitation(0) -> B_hydro_drag [nDOF,nDOF], F_hydro_drag [nDOF,nw]."""
+    nw, Ns = gd.od.nw, gd.od.Ns
+    Xi = np.ascontiguousarray(Xi, dtype=np.complex128)
+    u = np.ascontiguousarray(u, dtype=np.complex128)
+    Bmat = np.zeros([max(Ns, 1), 3, 3])
+    B = np.zeros([gd.n, gd.n])
+    F = np.zeros([gd.n, nw], dtype=np.complex128)
+    lib().ro_general_linearization(C.byref(gd.c), u.ctypes.data_as(C.c_void_p), Xi.ctypes.data_as(C.c_void_p), _dp(Bmat), _dp(B),
+                                   F.ctypes.data_as(C.c_void_p))
+    return B, F
+
+
 def qtf_slender(od, beta, Xi):
     """FOWT.calcQTF_slenderBody: heading ``beta`` [rad], motion RAOs ``Xi`` [6, nw2] on the second-order grid
     -> qtf [nw2, nw2, 6] complex, Hermitian-filled (fowt.qtf[:, :, 0, :])."""

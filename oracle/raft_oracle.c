@@ -1179,3 +1179,133 @@ int ro_system_response(int n, int nw, const cplx *Z_sys, const cplx *F, cplx *Xi
     }
     return bad;
 }
+
+/* ======================================================================================================
+ * Generalised degrees of freedom (flexible members, FOWT.nDOF > 6): FOWT.calcHydroExcitation / calcHydroLinearization
+ * with the transformation matrix fowt.T (raft_fowt.py:1854-1857, :1886-1888, :1913-1929; raft_member.py:1960-1992,
+ * 2040-2052, 2119-2126).  Every strip node carries the 6 x nDOF block of T of its structural node (Tn) and its offset
+ * from that node (rr; zero for the nodes of a flexible member): node motion = Tn Xi, node load -> Tn^T [f ; rr x f].
+ * GROUNDWORK for the next row of SURVEY.md 8(f): the CUDA path is rigid 6-DOF only; this pins the checker first.
+ * ====================================================================================================== */
+typedef struct {
+    const ro_design *d;          /* node tables (node_r, node_mem, Imat, areas, coefficients, member frames, grid)  */
+    int nDOF;
+    const double *Tn;            /* [Ns][6][nDOF]                                                                  */
+    const double *rr;            /* [Ns][3]                                                                        */
+} ro_general;
+
+/* zeta [nw], F_iner [nDOF][nw], u [Ns][3][nw] */
+int ro_general_excitation(const ro_general *g, int spec, double Hs, double Tp, double gamma, double beta_deg,
+                          double *zeta, cplx *F_iner, cplx *u_out)
+{
+    const ro_design *d = g->d;
+    int nw = d->nw, Ns = d->n_nodes, n = g->nDOF;
+    double *S = malloc(sizeof(double) * nw);
+    int rc = ro_sea_state(d->w, nw, d->dw, spec, Hs, Tp, gamma, S, zeta);
+    free(S);
+    if (rc) return rc;
+    double beta = beta_deg * (M_PI / 180.0);
+    cplx *ud = malloc(sizeof(cplx) * 3 * nw), *pD = malloc(sizeof(cplx) * nw);
+    for (size_t i = 0; i < (size_t)n * nw; i++) F_iner[i] = 0;
+    for (int il = 0; il < Ns; il++) {
+        const double *r = d->node_r + 3 * il, *q = d->mem_q + 3 * d->node_mem[il];
+        const double *Tn = g->Tn + (size_t)il * 6 * n, *rr = g->rr + 3 * il;
+        cplx *u = u_out + (size_t)il * 3 * nw;
+        ro_wave_kin(zeta, beta, d->w, d->k, d->depth, r, nw, 1025.0, 9.81, u, ud, pD);
+        const double *Im = d->node_Imat + 9 * il;
+        for (int i = 0; i < nw; i++) {
+            cplx f[3], f6[6];
+            for (int a = 0; a < 3; a++) {
+                if (d->node_Imat_w) {
+                    const cplx *Iw = d->node_Imat_w + (size_t)il * 9 * nw;
+                    f[a] = Iw[(3 * a) * nw + i] * ud[i] + Iw[(3 * a + 1) * nw + i] * ud[nw + i]
+                         + Iw[(3 * a + 2) * nw + i] * ud[2 * nw + i] + pD[i] * d->node_a_i[il] * q[a];
+                } else
+                f[a] = Im[3 * a] * ud[i] + Im[3 * a + 1] * ud[nw + i] + Im[3 * a + 2] * ud[2 * nw + i]
+                     + pD[i] * d->node_a_i[il] * q[a];
+            }
+            translate_force(f, rr, f6);
+            for (int c = 0; c < n; c++) {                              /* T^T (fowt:1888) */
+                cplx s = 0;
+                for (int b = 0; b < 6; b++) s += Tn[b * n + c] * f6[b];
+                F_iner[(size_t)c * nw + i] += s;
+            }
+        }
+    }
+    free(ud); free(pD);
+    return 0;
+}
+
+/* Xi [nDOF][nw] in; Bmat [Ns][3][3], B_drag [nDOF][nDOF], F_drag [nDOF][nw] out */
+void ro_general_linearization(const ro_general *g, const cplx *u_all, const cplx *Xi, double *Bmat_all, double *B_drag, cplx *F_drag)
+{
+    const ro_design *d = g->d;
+    int nw = d->nw, Ns = d->n_nodes, n = g->nDOF;
+    cplx *Xin = malloc(sizeof(cplx) * 6 * nw), *vrel = malloc(sizeof(cplx) * 3 * nw);
+    for (size_t i = 0; i < (size_t)n * n; i++) B_drag[i] = 0;
+    for (size_t i = 0; i < (size_t)n * nw; i++) F_drag[i] = 0;
+    for (int il = 0; il < Ns; il++) {
+        int m = d->node_mem[il];
+        const double *q = d->mem_q + 3 * m, *p1 = d->mem_p1 + 3 * m, *p2 = d->mem_p2 + 3 * m;
+        const double *Tn = g->Tn + (size_t)il * 6 * n, *rr = g->rr + 3 * il;
+        const cplx *u = u_all + (size_t)il * 3 * nw;
+        int circ = d->mem_circ[m];
+        for (int i = 0; i < nw; i++)                                   /* Xi_nodes = node.T @ Xi (fowt:1921) */
+            for (int a = 0; a < 6; a++) {
+                cplx s = 0;
+                for (int b = 0; b < n; b++) s += Tn[a * n + b] * Xi[(size_t)b * nw + i];
+                Xin[a * nw + i] = s;
+            }
+        double sq = 0, sp = 0, sp1 = 0, sp2 = 0;
+        for (int i = 0; i < nw; i++) {
+            const cplx th0 = Xin[3 * nw + i], th1 = Xin[4 * nw + i], th2 = Xin[5 * nw + i];
+            cplx dr[3], v[3];
+            dr[0] = Xin[0 * nw + i] + (-th2 * rr[1] + th1 * rr[2]);
+            dr[1] = Xin[1 * nw + i] + ( th2 * rr[0] - th0 * rr[2]);
+            dr[2] = Xin[2 * nw + i] + (-th1 * rr[0] + th0 * rr[1]);
+            for (int a = 0; a < 3; a++) { v[a] = I * d->w[i] * dr[a]; vrel[a * nw + i] = u[a * nw + i] - v[a]; }
+            cplx aq = 0, a1 = 0, a2 = 0;
+            for (int a = 0; a < 3; a++) { aq += vrel[a * nw + i] * q[a]; a1 += vrel[a * nw + i] * p1[a]; a2 += vrel[a * nw + i] * p2[a]; }
+            for (int a = 0; a < 3; a++) {
+                cplx vq = aq * q[a], vp = vrel[a * nw + i] - vq, v1 = a1 * p1[a], v2 = a2 * p2[a];
+                double t;
+                t = cabs(vq); sq += t * t;  t = cabs(vp); sp += t * t;
+                t = cabs(v1); sp1 += t * t; t = cabs(v2); sp2 += t * t;
+            }
+        }
+        double vRMS_q = sqrt(0.5 * sq), vRMS_p1, vRMS_p2;
+        if (circ) { vRMS_p1 = sqrt(0.5 * sp); vRMS_p2 = vRMS_p1; }
+        else { vRMS_p1 = sqrt(0.5 * sp1); vRMS_p2 = sqrt(0.5 * sp2); }
+        double c = sqrt(8.0 / M_PI), rho = d->rho;
+        double Bq  = c * vRMS_q  * 0.5 * rho * d->a_q[il]  * d->Cd_q[il];
+        double Bp1 = c * vRMS_p1 * 0.5 * rho * d->a_p1[il] * d->Cd_p1[il];
+        double Bp2 = c * vRMS_p2 * 0.5 * rho * d->a_p2[il] * d->Cd_p2[il];
+        double Be  = c * vRMS_q  * 0.5 * rho * d->a_End[il] * d->Cd_End[il];
+        double Bmat[3][3], B6[6][6];
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+            Bmat[a][b] = (Bq * (q[a] * q[b]) + Bp1 * (p1[a] * p1[b]) + Bp2 * (p2[a] * p2[b])) + Be * (q[a] * q[b]);
+            Bmat_all[9 * il + 3 * a + b] = Bmat[a][b];
+        }
+        translate_matrix(Bmat, rr, B6);
+        /* B_drag += Tn^T B6 Tn  (fowt:1927) */
+        double *TB = malloc(sizeof(double) * 6 * n);
+        for (int a = 0; a < 6; a++) for (int cc = 0; cc < n; cc++) {
+            double s = 0; for (int l = 0; l < 6; l++) s += B6[a][l] * Tn[l * n + cc]; TB[a * n + cc] = s;
+        }
+        for (int r_ = 0; r_ < n; r_++) for (int cc = 0; cc < n; cc++) {
+            double s = 0; for (int l = 0; l < 6; l++) s += Tn[l * n + r_] * TB[l * n + cc]; B_drag[(size_t)r_ * n + cc] += s;
+        }
+        free(TB);
+        for (int i = 0; i < nw; i++) {
+            cplx f[3], f6[6];
+            for (int a = 0; a < 3; a++) f[a] = Bmat[a][0] * u[i] + Bmat[a][1] * u[nw + i] + Bmat[a][2] * u[2 * nw + i];
+            translate_force(f, rr, f6);
+            for (int cc = 0; cc < n; cc++) {
+                cplx s = 0;
+                for (int b = 0; b < 6; b++) s += Tn[b * n + cc] * f6[b];
+                F_drag[(size_t)cc * nw + i] += s;
+            }
+        }
+    }
+    free(Xin); free(vrel);
+}

@@ -32,7 +32,7 @@ def _uses_mcf(mem):
     return bool(getattr(mem, "MCF", False)) and not bool(getattr(mem, "potMod", False))
 
 
-def pack_members(fowt, rho=None, g=None):
+def pack_members(fowt, rho=None, g=None, allow_flexible=False):
     """Flatten the submerged strip nodes of ``fowt.memberList`` into node + member tables.
 
     Only nodes with ``r_z < 0`` are kept (raft_member.py:1935, 1979, 2058, 2135); members with no
@@ -50,7 +50,8 @@ def pack_members(fowt, rho=None, g=None):
     cols = {k: [] for k in ("r", "mem", "ls", "cd_q", "cd_p1", "cd_p2", "in_q", "in_p1", "in_p2", "pa",
                             "Imat", "a_i", "a_q", "a_p1", "a_p2", "a_End", "Cd_q", "Cd_p1", "Cd_p2", "Cd_End")}
     for mem in fowt.memberList:
-        _member_is_supported(mem)
+        if not allow_flexible:
+            _member_is_supported(mem)
         sub = np.where(mem.r[:, 2] < 0)[0]
         if len(sub) == 0:
             continue
@@ -207,6 +208,29 @@ def pack_fowt(fowt, w=None, k=None):
     out.update(w=w, k=k, depth=np.float64(fowt.depth), dw=np.float64(w[1] - w[0]),
                x_ref=np.float64(getattr(fowt, "x_ref", 0.0)), y_ref=np.float64(getattr(fowt, "y_ref", 0.0)))
     out.update(pack_qtf(fowt))
+    return out
+
+
+def pack_general_dofs(fowt):
+    """Node tables + the per-strip-node blocks of ``fowt.T`` for FOWTs with generalised degrees of freedom (flexible
+    members, nDOF > 6; raft_fowt.py:1854-1857, 1913-1929).  GROUNDWORK: consumed by the oracle only
+    (``oracle.GeneralDesign``) -- the CUDA path is rigid 6-DOF and ``pack_fowt`` keeps rejecting flexible members.
+    Adds ``gen_nDOF``, ``gen_Tn`` [Ns,6,nDOF] (T rows of each strip node's structural node) and ``gen_rr`` [Ns,3]
+    (offset from that node; zero on flexible members, whose strip nodes are their structural nodes)."""
+    out = pack_members(fowt, allow_flexible=True)
+    T = np.asarray(fowt.T, dtype=float)
+    Tn, rr = [], []
+    for mem in fowt.memberList:
+        sub = np.where(mem.r[:, 2] < 0)[0]
+        for il in sub:
+            node = mem.nodeList[0] if getattr(mem, "type", "rigid") == "rigid" else mem.nodeList[il]
+            Tn.append(T[node.id * 6:(node.id + 1) * 6, :])
+            rr.append(np.asarray(mem.r[il], dtype=float) - np.asarray(node.r[:3], dtype=float))
+    ns = len(out["node_ls"])
+    out.update(gen_nDOF=np.int32(T.shape[1]), gen_Tn=np.array(Tn, dtype=float).reshape(ns, 6, T.shape[1]),
+               gen_rr=np.array(rr, dtype=float).reshape(ns, 3), w=np.array(fowt.w, dtype=float), k=np.array(fowt.k, dtype=float),
+               depth=np.float64(fowt.depth), dw=np.float64(fowt.w[1] - fowt.w[0]),
+               M0=np.zeros([6, 6]), B0=np.zeros([6, 6]), C0=np.zeros([6, 6]))
     return out
 
 

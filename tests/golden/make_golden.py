@@ -286,6 +286,41 @@ def fixture_slender(name, yaml_path, pickle_path, solve_cases):
                                                              os.path.getsize(path) / 1024))
 
 
+def fixture_flexible(name, yaml_path, pickles):
+    """Generalised degrees of freedom (flexible members, nDOF = 150): the reference's golden excitation / linearisation
+    pickles of VolturnUS-S-flexible with the tables packed by packer.pack_general_dofs (oracle groundwork for the next row).
+    The design keeps its turbine (the tower is one of the flexible members); CCBlade is stubbed, mooring stripped."""
+    import contextlib
+    import copy
+    import io
+    t0 = time.time()
+    raft = rh.load_reference()
+    design = rh.load_design(yaml_path, strip=False)
+    design.pop("mooring", None)
+    design["platform"]["potSecOrder"] = 0
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = raft.Model(copy.deepcopy(design))
+        fowt = model.fowtList[0]
+        fowt.setPosition(np.zeros(fowt.nDOF))
+        fowt.calcStatics()
+        fowt.calcTurbineConstants(rh.make_case(), ptfm_pitch=0)
+        fowt.calcHydroConstants()
+    P = packer.pack_general_dofs(fowt)
+    out = {"P_" + k: np.asarray(v) for k, v in P.items()}
+    with open(pickles + "_true_hydroExcitation.pkl", "rb") as f:
+        tv = pickle.load(f)
+    out["ref_pickle_exc_heading"] = np.array([t["case"]["wave_heading"] for t in tv], dtype=float)
+    out["ref_pickle_exc_period"] = np.array([t["case"]["wave_period"] for t in tv], dtype=float)
+    out["ref_pickle_exc_height"] = np.array([t["case"]["wave_height"] for t in tv], dtype=float)
+    out["ref_pickle_exc_F_hydro_iner"] = np.array([t["F_hydro_iner"][0] for t in tv])
+    with open(pickles + "_true_hydroLinearization.pkl", "rb") as f:
+        tv = pickle.load(f)
+    out["ref_pickle_lin_B_hydro_drag"], out["ref_pickle_lin_F_hydro_drag"] = np.array(tv["B_hydro_drag"]), np.array(tv["F_hydro_drag"])
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-28s nDOF=%3d Ns=%3d  %.1f s  %.0f KB" % (name, int(P["gen_nDOF"]), len(P["node_ls"]), time.time() - t0, os.path.getsize(path) / 1024))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -325,6 +360,8 @@ def main():
         # the reference's second slender-body QTF golden (oracle-only fixture: tables + its pickle, no solves)
         fixture_slender("pinq_VolturnUS-S-pointInertia", os.path.join(td, "VolturnUS-S-pointInertia.yaml"),
                         os.path.join(td, "VolturnUS-S-pointInertia_true_calcQTF_slenderBody.pkl"), solve_cases=[(6.0, 12.0, 30.0)])
+    if not args.only or args.only in "flex_VolturnUS-S-flexible":
+        fixture_flexible("flex_VolturnUS-S-flexible", os.path.join(td, "VolturnUS-S-flexible.yaml"), os.path.join(td, "VolturnUS-S-flexible"))
     if not args.only or args.only in "slender_VolturnUS-S":
         fixture_slender("slender_VolturnUS-S", os.path.join(td, "VolturnUS-S.yaml"), os.path.join(td, "VolturnUS-S_true_calcQTF_slenderBody.pkl"),
                         solve_cases=[(6.0, 12.0, 30.0), (2.0, 7.5, -75.0), (9.0, 15.0, 160.0)])

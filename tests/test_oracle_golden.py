@@ -238,3 +238,26 @@ def test_slender_body_qtf_second_reference_pickle(oracle):
     Hs, Tp, beta = z["ref_run_solve_cases"][0]
     Xi, st = oracle.solve_dynamics(od, 0, Hs, Tp, 0.0, beta, nIter=int(z["n_iter"]), XiStart=float(z["xi_start"]))
     assert st[0] == z["ref_run_solve_passes"][0] and response_err(Xi, z["ref_run_solve_Xi"][0]) < 1e-11
+
+
+def test_generalised_dofs_vs_reference_flexible_pickles(oracle):
+    """Groundwork for the next row (flexible members, nDOF = 150): the oracle's generalised calcHydroExcitation /
+    calcHydroLinearization with fowt.T against the reference's VolturnUS-S-flexible golden pickles."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "flex_VolturnUS-S-flexible.npz"))
+    P = {k[2:]: z[k] for k in z.files if k.startswith("P_")}
+    gd = oracle.GeneralDesign(P)
+    assert gd.n == 150
+    ref = z["ref_pickle_exc_F_hydro_iner"]
+    worst = 0.0
+    for i in range(len(ref)):
+        _, F, _ = oracle.general_excitation(gd, 0, float(z["ref_pickle_exc_height"][i]), float(z["ref_pickle_exc_period"][i]), 0.0,
+                                            float(z["ref_pickle_exc_heading"][i]))
+        worst = max(worst, np.abs(F - ref[i]).max() / np.abs(ref).max())
+    assert worst < 1e-13
+    _, _, u = oracle.general_excitation(gd, 1, 2.0, 10.0, 0.0, 0.0)                 # the reference's own recipe (test_fowt.py:150-175)
+    nw = len(P["w"])
+    Xi = 0.1 * np.exp(1j * np.linspace(0, 2 * np.pi, nw * gd.n).reshape(gd.n, nw))
+    B, F = oracle.general_linearization(gd, u, Xi)
+    assert relerr(B, z["ref_pickle_lin_B_hydro_drag"]) < 1e-13 and relerr(F, z["ref_pickle_lin_F_hydro_drag"]) < 1e-13
