@@ -252,8 +252,9 @@ def test_generalised_dofs_vs_reference_flexible_pickles(oracle):
     ref = z["ref_pickle_exc_F_hydro_iner"]
     worst = 0.0
     for i in range(len(ref)):
-        _, F, _ = oracle.general_excitation(gd, 0, float(z["ref_pickle_exc_height"][i]), float(z["ref_pickle_exc_period"][i]), 0.0,
-                                            float(z["ref_pickle_exc_heading"][i]))
+        sc = lambda x: float(np.ravel(x)[0])
+        _, F, _ = oracle.general_excitation(gd, 0, sc(z["ref_pickle_exc_height"][i]), sc(z["ref_pickle_exc_period"][i]), 0.0,
+                                            sc(z["ref_pickle_exc_heading"][i]))
         worst = max(worst, np.abs(F - ref[i]).max() / np.abs(ref).max())
     assert worst < 1e-13
     _, _, u = oracle.general_excitation(gd, 1, 2.0, 10.0, 0.0, 0.0)                 # the reference's own recipe (test_fowt.py:150-175)
