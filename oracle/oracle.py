@@ -273,6 +273,20 @@ def general_linearization(gd, u, Xi):
     return B, F
 
 
+def general_solve_dynamics(gd, M, B, Cm, spec, Hs, Tp, gamma, beta_deg, nIter=10, tol=0.01, XiStart=0.0):
+    """Model.solveDynamics with nDOF reduced degrees of freedom -> Xi [nDOF,nw], status (passes, converged, nan)."""
+    n, nw = gd.n, gd.od.nw
+    M, B, Cm = (np.ascontiguousarray(x, dtype=np.float64).reshape(n, n) for x in (M, B, Cm))
+    Xi = np.zeros([n, nw], dtype=np.complex128)
+    st = np.zeros(3, dtype=np.int32)
+    rc = lib().ro_general_solve_dynamics(C.byref(gd.c), _dp(M), _dp(B), _dp(Cm), C.c_int(spec), C.c_double(float(Hs)), C.c_double(float(Tp)),
+                                         C.c_double(float(gamma)), C.c_double(float(beta_deg)), C.c_int(nIter), C.c_double(tol),
+                                         C.c_double(XiStart), Xi.ctypes.data_as(C.c_void_p), _ip(st))
+    if rc:
+        raise ValueError("Wave spectrum input not recognized.")
+    return Xi, st
+
+
 def qtf_slender(od, beta, Xi):
     """FOWT.calcQTF_slenderBody: heading ``beta`` [rad], motion RAOs ``Xi`` [6, nw2] on the second-order grid
     -> qtf [nw2, nw2, 6] complex, Hermitian-filled (fowt.qtf[:, :, 0, :])."""

@@ -1309,3 +1309,70 @@ void ro_general_linearization(const ro_general *g, const cplx *u_all, const cplx
     }
     free(Xin); free(vrel);
 }
+
+/* Model.solveDynamics for one FOWT with nDOF reduced degrees of freedom and one single-train case
+ * (raft_model.py:994-1156, 1189-1216): M, B, C [nDOF][nDOF] constant matrices (M_struc + A_hydro_morison + ..., B_struc + ...,
+ * C_struc + C_hydro + C_moor + C_elast).  Xi_out [nDOF][nw]; status = {passes, converged, nan}. */
+int ro_general_solve_dynamics(const ro_general *g, const double *M, const double *B, const double *Cm, int spec, double Hs, double Tp,
+                              double gamma, double beta_deg, int nIter, double tol, double XiStart, cplx *Xi_out, int *status)
+{
+    const ro_design *d = g->d;
+    int nw = d->nw, Ns = d->n_nodes > 0 ? d->n_nodes : 1, n = g->nDOF;
+    double *zeta = malloc(sizeof(double) * nw), *Bmat = malloc(sizeof(double) * 9 * Ns), *B_drag = malloc(sizeof(double) * n * n);
+    cplx *F_iner = malloc(sizeof(cplx) * n * nw), *u = malloc(sizeof(cplx) * (size_t)Ns * 3 * nw);
+    cplx *XiLast = malloc(sizeof(cplx) * n * nw), *Xi = malloc(sizeof(cplx) * n * nw), *F_drag = malloc(sizeof(cplx) * n * nw);
+    cplx *Z = malloc(sizeof(cplx) * (size_t)n * n * nw);
+    status[0] = status[1] = status[2] = 0;
+    int rc = ro_general_excitation(g, spec, Hs, Tp, gamma, beta_deg, zeta, F_iner, u);
+    if (rc) goto done;
+    for (int i = 0; i < n * nw; i++) XiLast[i] = XiStart;
+    int passes = 0, conv = 0;
+    for (int iiter = 0; iiter < nIter + 1; iiter++) {
+        ro_general_linearization(g, u, XiLast, Bmat, B_drag, F_drag);
+        passes++;
+        int nan = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(|:nan)
+#endif
+        for (int ii = 0; ii < nw; ii++) {
+            cplx *A = malloc(sizeof(cplx) * n * n), *b = malloc(sizeof(cplx) * n);
+            double wv = d->w[ii];
+            for (int a = 0; a < n; a++) {
+                for (int c = 0; c < n; c++)
+                    A[a * n + c] = -wv * wv * M[a * n + c] + I * wv * (B[a * n + c] + B_drag[a * n + c]) + Cm[a * n + c];
+                b[a] = F_iner[a * nw + ii] + F_drag[a * nw + ii];
+            }
+            memcpy(Z + (size_t)ii * n * n, A, sizeof(cplx) * n * n);
+            ro_zgesv(n, A, b);
+            for (int a = 0; a < n; a++) { Xi[a * nw + ii] = b[a]; if (isnan(creal(b[a])) || isnan(cimag(b[a]))) nan = 1; }
+            free(A); free(b);
+        }
+        if (nan) { status[2] = 1; break; }
+        int all = 1;
+        for (int i = 0; i < n * nw; i++) {
+            double tc = cabs(Xi[i] - XiLast[i]) / (cabs(Xi[i]) + tol);
+            if (!(tc < tol)) { all = 0; break; }
+        }
+        if (all) { conv = 1; break; }
+        for (int i = 0; i < n * nw; i++) XiLast[i] = 0.2 * XiLast[i] + 0.8 * Xi[i];
+    }
+    status[0] = passes; status[1] = conv;
+    /* system response through the explicit inverse of the last Z (raft_model.py:1189-1216) */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int ii = 0; ii < nw; ii++) {
+        cplx *A = malloc(sizeof(cplx) * n * n), *Ai = malloc(sizeof(cplx) * n * n);
+        memcpy(A, Z + (size_t)ii * n * n, sizeof(cplx) * n * n);
+        if (ro_zinv(n, A, Ai)) { for (int a = 0; a < n; a++) Xi_out[a * nw + ii] = NAN; }
+        else for (int a = 0; a < n; a++) {
+            cplx s = 0;
+            for (int c = 0; c < n; c++) s += Ai[a * n + c] * (F_iner[c * nw + ii] + F_drag[c * nw + ii]);
+            Xi_out[a * nw + ii] = s;
+        }
+        free(A); free(Ai);
+    }
+done:
+    free(zeta); free(Bmat); free(B_drag); free(F_iner); free(u); free(XiLast); free(Xi); free(F_drag); free(Z);
+    return rc;
+}

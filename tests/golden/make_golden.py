@@ -316,6 +316,25 @@ def fixture_flexible(name, yaml_path, pickles):
     with open(pickles + "_true_hydroLinearization.pkl", "rb") as f:
         tv = pickle.load(f)
     out["ref_pickle_lin_B_hydro_drag"], out["ref_pickle_lin_F_hydro_drag"] = np.array(tv["B_hydro_drag"]), np.array(tv["F_hydro_drag"])
+    # full Model.solveDynamics of the 150-DOF system (synthetic mooring stiffness on the rigid-body DOFs 0..5)
+    n = fowt.nDOF
+    Cmoor = np.zeros([n, n])
+    Cmoor[:6, :6] = rh.C_MOOR_DEFAULT
+    fowt.C_moor = Cmoor
+    out["gen_M"] = np.sum(fowt.A_aero, axis=3)[:, :, 0] + fowt.M_struc + fowt.A_hydro_morison      # raft_model.py:1045-1047 (turbine off: no w dependence)
+    out["gen_B"] = np.sum(fowt.B_aero, axis=3)[:, :, 0] + fowt.B_struc + np.sum(fowt.B_gyro, axis=2)
+    out["gen_C"] = fowt.C_struc + fowt.C_hydro + Cmoor + fowt.C_elast
+    assert np.abs(fowt.A_aero).max() == 0 and np.abs(fowt.A_BEM).max() == 0
+    cnt, orig = count_passes(fowt)
+    cases = [(6.0, 12.0, 30.0), (2.0, 8.0, -60.0)]
+    Xi, passes = [], []
+    for (Hs, Tp, beta) in cases:
+        cnt[0] = 0
+        x = rh.solve_dynamics(model, rh.make_case(Hs, Tp, beta))
+        Xi.append(np.array(x[0])), passes.append(cnt[0])
+    fowt.calcHydroLinearization = orig
+    out["n_iter"], out["xi_start"] = np.int32(int(model.nIter)), np.float64(model.XiStart)
+    out["ref_run_solve_cases"], out["ref_run_solve_Xi"], out["ref_run_solve_passes"] = np.array(cases), np.array(Xi), np.array(passes, dtype=np.int32)
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **out)
     print("%-28s nDOF=%3d Ns=%3d  %.1f s  %.0f KB" % (name, int(P["gen_nDOF"]), len(P["node_ls"]), time.time() - t0, os.path.getsize(path) / 1024))
