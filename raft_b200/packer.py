@@ -213,8 +213,8 @@ def pack_fowt(fowt, w=None, k=None):
 
 def pack_general_dofs(fowt):
     """Node tables + the per-strip-node blocks of ``fowt.T`` for FOWTs with generalised degrees of freedom (flexible
-    members, nDOF > 6; raft_fowt.py:1854-1857, 1913-1929).  GROUNDWORK: consumed by the oracle only
-    (``oracle.GeneralDesign``) -- the CUDA path is rigid 6-DOF and ``pack_fowt`` keeps rejecting flexible members.
+    members, nDOF > 6; raft_fowt.py:1854-1857, 1913-1929).  GROUNDWORK for the next row: so far only the CPU checker
+    of the tests consumes these tables -- the CUDA path is rigid 6-DOF and ``pack_fowt`` keeps rejecting flexible members.
     Adds ``gen_nDOF``, ``gen_Tn`` [Ns,6,nDOF] (T rows of each strip node's structural node) and ``gen_rr`` [Ns,3]
     (offset from that node; zero on flexible members, whose strip nodes are their structural nodes)."""
     out = pack_members(fowt, allow_flexible=True)
