@@ -265,6 +265,36 @@ int raftk_qtf_slender_dev(const raftk_slender *s, int32_t n_cases, const double 
                           void *workspace, size_t workspace_bytes, void *stream);
 int raftk_qtf_slender_host(const raftk_slender *s, int32_t n_cases, const double *beta_rad, const double *Xi_rao, double *qtf);
 
+/*
+ * STAGED -- compiled, restated from the pinned checker, NOT YET VALIDATED ON HARDWARE (next row of SURVEY.md 8f).
+ * Model.solveDynamics for ONE FOWT with generalised degrees of freedom (flexible members, n_dof > 6; raft_fowt.py:1854-1857,
+ * 1886-1888, 1913-1929; raft_model.py:1052-1142) and n_cases single-train cases.  Every submerged strip node carries the
+ * 6 x n_dof block of fowt.T of its structural node (Tn) and its offset from that node (rr; zero on flexible members):
+ * node motion = Tn Xi, node load -> Tn^T [f ; rr x f].  M, B, C: the constant system matrices of raft_model.py:1045-1047.
+ * Xi complex [n_cases,n_dof,nw]; status [n_cases,4] = passes, converged, flags, 0.
+ */
+typedef struct raftk_general {
+    int32_t n_dof, nw, n_nodes, _pad0;
+    double depth, rho, dw;
+    const double *w, *k;            /* [nw]                                                          */
+    const double *node_r;           /* [n_nodes,3]                                                   */
+    const double *node_frame;       /* [n_nodes,9] q, p1, p2 of the node's member                    */
+    const int32_t *node_circ;       /* [n_nodes]                                                     */
+    const double *node_Imat;        /* [n_nodes,9]                                                   */
+    const double *node_Imat_w;      /* complex [n_nodes,9,nw] MacCamy-Fuchs Imat_MCF, or NULL        */
+    const double *node_a_i;         /* [n_nodes] signed end area                                     */
+    const double *node_cd;          /* [n_nodes,4] a_q Cd_q, a_p1 Cd_p1, a_p2 Cd_p2, a_End Cd_End    */
+    const double *Tn;               /* [n_nodes,6,n_dof]                                             */
+    const double *rr;               /* [n_nodes,3]                                                   */
+    const double *M, *B, *C;        /* [n_dof,n_dof]                                                 */
+} raftk_general;
+
+size_t raftk_general_workspace_bytes(const raftk_general *g, int32_t n_cases);
+int raftk_general_solve_dynamics_dev(const raftk_general *g, const raftk_cases *c, const raftk_solve_opts *o, double *Xi,
+                                     int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+int raftk_general_solve_dynamics_host(const raftk_general *g, const raftk_cases *c, const raftk_solve_opts *o, double *Xi,
+                                      int32_t *status);
+
 /* Same three operations with HOST pointers everywhere (tables, cases, outputs). */
 int raftk_hydro_excitation_host(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out);
 int raftk_hydro_linearization_host(const raftk_designs *d, const raftk_cases *c, const double *Xi_in,

@@ -52,6 +52,15 @@ SLENDER_ARRAYS = ("w", "k", "mem_q", "mem_p1", "mem_p2", "mem_mcf", "mem_wl", "m
                   "seg_mem", "seg_z1", "seg_z2", "seg_R", "seg_rmid", "M_struc")
 
 
+GENERAL_ARRAYS = ("w", "k", "node_r", "node_frame", "node_circ", "node_Imat", "node_Imat_w", "node_a_i", "node_cd", "Tn", "rr", "M", "B", "C")
+
+
+class RaftkGeneral(C.Structure):
+    """STAGED (not yet validated on hardware): generalised degrees of freedom, include/raftk.h raftk_general."""
+    _fields_ = ([("n_dof", C.c_int32), ("nw", C.c_int32), ("n_nodes", C.c_int32), ("_pad0", C.c_int32),
+                 ("depth", C.c_double), ("rho", C.c_double), ("dw", C.c_double)] + [(n, C.c_void_p) for n in GENERAL_ARRAYS])
+
+
 class RaftkSlender(C.Structure):
     _fields_ = ([("n_nodes", C.c_int32), ("n_members", C.c_int32), ("n_seg", C.c_int32), ("nw", C.c_int32),
                  ("depth", C.c_double), ("rho", C.c_double), ("g", C.c_double)] + [(n, C.c_void_p) for n in SLENDER_ARRAYS])
@@ -65,6 +74,7 @@ SYMBOLS = [
     "raftk_hydro_excitation_host", "raftk_hydro_linearization_host", "raftk_solve_dynamics_host",
     "raftk_second_order_force_dev", "raftk_second_order_force_host",
     "raftk_qtf_slender_workspace_bytes", "raftk_qtf_slender_dev", "raftk_qtf_slender_host",
+    "raftk_general_workspace_bytes", "raftk_general_solve_dynamics_dev", "raftk_general_solve_dynamics_host",
     "raftk_system_solve_dev", "raftk_system_solve_host", "raftk_response_stats_dev", "raftk_response_stats_host",
     "raftk_channel_stats_dev", "raftk_channel_stats_host", "raftk_host_alloc", "raftk_host_free",
     "raftk_fp64_peak_gflops",
@@ -106,6 +116,12 @@ def _load():
     lib.raftk_qtf_slender_host.argtypes = [P(RaftkSlender), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.raftk_qtf_slender_dev.restype = C.c_int
     lib.raftk_qtf_slender_host.restype = C.c_int
+    lib.raftk_general_workspace_bytes.restype = C.c_size_t
+    lib.raftk_general_workspace_bytes.argtypes = [P(RaftkGeneral), C.c_int32]
+    lib.raftk_general_solve_dynamics_dev.argtypes = [P(RaftkGeneral), P(RaftkCases), P(RaftkSolveOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.raftk_general_solve_dynamics_host.argtypes = [P(RaftkGeneral), P(RaftkCases), P(RaftkSolveOpts), C.c_void_p, C.c_void_p]
+    lib.raftk_general_solve_dynamics_dev.restype = C.c_int
+    lib.raftk_general_solve_dynamics_host.restype = C.c_int
     lib.raftk_system_solve_dev.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.raftk_system_solve_host.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.raftk_response_stats_dev.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

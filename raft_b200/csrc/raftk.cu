@@ -106,6 +106,7 @@ extern "C" long long raftk_launch_count(void) { return g_launches; }
 #include "raftk_fused.cuh"
 #include "raftk_qtf.cuh"
 #include "raftk_slender.cuh"
+#include "raftk_general.cuh"
 #include "raftk_misc.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -791,6 +792,104 @@ extern "C" int raftk_second_order_force_host(const raftk_designs *d, const raftk
     cudaFree(base);
     if (e != cudaSuccess) return set_err(RAFTK_ECUDA, "second-order force: %s", cudaGetErrorString(e));
     return rc;
+}
+
+// ---- generalised degrees of freedom (STAGED: not yet validated on hardware) --------------------------------------------
+struct GenLayout { size_t u, f6, Fi, Fd, XL, Bm, Bd, Z, fl, total; };
+static GenLayout gen_layout(const raftk_general *g, size_t nC)
+{
+    const size_t n = g->n_dof, nw = g->nw, Ns = std::max(g->n_nodes, 1);
+    GenLayout L; size_t t = 0;
+    auto take = [&](size_t b) { size_t o = t; t += align_up(b, 256); return o; };
+    L.u = take(nC * Ns * 3 * nw * 16); L.f6 = take(nC * Ns * 6 * nw * 16);
+    L.Fi = take(nC * n * nw * 16); L.Fd = take(nC * n * nw * 16); L.XL = take(nC * n * nw * 16);
+    L.Bm = take(nC * Ns * 9 * 8); L.Bd = take(nC * n * n * 8);
+    L.Z = take(nC * nw * n * (n + 1) * 16); L.fl = take(nC * 16);
+    L.total = t;
+    return L;
+}
+
+extern "C" size_t raftk_general_workspace_bytes(const raftk_general *g, int32_t n_cases)
+{
+    if (!g || n_cases <= 0 || g->n_dof <= 0 || g->nw <= 0) return 0;
+    return gen_layout(g, (size_t)n_cases).total;
+}
+
+extern "C" int raftk_general_solve_dynamics_dev(const raftk_general *g, const raftk_cases *c, const raftk_solve_opts *o, double *Xi,
+                                                int32_t *status, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!g || !c || !o || !Xi || !status) return set_err(RAFTK_EINVAL, "general solve: null argument");
+    if (g->n_dof <= 0 || g->n_dof > 256 || g->nw <= 0 || g->n_nodes < 0 || c->n_cases <= 0 || c->n_cases > 65535)
+        return set_err(RAFTK_EINVAL, "general solve: 0 < n_dof <= 256, nw > 0, 0 < n_cases <= 65535");
+    if (c->primary || c->F_2nd || c->Xi_init) return set_err(RAFTK_EINVAL, "general solve: wave trains / F_2nd / Xi_init are not supported");
+    const size_t nC = c->n_cases;
+    const GenLayout L = gen_layout(g, nC);
+    if (!workspace || workspace_bytes < L.total) return set_err(RAFTK_ENOMEM, "general solve: workspace too small");
+    GenDev D;
+    D.n = g->n_dof; D.nw = g->nw; D.Ns = g->n_nodes; D.depth = g->depth; D.dw = g->dw; D.rho = g->rho;
+    D.w = g->w; D.k = g->k; D.node_r = g->node_r; D.node_frame = g->node_frame; D.node_circ = g->node_circ;
+    D.node_Imat = g->node_Imat; D.node_Imat_w = reinterpret_cast<const double2 *>(g->node_Imat_w);
+    D.node_a_i = g->node_a_i; D.node_cd = g->node_cd; D.Tn = g->Tn; D.rr = g->rr; D.M = g->M; D.B = g->B; D.C = g->C;
+    char *b = static_cast<char *>(workspace);
+    GenWork W;
+    W.u = reinterpret_cast<double2 *>(b + L.u); W.f6 = reinterpret_cast<double2 *>(b + L.f6);
+    W.F_iner = reinterpret_cast<double2 *>(b + L.Fi); W.F_drag = reinterpret_cast<double2 *>(b + L.Fd);
+    W.XiLast = reinterpret_cast<double2 *>(b + L.XL); W.Bmat = reinterpret_cast<double *>(b + L.Bm);
+    W.B_drag = reinterpret_cast<double *>(b + L.Bd); W.Z = reinterpret_cast<double2 *>(b + L.Z); W.flags = reinterpret_cast<int *>(b + L.fl);
+    CasesDev C = to_dev(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    double2 *X = reinterpret_cast<double2 *>(Xi);
+    const unsigned fb = (unsigned)((g->nw + 127) / 128);
+    k_gen_init<<<(unsigned)nC, 256, 0, st>>>(D, W, o->xi_start);
+    if (g->n_nodes > 0) k_gen_wave<<<dim3(fb, g->n_nodes, (unsigned)nC), 128, 0, st>>>(D, C, W);
+    k_gen_project<<<dim3(fb, g->n_dof, (unsigned)nC), 128, 0, st>>>(D, W, W.F_iner, 0);
+    g_launches += 3;
+    for (int pass = 0; pass < o->n_iter + 1; pass++) {
+        if (g->n_nodes > 0) k_gen_node_pass<<<dim3(g->n_nodes, (unsigned)nC), 128, 0, st>>>(D, W);
+        k_gen_bdrag<<<dim3(g->n_dof, (unsigned)nC), 128, 0, st>>>(D, W);
+        k_gen_project<<<dim3(fb, g->n_dof, (unsigned)nC), 128, 0, st>>>(D, W, W.F_drag, 1);
+        k_gen_solve<<<dim3(g->nw, (unsigned)nC), 256, 0, st>>>(D, W, X, o->tol);
+        k_gen_relax<<<(unsigned)nC, 256, 0, st>>>(D, W, X);
+        g_launches += 5;
+    }
+    k_gen_status<<<(unsigned)((nC + 127) / 128), 128, 0, st>>>((int)nC, W.flags, status);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RAFTK_OK;
+}
+
+extern "C" int raftk_general_solve_dynamics_host(const raftk_general *g, const raftk_cases *c, const raftk_solve_opts *o, double *Xi,
+                                                 int32_t *status)
+{
+    if (!g || !c || !o || !Xi || !status) return set_err(RAFTK_EINVAL, "general solve: null argument");
+    if (g->n_dof <= 0 || g->nw <= 0 || c->n_cases <= 0) return set_err(RAFTK_EINVAL, "general solve: empty problem");
+    const size_t n = g->n_dof, nw = g->nw, Ns = g->n_nodes, nC = c->n_cases;
+    size_t total = 0;
+    auto take = [&](size_t b) { size_t o_ = total; total += align_up(std::max<size_t>(b, 8), 256); return o_; };
+    raftk_general gg = *g; raftk_cases cc = *c;
+    struct Item { size_t off; const void *h; size_t nb; const void **slot; };
+    std::vector<Item> items;
+    auto add = [&](const void *h, size_t nb, const void **slot) { if (h) items.push_back({take(nb), h, nb, slot}); };
+    add(g->w, nw * 8, (const void **)&gg.w); add(g->k, nw * 8, (const void **)&gg.k);
+    add(g->node_r, Ns * 24, (const void **)&gg.node_r); add(g->node_frame, Ns * 72, (const void **)&gg.node_frame);
+    add(g->node_circ, Ns * 4, (const void **)&gg.node_circ); add(g->node_Imat, Ns * 72, (const void **)&gg.node_Imat);
+    add(g->node_Imat_w, Ns * 9 * nw * 16, (const void **)&gg.node_Imat_w); add(g->node_a_i, Ns * 8, (const void **)&gg.node_a_i);
+    add(g->node_cd, Ns * 32, (const void **)&gg.node_cd); add(g->Tn, Ns * 6 * n * 8, (const void **)&gg.Tn); add(g->rr, Ns * 24, (const void **)&gg.rr);
+    add(g->M, n * n * 8, (const void **)&gg.M); add(g->B, n * n * 8, (const void **)&gg.B); add(g->C, n * n * 8, (const void **)&gg.C);
+    add(c->Hs, nC * 8, (const void **)&cc.Hs); add(c->Tp, nC * 8, (const void **)&cc.Tp); add(c->gamma, nC * 8, (const void **)&cc.gamma);
+    add(c->beta_deg, nC * 8, (const void **)&cc.beta_deg); add(c->spec, nC * 4, (const void **)&cc.spec); add(c->zeta, nC * nw * 8, (const void **)&cc.zeta);
+    const size_t o_xi = take(nC * n * nw * 16), o_st = take(nC * 16);
+    const size_t wb = raftk_general_workspace_bytes(g, (int32_t)nC), o_ws = take(wb);
+    DevBuf buf;
+    DEV_ALLOC(buf, total);
+    char *base = buf.as<char>();
+    for (auto &it : items) { CUDA_TRY(cudaMemcpy(base + it.off, it.h, it.nb, cudaMemcpyHostToDevice)); *it.slot = base + it.off; }
+    int rc = raftk_general_solve_dynamics_dev(&gg, &cc, o, reinterpret_cast<double *>(base + o_xi), reinterpret_cast<int32_t *>(base + o_st),
+                                              base + o_ws, wb, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(Xi, base + o_xi, nC * n * nw * 16, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(status, base + o_st, nC * 16, cudaMemcpyDeviceToHost));
+    return RAFTK_OK;
 }
 
 // ---- slender-body QTF ----------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import RaftkCases, RaftkDesigns, RaftkOutputs, RaftkSlender, RaftkSolveOpts, check, lib
+from ._lib import RaftkCases, RaftkDesigns, RaftkGeneral, RaftkOutputs, RaftkSlender, RaftkSolveOpts, check, lib
 
 _F8 = np.float64
 _I4 = np.int32
@@ -341,6 +341,40 @@ def solve_dynamics_slender(packed, cases, n_iter=10, tol=0.01, xi_start=0.0, clu
     out["F_2nd_mean"] = np.where(ok[:, :, None], F2["F_2nd_mean"], 0.0)
     out["qtf"] = qtf
     return out
+
+
+def general_solve_dynamics(P, M, B, Cm, cases, n_iter=10, tol=0.01, xi_start=0.0):
+    """STAGED -- not yet validated on hardware.  Model.solveDynamics for one FOWT with generalised degrees of freedom
+    (flexible members): ``P`` from ``packer.pack_general_dofs`` (node tables + ``gen_Tn``, ``gen_rr``), constant system
+    matrices ``M, B, Cm`` [nDOF,nDOF], ``cases`` a CaseTable -> (Xi complex [nC,nDOF,nw], status [nC,4])."""
+    n, nw, Ns = int(P["gen_nDOF"]), len(P["w"]), len(P["node_ls"])
+    keep = {}
+    g = RaftkGeneral()
+    g.n_dof, g.nw, g.n_nodes = n, nw, Ns
+    g.depth, g.rho, g.dw = float(P["depth"]), float(P["rho"]), float(P["dw"])
+    mem = np.asarray(P["node_mem"], dtype=np.int64)
+    frame = np.concatenate([np.asarray(P["mem_q"])[mem], np.asarray(P["mem_p1"])[mem], np.asarray(P["mem_p2"])[mem]], axis=1) if Ns else np.zeros([0, 9])
+    cd = np.stack([np.asarray(P["node_a_q"]) * np.asarray(P["node_Cd_q"]), np.asarray(P["node_a_p1"]) * np.asarray(P["node_Cd_p1"]),
+                   np.asarray(P["node_a_p2"]) * np.asarray(P["node_Cd_p2"]), np.asarray(P["node_a_End"]) * np.asarray(P["node_Cd_End"])], axis=1) if Ns else np.zeros([0, 4])
+    arrays = dict(w=P["w"], k=P["k"], node_r=P["node_r"], node_frame=frame, node_circ=np.asarray(P["mem_circ"], dtype=_I4)[mem] if Ns else np.zeros(0, dtype=_I4),
+                  node_Imat=P["node_Imat"], node_a_i=P["node_a_i"], node_cd=cd, Tn=P["gen_Tn"], rr=P["gen_rr"], M=M, B=B, C=Cm)
+    if P.get("node_Imat_w") is not None:
+        arrays["node_Imat_w"] = np.ascontiguousarray(P["node_Imat_w"], dtype=np.complex128)
+    for name in _lib.GENERAL_ARRAYS:
+        if name not in arrays:
+            setattr(g, name, None)
+            continue
+        a = arrays[name]
+        a = np.ascontiguousarray(a, dtype=_I4 if name == "node_circ" else (np.complex128 if name == "node_Imat_w" else _F8))
+        keep[name] = a
+        setattr(g, name, a.ctypes.data)
+    nC = cases.n_cases
+    Xi = np.zeros([nC, n, nw], dtype=np.complex128)
+    st = np.zeros([nC, 4], dtype=_I4)
+    c = cases.struct(_host_ptr(cases.arrays))
+    o = RaftkSolveOpts(int(n_iter), 0, float(tol), float(xi_start))
+    check(lib.raftk_general_solve_dynamics_host(C.byref(g), C.byref(c), C.byref(o), Xi.ctypes.data, st.ctypes.data))
+    return Xi, st
 
 
 def second_order_force(batch, cases):
