@@ -1,7 +1,8 @@
 """STAGED kernels (raft_b200/csrc/raftk_general.cuh): generalised degrees of freedom, flexible members, nDOF = 150.
 
 The kernels were written after the round's GPU budget was spent and have NEVER RUN ON HARDWARE.  During development they were
-executed as written under a host emulation (CUDA threads as std::threads, __syncthreads / shuffles as barriers): on this
+executed as written under a host emulation (tools/host_emu: CUDA threads as std::threads, __syncthreads / shuffles as
+barriers; log profiles/r01_host_emu_general.txt): on this
 fixture that reproduced the reference run to 1.5e-11 with identical pass counts, and the checker's F_iner / B_drag / F_drag to
 5e-16.  What has not been exercised is the GPU itself, so the test is marked xfail(strict=False): an XPASS at the round-end run
 means the row is built and parity-green, an XFAIL means debugging starts here next round.  It is the last file of the suite on
