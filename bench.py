@@ -91,11 +91,44 @@ def build_workload(args, rank, world):
         z = np.load(os.path.join(ROOT, "tests", "golden", "cfg2_VolturnUS-S_nw64.npz"))
         mats = dict(M_struc=z["P_M0"] - z["A_hydro_morison"], C_struc=z["P_C0"] - z["C_moor"], C_moor=z["C_moor"])
         fac = sweep.sample_factors(nD * world, seed=40)[rank * nD:(rank + 1) * nD]
-        designs = sweep.build_variants(base, mats, fac, nw=args.nw or 512, max_freq=0.40, depth=float(z["P_depth"]))
+        nw, depth = args.nw or 512, float(z["P_depth"])
+        t0 = time.perf_counter()
+        batch = sweep.build_variants_batched(base, mats, fac, nw=nw, max_freq=0.40, depth=depth)      # all designs in one NumPy pass
+        t_build = time.perf_counter() - t0
+        designs = SweepDesigns(batch, lambda i: sweep.build_variants(base, mats, fac[i:i + 1], nw=nw, max_freq=0.40, depth=depth)[0])
         cs = sea_states(4, nC)
-        cfg = dict(workload="sweep: %d synthetic VolturnUS-S geometry variants x %d sea states x %d bins per GPU, fp64" % (nD, nC, len(designs[0]["w"])),
-                   designs_per_gpu=nD, cases_per_gpu=nC, nw=len(designs[0]["w"]))
+        cfg = dict(workload="sweep: %d synthetic VolturnUS-S geometry variants x %d sea states x %d bins per GPU, fp64" % (nD, nC, batch.nw),
+                   designs_per_gpu=nD, cases_per_gpu=nC, nw=batch.nw, table_build_s=t_build,
+                   table_builder="raft_b200.batch_builder (vectorised over the design axis)")
         return designs, cs, cfg
+
+
+class SweepDesigns:
+    """The sweep shard: ``batch`` is the DesignBatch the batched builder produced (what is solved and timed); indexing
+    gives the packed dict of one design from the PER-DESIGN builder (what the CPU checker / baseline consume)."""
+
+    def __init__(self, batch, packed_of, index=None):
+        self.batch, self._of, self._cache = batch, packed_of, {}
+        self.index = list(range(batch.n_designs)) if index is None else index
+
+    def __len__(self):
+        return len(self.index)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        j = self.index[i]
+        if j not in self._cache:
+            self._cache[j] = self._of(j)
+        return self._cache[j]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def as_batch(designs):
+    from raft_b200 import solver
+    return designs.batch if isinstance(designs, SweepDesigns) else solver.DesignBatch(designs)
 
 
 class ClockSampler:
@@ -202,8 +235,47 @@ def cpu_oracle_rate(designs, cs, min_seconds, nthreads=0):
     return done / dt, used, done, dt
 
 
+def response_err(Xi, ref):
+    """Parity metric (same as tests/conftest.py): per frequency, the error of a DOF relative to the
+    largest reference amplitude in its 3-DOF unit group (translations / rotations) -- every frequency is an
+    independent linear solve and the three DOFs of a group share units."""
+    err = 0.0
+    for g in (slice(0, 3), slice(3, 6)):
+        d = np.abs(Xi[..., g, :] - ref[..., g, :])
+        scale = np.abs(ref[..., g, :]).max(axis=-2, keepdims=True)
+        ok = scale > 0
+        if np.any(ok):
+            err = max(err, float((d / np.where(ok, scale, 1.0))[np.broadcast_to(ok, d.shape)].max()))
+    return err
+
+
+def parity_block(designs, cs, Xi, status, max_designs=8):
+    """Outside the timed region: this rank's benchmarked outputs against the pinned C oracle on the SAME inputs
+    (BASELINE.md 4.5).  Whole shard when it holds <= max_designs designs, else an evenly spaced sample of designs
+    (every case and bin of each).  -> dict for the JSON line."""
+    from oracle import oracle as orc
+    orc.build()
+    nD = len(designs)
+    pick = list(range(nD)) if nD <= max_designs else sorted(set(np.linspace(0, nD - 1, max_designs).round().astype(int).tolist()))
+    worst, mism, units = 0.0, 0, 0
+    for d in pick:
+        Xi_o, st_o, _ = orc.solve_cases(orc.OracleDesign(designs[int(d)]), cs, nIter=10, nthreads=os.cpu_count() or 1)
+        mism += int(np.sum((status[d, :, 0] != st_o[:, 0]) | (status[d, :, 1] != st_o[:, 1])))
+        worst = max(worst, response_err(Xi[d], Xi_o))
+        units += Xi_o.shape[0]
+    return dict(max_rel_err=worst, pass_mismatch_units=mism, units_checked=units, bins_per_unit=int(Xi.shape[-1]),
+                designs_checked=len(pick), designs_in_shard=nD, rtol=1e-10, ok=bool(worst < 1e-10 and mism == 0),
+                metric="response_err: max over (unit, DOF, bin) of |Xi - Xi_oracle| / max|Xi_oracle| over the DOF's "
+                       "translation/rotation group at that bin; pass_mismatch_units = (design, case) units whose number of "
+                       "drag-linearisation passes or converged flag differ",
+                checker="oracle/raft_oracle.c (pinned to reference pickles and reference runs: tests/test_oracle_golden.py)")
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path = the pinned oracle port, all host threads."""
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores.  Two numbers:
+    the pinned C oracle port with all host threads (the STRONG CPU figure: value of the line) and, when
+    oracle/_ref holds the unmodified Python reference (oracle/make_ref.py), that code itself under the stub
+    harness on a bounded sample (cpu_baseline.reference_numpy).  This process never maps libraftk.so."""
     if rank != 0:
         return
     designs, cs, cfg = build_workload(args, 0, 1)
@@ -215,22 +287,39 @@ def run_reference(args, rank, world):
     nw = ods[0].nw
     units = len(designs) * len(cs["Hs"]) * nw
     used = 1
-    nthreads = os.cpu_count() or 1          # torchrun exports OMP_NUM_THREADS=1; the baseline may use every host core
+    ncpu = os.cpu_count() or 1              # torchrun exports OMP_NUM_THREADS=1; the baseline may use every host core
     for _ in range(args.warmup):
-        orc.solve_cases(ods[0], cs, nIter=10, nthreads=nthreads)
+        orc.solve_cases(ods[0], cs, nIter=10, nthreads=ncpu)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for od in ods:
-            _, _, used = orc.solve_cases(od, cs, nIter=10, nthreads=nthreads)
+            _, _, used = orc.solve_cases(od, cs, nIter=10, nthreads=ncpu)
     dt = time.perf_counter() - t0
     val = units * args.steps / dt
     sample = "%d design(s) x %d sea states x %d bins per step, %d steps" % (len(designs), len(cs["Hs"]), nw, args.steps)
+    threads = int(min(used, len(cs["Hs"])))          # the port parallelises over cases: never more threads than cases
+    cpu = dict(value=val, unit=UNIT, cores=threads, host_cpus=ncpu, kind="port", sample=sample)
+    ref = reference_numpy_rate(args.workload, budget_s=20.0)
+    if ref is not None:
+        cpu["reference_numpy"] = ref
+    import raft_b200._lib as _l
     line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                data="synthetic", config=cfg, impl="reference",
-                cpu_baseline=dict(value=val, unit=UNIT, cores=int(min(used, len(cs["Hs"]))), kind="port", sample=sample),
-                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+                data="synthetic", config=cfg, impl="reference", cpu_baseline=cpu,
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                cuda_library_mapped=bool(_l.loaded()))
     print(json.dumps(line))
+
+
+def reference_numpy_rate(workload, budget_s=20.0):
+    """The UNMODIFIED Python reference (copied by oracle/make_ref.py into oracle/_ref, git-ignored, shipped to the GPU
+    box) timed under oracle/ref_harness.py on a bounded sample of the workload, single process (it is single-threaded)
+    and P processes.  None when oracle/_ref is absent or the harness cannot run."""
+    try:
+        from oracle import ref_timing
+        return ref_timing.measure(workload, budget_s=budget_s)
+    except Exception as e:                                   # noqa: BLE001  (report, never fail the bench on the baseline)
+        return dict(unavailable="%s: %s" % (type(e).__name__, str(e)[:200]))
 
 
 def main():
@@ -239,16 +328,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg3q", "sweep"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg3q", "sweep", "farm", "flex"])
     ap.add_argument("--nw", type=int, default=0)
     ap.add_argument("--cases", type=int, default=0)
     ap.add_argument("--designs", type=int, default=0)
+    ap.add_argument("--turbines", type=int, default=0, help="farm workload: number of FOWTs (default 2 as shipped)")
     ap.add_argument("--cluster", type=int, default=0)
-    ap.add_argument("--chunks", type=int, default=1, help="N>1: 1 = solve then ONE all-gather on the same stream (default; measured "
-                                                          "fastest: 0.065 ms for 6.3 MB x 4 ranks); >1 = PipelinedSolve (chunked launches, "
-                                                          "gathers on a side stream) -- NCCL and the cluster kernels then compete for SMs")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: 'fused' = the solve kernel stores every finished unit into all ranks' gathered arrays over NVLink "
+                         "(peer-mapped memory) + an arrival-flag barrier; 'nccl' = solve, then one all_gather_into_tensor")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained-load and sweep-shard extra keys")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -267,35 +359,77 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    from raft_b200 import solver
+    if args.workload in ("farm", "flex"):
+        from raft_b200 import workloads
+        workloads.bench_special(args, rank, world, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    from raft_b200 import solver, sweep
 
     designs, cs, cfg = build_workload(args, rank, world)
-    batch, cases = solver.DesignBatch(designs), solver.CaseTable(cs)
+    line = measure(args, designs, cs, cfg, rank, world, dev, full=True)
+    if not args.no_extras and args.workload == "cfg2":
+        # the north-star's multi-GPU configuration next to the default line: configs[3] shard (design sweep), same
+        # exchange, fewer steps; carried as an extra key so the driver's per-N records hold it too
+        a2 = argparse.Namespace(**vars(args))
+        a2.workload, a2.nw, a2.cases, a2.designs, a2.steps, a2.warmup = "sweep", 0, 0, args.designs or 0, max(2, min(args.steps, 3)), 3
+        d2, c2, g2 = build_workload(a2, rank, world)
+        t_build = g2["table_build_s"]
+        sw = measure(a2, d2, c2, g2, rank, world, dev, full=False)
+        if rank == 0:
+            sw["e2e_including_table_build"] = dict(
+                value=sw["config"]["units_per_step"] / (t_build + sw["e2e"]["ms_per_step"] * 1e-3) if sw.get("e2e") else None, unit=UNIT,
+                note="one sweep step end to end: batched node-table build of this rank's designs on the host + H2D + solve + exchange + D2H")
+            line["sweep"] = sw
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure(args, designs, cs, cfg, rank, world, dev, full):
+    """Time one workload on this rank's GPU (all ranks call it together).  -> the JSON line (dict) on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from raft_b200 import solver, sweep
+    local = dev.index
+    sh, gathered, exch_note = None, None, "none"
+    if world > 1 and args.exchange == "fused":
+        ok = torch.ones(1, device=dev)
+        try:
+            sh = sweep.ShardedSolve(as_batch(designs), cs, device=dev)
+        except Exception as e:                                # noqa: BLE001  (CUDA IPC unavailable on this box -> NCCL)
+            ok.zero_()
+            exch_note = "fused exchange unavailable (%s: %s)" % (type(e).__name__, str(e)[:120])
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1:
+            if sh is not None:
+                sh.close()
+            sh = None
+    if sh is not None:
+        batch, cases, sess = sh.batch, sh.cases, sh.sess
+    else:
+        batch, cases = as_batch(designs), solver.CaseTable(cs)
+        sess = solver.DeviceSession(batch, cases, device=dev)
     nD, nC, nw = batch.n_designs, cases.n_cases, batch.nw
     units = nD * nC * nw
-    sess = solver.DeviceSession(batch, cases, device=dev)
     Xi = sess.out["Xi"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    pipe, gathered = None, None
-    if world > 1 and args.chunks > 1:
-        # optional: chunked launches whose RAO all-gathers run on a side stream and overlap later kernels
-        from raft_b200 import sweep as _sw
-        pipe = _sw.PipelinedSolve(designs, cs, n_chunks=args.chunks, split="cases" if nD == 1 else "designs", device=dev)
-    elif world > 1:
+    if world > 1 and sh is None:
         gathered = torch.empty((world,) + tuple(Xi.shape), dtype=Xi.dtype, device=dev)
+    last = {}
 
     def step():
-        if pipe is not None:
-            pipe.step(n_iter=10, tol=0.01, xi_start=0.0, cluster_size=args.cluster)
+        if sh is not None:
+            last["g"], last["s"] = sh.step(n_iter=10, tol=0.01, xi_start=0.0, cluster_size=args.cluster)
         else:
             sess.solve(n_iter=10, tol=0.01, xi_start=0.0, cluster_size=args.cluster)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, Xi)      # the path's one collective, same stream, once per step
+                dist.all_gather_into_tensor(gathered, Xi)      # fallback exchange: one NCCL collective per step
 
     for _ in range(args.warmup):
         step()
-    if pipe is not None:
-        pipe.drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -312,11 +446,6 @@ def main():
         a.record()
         step()
         b.record()
-    drain_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    drain_ev[0].record()
-    if pipe is not None:
-        pipe.drain()                         # timed: the last step's all-gathers must land inside the K-step total
-    drain_ev[1].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -324,12 +453,29 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = solver.launch_count() - launches0
     clocks = sampler.stop()
-    ms = sum(a.elapsed_time(b) for a, b in ev) + drain_ev[0].elapsed_time(drain_ev[1])
+    ms = sum(a.elapsed_time(b) for a, b in ev)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
     value = units * world * args.steps / (ms * 1e-3)
+    if sh is not None:
+        assert not sh.timed_out(), "peer arrival barrier timed out"
+        nb = Xi.numel() * 16
+        exch_note = ("fused into k_rao_fused: every finished unit's Xi (%d B per rank and step) is stored into all %d ranks' gathered "
+                     "arrays through peer-mapped pointers (NVLink), then a flag barrier kernel; no NCCL on the data path" % (nb, world))
+    elif world > 1:
+        exch_note = "all_gather_into_tensor of Xi (%d B per rank) once per step; %s" % (Xi.numel() * 16, exch_note)
+
+    # ---- what the exchange delivered: every rank's block must equal what that rank computed -----------------
+    exchange_check = None
+    if sh is not None:
+        g, s = last["g"], last["s"]
+        mine = g[sh.rank].contiguous()
+        allb = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allb, mine)
+        exchange_check = bool(all(torch.equal(g[r], allb[r]) for r in range(world)))
+        assert exchange_check, "fused exchange delivered different data than NCCL all_gather of the same blocks"
 
     # ---- roofline of the dominant kernel (drag-linearise + solve), timed live with CUDA events ----
     solver.profile_enable(True)
@@ -342,7 +488,9 @@ def main():
         kms = [x + y for x, y in zip(kms, m)]
         kn = [x + y for x, y in zip(kn, n)]
     solver.profile_enable(False)
+    torch.cuda.synchronize()
     status = sess.out["status"].cpu().numpy()
+    Xi_host = sess.out["Xi"].cpu().numpy() if not args.no_parity and rank == 0 else None
     mean_passes = float(status[..., 0].mean())
     k2_ms = kms[2] / max(kn[2], 1)
     launches_per_step = kn[2] / reps
@@ -369,58 +517,114 @@ def main():
                     note="the contract's two bounds are hbm | tensor; this kernel is neither: ~80 kflop of dependent FP64 per 104 "
                          "algorithmic bytes, DRAM traffic below the algorithmic bytes (tables live on chip). Its binding resource is "
                          "the FP64 pipe: see roofline_fp64 (same kernel, same timing)")
-    fp64_peak = solver.fp64_peak_gflops(20000) if rank == 0 else 0.0
+    fp64_peak = solver.fp64_peak_gflops(20000) if (rank == 0 and full) else 0.0
     f_alg = algorithmic_flops_per_solve(Ns, mean_passes)
     fp64_ach = f_alg * units_per_launch / (k2_ms * 1e-3) / 1e9
     roofline_fp64 = dict(bound="fp64", achieved=fp64_ach / 1e3, peak=fp64_peak / 1e3, unit="TFLOP/s",
                          frac=(fp64_ach / fp64_peak) if fp64_peak > 0 else None, algorithmic_flops_per_solve=f_alg,
                          mean_passes=mean_passes, peak_source="DFMA micro-kernel measured in this run")
 
-    # ---- e2e: host buffers through the reference-facing C-ABI call, H2D + D2H inside the timed region ----
+    # ---- e2e: host buffers in and out, H2D + D2H (and at N > 1 the exchange) inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        for k_, v in list(batch.arrays.items()):
-            p = solver.pinned_empty(v.shape, v.dtype); p[...] = v; batch.arrays[k_] = p
-        for k_, v in list(cases.arrays.items()):
-            p = solver.pinned_empty(v.shape, v.dtype); p[...] = v; cases.arrays[k_] = p
-        outs = dict(Xi=solver.pinned_empty([nD, nC, 6, nw], np.complex128), status=solver.pinned_empty([nD, nC, 4], np.int32),
-                    B_drag=solver.pinned_empty([nD, nC, 6, 6], np.float64))
-        h2d = batch.input_bytes() + cases.input_bytes()
-        d2h = int(sum(v.nbytes for v in outs.values()))
-        for _ in range(args.warmup):
-            solver.solve_dynamics(batch, cases, n_iter=10, cluster_size=args.cluster, out=outs)
+        if sh is not None:
+            for _ in range(args.warmup):
+                sh.step_host(n_iter=10, cluster_size=args.cluster)
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                xi_h, st_h, h2d, d2h = sh.step_host(n_iter=10, cluster_size=args.cluster)
+            dt_e = time.perf_counter() - t0
+            st_e = st_h.numpy()
+        else:
+            for k_, v in list(batch.arrays.items()):
+                p = solver.pinned_empty(v.shape, v.dtype); p[...] = v; batch.arrays[k_] = p
+            for k_, v in list(cases.arrays.items()):
+                p = solver.pinned_empty(v.shape, v.dtype); p[...] = v; cases.arrays[k_] = p
+            outs = dict(Xi=solver.pinned_empty([nD, nC, 6, nw], np.complex128), status=solver.pinned_empty([nD, nC, 4], np.int32),
+                        B_drag=solver.pinned_empty([nD, nC, 6, 6], np.float64))
+            h2d = batch.input_bytes() + cases.input_bytes()
+            d2h = int(sum(v.nbytes for v in outs.values()))
+            for _ in range(args.warmup):
+                solver.solve_dynamics(batch, cases, n_iter=10, cluster_size=args.cluster, out=outs)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                solver.solve_dynamics(batch, cases, n_iter=10, cluster_size=args.cluster, out=outs)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, Xi)
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            dt_e = time.perf_counter() - t0
+            st_e = outs["status"]
+        te = torch.tensor([dt_e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert np.array_equal(st_e, status), "e2e and resident paths disagree"
+        e2e = dict(value=units * world * args.steps / float(te.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
+                   d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * float(te.item()) / args.steps,
+                   includes=("pinned host inputs -> H2D, solve%s, D2H of this rank's Xi + status; wall clock, max over ranks"
+                             % (" + fused exchange + arrival barrier" if sh is not None else (" + all-gather" if world > 1 else ""))))
+
+    # ---- sustained load: >= 2 s of back-to-back steps (no flush: inputs + outputs exceed nothing, tables are on chip) ----
+    sustained = None
+    if full and not args.no_extras:
+        samp2 = ClockSampler(local)
+        n_rep = max(10, int(2.2e3 / max(ms / args.steps, 1e-3)))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            solver.solve_dynamics(batch, cases, n_iter=10, cluster_size=args.cluster, out=outs)
+        samp2.start()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_rep):
+            step()
+        b.record()
         torch.cuda.synchronize()
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        ck = samp2.stop()
+        t_s = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        assert np.array_equal(outs["status"], status), "e2e and resident paths disagree"
-        e2e = dict(value=units * world * args.steps / float(te.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
-                   d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * float(te.item()) / args.steps)
+            dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        sustained = dict(value=units * world * n_rep / (float(t_s.item()) * 1e-3), unit=UNIT, steps=n_rep, seconds=float(t_s.item()) * 1e-3,
+                         ms_per_step=float(t_s.item()) / n_rep, clocks=ck, l2="not flushed (back-to-back steps)")
+
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_block(designs, cs, Xi_host, status)
+        parity["scope"] = "rank 0's shard of the benchmarked step" if world > 1 else "the benchmarked step"
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, used, done, dt = cpu_oracle_rate(designs[:4], cs, min_seconds=8.0, nthreads=os.cpu_count() or 1)
-        cpu = dict(value=rate, unit=UNIT, cores=int(min(used, len(cs["Hs"]))), kind="port",
+    if rank == 0 and world == 1 and full and not args.no_cpu_baseline:
+        ncpu = os.cpu_count() or 1
+        rate, used, done, dt = cpu_oracle_rate(designs[:4], cs, min_seconds=8.0, nthreads=ncpu)
+        cpu = dict(value=rate, unit=UNIT, cores=int(min(used, len(cs["Hs"]))), host_cpus=ncpu, kind="port",
                    sample="%d RAO solves of the same workload (%.1f s, OpenMP over cases, C oracle pinned to the reference)" % (done, dt))
+        ref = reference_numpy_rate(args.workload, budget_s=15.0)
+        if ref is not None:
+            cpu["reference_numpy"] = ref
 
+    line = None
     if rank == 0:
         cfg.update(l2="flushed between timed steps (256 MiB write)", cluster_size=args.cluster or "auto",
-                   units_per_step=units * world, mean_passes=mean_passes, wall_s_timed_region=t_wall,
-                   collective=("all_gather_into_tensor of Xi (%d B per rank) once per step%s" % (Xi.numel() * 16,
-                               "" if args.chunks <= 1 else ", in %d chunks on a side stream" % args.chunks)) if world > 1 else "none")
+                   units_per_step=units * world, mean_passes=mean_passes, wall_s_timed_region=t_wall, collective=exch_note)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic", config=cfg, clocks=clocks, e2e=e2e, gpu_launches=int(launches),
-                    roofline=roofline, roofline_fp64=roofline_fp64, cpu_baseline=cpu)
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+                    roofline=roofline, roofline_fp64=roofline_fp64, cpu_baseline=cpu, parity=parity)
+        if exchange_check is not None:
+            line["exchange_verified"] = exchange_check
+        if sustained is not None:
+            line["sustained"] = sustained
+    if sh is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sh.close()
+    del flush
+    torch.cuda.empty_cache()
+    return line
 
 
 if __name__ == "__main__":

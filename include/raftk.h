@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RAFTK_VERSION 120 /* 0.1.2: + external-QTF and slender-body second-order forces, output channels */
+#define RAFTK_VERSION 130 /* 0.1.3: + peer exchange over NVLink, farm system response on device, blocked generalised-DOF solve */
 
 enum {
     RAFTK_OK = 0,
@@ -294,6 +294,44 @@ int raftk_general_solve_dynamics_dev(const raftk_general *g, const raftk_cases *
                                      int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 int raftk_general_solve_dynamics_host(const raftk_general *g, const raftk_cases *c, const raftk_solve_opts *o, double *Xi,
                                       int32_t *status);
+
+/*
+ * Multi-GPU exchange of the responses (the reference's sweep driver parametersweep.py:49-95 collects
+ * every design's results in one array).  One process per GPU; rank r solves its shard of units.  Instead of a separate
+ * all-gather after the solve, the solve kernel itself stores each finished unit's Xi into EVERY rank's copy of the
+ * gathered array through peer-mapped pointers (NVLink stores, overlapped with the units still computing), and
+ * raftk_peer_barrier_dev makes the stream wait until every peer's stores into THIS rank's copy have landed.
+ *
+ * Setup (once): each rank allocates its copy with raftk_peer_alloc -- plain cudaMalloc memory plus the 64-byte CUDA IPC
+ * handle --, the handles are exchanged out of band (torch.distributed all_gather_object in raft_b200.sweep) and opened
+ * with raftk_peer_open.  A copy holds complex [n_ranks, units_per_rank, 6, nw] responses, uint32 [n_ranks] arrival flags
+ * and optionally int32 [n_ranks, units_per_rank, 4] status words; gathered[p] / flags[p] / status[p] below are rank p's
+ * copy as mapped in THIS process.  A rank may run one step ahead of a peer, so consumers that read other ranks' blocks
+ * should alternate between two copies (raft_b200.sweep.PeerExchange does).
+ */
+#define RAFTK_MAX_PEERS 16
+typedef struct raftk_peers {
+    int32_t n_ranks, rank;
+    uint32_t epoch;          /* step counter, > 0 and increasing by one per exchange (the barrier waits for flags >= epoch) */
+    int32_t _pad0;
+    size_t block_elems;      /* complex elements per rank block = units_per_rank * 6 * nw                              */
+    double *gathered[RAFTK_MAX_PEERS];     /* [p]: base of rank p's gathered array (p == rank: the local allocation)    */
+    uint32_t *flags[RAFTK_MAX_PEERS];      /* [p]: rank p's arrival flags uint32[n_ranks]                               */
+    int32_t *status[RAFTK_MAX_PEERS];      /* [p]: rank p's gathered status int32 [n_ranks, units_per_rank, 4]; all NULL: not exchanged */
+} raftk_peers;
+
+int raftk_peer_alloc(size_t bytes, void **dev_ptr, unsigned char handle[64]);
+int raftk_peer_free(void *dev_ptr);
+int raftk_peer_open(const unsigned char handle[64], void **dev_ptr);
+int raftk_peer_close(void *dev_ptr);
+/* raftk_solve_dynamics_dev with the exchange fused into the kernel's epilogue: out->Xi must be
+ * peers->gathered[rank] + 2 * rank * block_elems (the rank's own block of its own copy). */
+int raftk_solve_dynamics_gather_dev(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o,
+                                    const raftk_outputs *out, const raftk_peers *peers, void *workspace,
+                                    size_t workspace_bytes, void *stream);
+/* Enqueue: tell every peer "my stores of this epoch are done", then wait (bounded: ~4 s, then *timeout_flag = 1 if
+ * given) until every peer said so.  After it, gathered[rank] holds all ranks' blocks of this epoch. */
+int raftk_peer_barrier_dev(const raftk_peers *peers, int32_t *timeout_flag, void *stream);
 
 /* Same three operations with HOST pointers everywhere (tables, cases, outputs). */
 int raftk_hydro_excitation_host(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out);

@@ -1,5 +1,10 @@
 """ctypes binding of libraftk.so (include/raftk.h).  No CPU fallback: if the CUDA library is not
-built, importing this module raises -- the product path must fail loudly, never degrade."""
+built, importing this module raises -- the product path must fail loudly, never degrade.
+
+The shared object is mapped on the first call into it (``lib.<symbol>``), not at import: the pure-NumPy
+host helpers of the package (grid, packer, member builder) can then be imported by a process that must
+not load CUDA code -- ``bench.py --impl reference`` -- while every product call still goes through
+``lib`` and a missing file is an ImportError at import time."""
 import ctypes as C
 import os
 
@@ -47,6 +52,16 @@ class RaftkOutputs(C.Structure):
                 ("F_2nd", C.c_void_p), ("F_2nd_mean", C.c_void_p), ("Xi_last", C.c_void_p)]
 
 
+MAX_PEERS = 16
+
+
+class RaftkPeers(C.Structure):
+    """include/raftk.h raftk_peers: peer-mapped gathered arrays of the fused multi-GPU exchange."""
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint32), ("_pad0", C.c_int32),
+                ("block_elems", C.c_size_t), ("gathered", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS),
+                ("status", C.c_void_p * MAX_PEERS)]
+
+
 SLENDER_ARRAYS = ("w", "k", "mem_q", "mem_p1", "mem_p2", "mem_mcf", "mem_wl", "mem_r_int", "mem_a_wl", "mem_rwl", "mem_R_wl", "mem_node_start",
                   "node_r", "node_v_side", "node_Ca_p1", "node_Ca_p2", "node_Ca_End", "node_v_end", "node_a_i",
                   "seg_mem", "seg_z1", "seg_z2", "seg_R", "seg_rmid", "M_struc")
@@ -78,6 +93,8 @@ SYMBOLS = [
     "raftk_system_solve_dev", "raftk_system_solve_host", "raftk_response_stats_dev", "raftk_response_stats_host",
     "raftk_channel_stats_dev", "raftk_channel_stats_host", "raftk_host_alloc", "raftk_host_free",
     "raftk_fp64_peak_gflops",
+    "raftk_peer_alloc", "raftk_peer_free", "raftk_peer_open", "raftk_peer_close",
+    "raftk_solve_dynamics_gather_dev", "raftk_peer_barrier_dev",
 ]
 
 
@@ -85,11 +102,15 @@ class RaftkError(RuntimeError):
     pass
 
 
-def _load():
+def _require():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             "raft_b200: CUDA library %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+
+
+def _load():
+    _require()
     lib = C.CDLL(LIB_PATH)
     P = C.POINTER
     lib.raftk_version.restype = C.c_int
@@ -137,6 +158,16 @@ def _load():
     lib.raftk_host_free.argtypes = [C.c_void_p]
     lib.raftk_fp64_peak_gflops.restype = C.c_double
     lib.raftk_fp64_peak_gflops.argtypes = [C.c_int]
+    lib.raftk_peer_alloc.argtypes = [C.c_size_t, P(C.c_void_p), C.c_char_p]
+    lib.raftk_peer_open.argtypes = [C.c_char_p, P(C.c_void_p)]
+    lib.raftk_peer_free.argtypes = [C.c_void_p]
+    lib.raftk_peer_close.argtypes = [C.c_void_p]
+    lib.raftk_solve_dynamics_gather_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkSolveOpts), P(RaftkOutputs), P(RaftkPeers),
+                                                    C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.raftk_peer_barrier_dev.argtypes = [P(RaftkPeers), C.c_void_p, C.c_void_p]
+    for fn in ("raftk_peer_alloc", "raftk_peer_open", "raftk_peer_free", "raftk_peer_close", "raftk_solve_dynamics_gather_dev",
+               "raftk_peer_barrier_dev"):
+        getattr(lib, fn).restype = C.c_int
     for fn in ("raftk_hydro_excitation_dev", "raftk_hydro_linearization_dev", "raftk_solve_dynamics_dev",
                "raftk_hydro_excitation_host", "raftk_hydro_linearization_host", "raftk_solve_dynamics_host",
                "raftk_system_solve_dev", "raftk_system_solve_host",
@@ -145,7 +176,23 @@ def _load():
     return lib
 
 
-lib = _load()
+class _LazyLib:
+    """Proxy that dlopens libraftk.so on first attribute access (see the module docstring)."""
+    _real = None
+
+    def __getattr__(self, name):
+        if _LazyLib._real is None:
+            _LazyLib._real = _load()
+        return getattr(_LazyLib._real, name)
+
+
+_require()          # fail loudly at import when the library has not been built
+lib = _LazyLib()
+
+
+def loaded():
+    """True once the shared object has been mapped into this process."""
+    return _LazyLib._real is not None
 
 
 def check(rc):

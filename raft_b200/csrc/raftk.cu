@@ -52,6 +52,31 @@ static int set_err(int code, const char *fmt, const char *a = "", const char *b 
         if (_e != cudaSuccess) return set_err(RAFTK_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
 
+// ---- per-device opt-in for > 48 KB of dynamic shared memory ------------------------------------------
+// cudaFuncSetAttribute applies to the CURRENT device only, so the high-water mark is kept per device
+// (a process may drive several GPUs through DeviceSession(device=...)).
+#define RAFTK_MAX_DEV 64
+static int cur_dev()
+{
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (d >= 0 && d < RAFTK_MAX_DEV) ? d : 0;
+}
+struct SmemOptIn {
+    std::mutex mu;
+    size_t set[RAFTK_MAX_DEV];
+    explicit SmemOptIn(size_t floor = 0) { for (auto &v : set) v = floor; }
+    template <class K> cudaError_t ensure(K kernel, size_t bytes)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        const int d = cur_dev();
+        if (bytes <= set[d]) return cudaSuccess;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) set[d] = bytes;
+        return e;
+    }
+};
+
 // ---- optional per-kernel event timing (roofline report) ----------------------------------------------
 struct ProfRec { cudaEvent_t a, b; int kind; };
 static bool g_prof_on = false;
@@ -197,16 +222,9 @@ static int run_qtf(const raftk_designs *d, const raftk_cases *c, double *F2, dou
     P.qtf = reinterpret_cast<const double2 *>(d->qtf);
     P.F2 = F2; P.F2mean = F2mean;
     const size_t smem = (size_t)d->nw * 20;
-    static std::mutex mu;
-    static size_t smem_set = 48 * 1024;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if (smem > smem_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_qtf_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUDA_TRY(cudaFuncSetAttribute(k_qtf_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set = smem;
-        }
-    }
+    static SmemOptIn opt_plain(48 * 1024), opt_mix(48 * 1024), opt_tiles(48 * 1024);
+    CUDA_TRY(opt_plain.ensure(k_qtf_force<false>, smem));
+    CUDA_TRY(opt_mix.ensure(k_qtf_force<true>, smem));
     if (P.shared != 1 && d->n_designs > 65535) return set_err(RAFTK_EINVAL, "second-order force: more than 65535 designs per call");
     if (c->n_cases > 65535) return set_err(RAFTK_EINVAL, "second-order force: more than 65535 cases per call");
     // tile variant (registers hold the table-cell corners, systolic diagonal accumulators) when its shared-memory
@@ -215,14 +233,7 @@ static int run_qtf(const raftk_designs *d, const raftk_cases *c, double *F2, dou
     const size_t tsmem = (size_t)d->nw * 68 + (size_t)ncell * 8 + 16;
     const bool tiles = !getenv("RAFTK_QTF_DIAG") && tsmem <= 226 * 1024 && d->nw <= 4096;
     if (tiles) {
-        static size_t tsmem_set = 48 * 1024;
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            if (tsmem > tsmem_set) {
-                CUDA_TRY(cudaFuncSetAttribute(k_qtf_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-                tsmem_set = tsmem;
-            }
-        }
+        CUDA_TRY(opt_tiles.ensure(k_qtf_tiles, tsmem));
         QtfTileParams TP;
         TP.q = P; TP.ncell = ncell;
         const size_t rows = (size_t)((P.shared == 1) ? 1 : d->n_designs) * c->n_cases * 6 * d->nw;
@@ -331,15 +342,8 @@ static bool fused_plan(const raftk_designs *d, int units, int requested_cs, bool
 template <int T>
 static int fused_launch(const DesignsDev &D, const CasesDev &C, const FusedParams &P, const FPlan &pl, int units, cudaStream_t st)
 {
-    static std::mutex mu;
-    static size_t smem_set = 0;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if (pl.smem > smem_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_rao_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-            smem_set = pl.smem;
-        }
-    }
+    static SmemOptIn opt;
+    CUDA_TRY(opt.ensure(k_rao_fused<T>, pl.smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)((size_t)units * pl.CS), 1, 1);
@@ -360,7 +364,7 @@ static int fused_launch(const DesignsDev &D, const CasesDev &C, const FusedParam
 }
 
 static int run_fused(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o, const raftk_outputs *out,
-                     const FPlan &pl, void *workspace, size_t wbytes, cudaStream_t st)
+                     const FPlan &pl, void *workspace, size_t wbytes, cudaStream_t st, const raftk_peers *peers = nullptr)
 {
     prof_begin_call();
     DesignsDev D = to_dev(d, d->max_nodes, d->max_members);
@@ -378,6 +382,16 @@ static int run_fused(const raftk_designs *d, const raftk_cases *c, const raftk_s
     P.F0g = pl.f0_global ? reinterpret_cast<double2 *>(workspace) : nullptr;
     const int units = d->n_designs * c->n_cases;
     P.lin_g = nullptr; P.phase = -1;
+    P.n_peers = 0; P.peer_rank = 0;
+    for (int p = 0; p < RAFTK_MAX_PEERS; p++) { P.peer_Xi[p] = nullptr; P.peer_status[p] = nullptr; }
+    if (peers && peers->n_ranks > 1) {
+        P.n_peers = peers->n_ranks; P.peer_rank = peers->rank;
+        const size_t units_per_rank = peers->block_elems / ((size_t)6 * d->nw);
+        for (int p = 0; p < peers->n_ranks; p++) {
+            P.peer_Xi[p] = reinterpret_cast<double2 *>(peers->gathered[p]) + (size_t)peers->rank * peers->block_elems;
+            P.peer_status[p] = peers->status[p] ? peers->status[p] + (size_t)peers->rank * units_per_rank * 4 : nullptr;
+        }
+    }
     if (c->primary) {                                  // wave trains: primaries first, then the trains that follow them
         const size_t f0b = align_up((size_t)units * 6 * d->nw * sizeof(double2), 256);
         const size_t need = f0b + (size_t)units * ((size_t)NCOEF * d->max_nodes + 36) * sizeof(double);
@@ -396,7 +410,7 @@ static int run_fused(const raftk_designs *d, const raftk_cases *c, const raftk_s
 
 static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o, const raftk_outputs *out,
                const double *Xi_in, int mode /*0 solve, 1 linearise, 2 excitation only*/, bool do_excitation,
-               void *workspace, size_t wbytes, cudaStream_t st)
+               void *workspace, size_t wbytes, cudaStream_t st, const raftk_peers *peers = nullptr)
 {
     int rc = validate(d, c);
     if (rc) return rc;
@@ -404,7 +418,8 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
     if (mode == 0) {                                   // fused on-chip solver when the slice fits in shared memory
         FPlan fp;
         const bool have_ws = workspace && wbytes >= (size_t)nD * nC * 6 * nw * sizeof(double2);
-        if (fused_plan(d, nD * nC, o ? o->cluster_size : 0, have_ws, fp)) return run_fused(d, c, o, out, fp, workspace, wbytes, st);
+        if (fused_plan(d, nD * nC, o ? o->cluster_size : 0, have_ws, fp)) return run_fused(d, c, o, out, fp, workspace, wbytes, st, peers);
+        if (peers && peers->n_ranks > 1) return set_err(RAFTK_EINVAL, "the fused exchange needs the fused solver; the design's frequency slice does not fit on chip");
         if (c->primary) return set_err(RAFTK_EINVAL, "wave-train cases (cases.primary) need the fused solver; the design's frequency slice does not fit on chip");
         if (c->Xi_init || out->Xi_last) return set_err(RAFTK_EINVAL, "cases.Xi_init / outputs.Xi_last need the fused solver; the design's frequency slice does not fit on chip");
     }
@@ -423,13 +438,8 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
     if (mode != 2) {
         rc = make_plan(d, std::min(per, nD) * nC, o ? o->cluster_size : 0, pl);
         if (rc) return rc;
-        static std::mutex mu;
-        static size_t smem_set = 0;
-        std::lock_guard<std::mutex> lk(mu);
-        if (pl.smem > smem_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_drag_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-            smem_set = pl.smem;
-        }
+        static SmemOptIn opt;
+        CUDA_TRY(opt.ensure(k_drag_solve, pl.smem));
     }
 
     for (int d0 = 0; d0 < nD; d0 += per) {
@@ -531,21 +541,88 @@ extern "C" int raftk_solve_dynamics_dev(const raftk_designs *d, const raftk_case
     return run(d, c, o, out, nullptr, 0, true, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// ---- multi-GPU exchange fused into the solve (peer stores over NVLink) ------------------------------------------
+extern "C" int raftk_peer_alloc(size_t bytes, void **dev_ptr, unsigned char handle[64])
+{
+    if (!dev_ptr || !handle || bytes == 0) return set_err(RAFTK_EINVAL, "peer_alloc: null argument / zero size");
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return set_err(RAFTK_ECUDA, "peer_alloc: %s", cudaGetErrorString(e)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memcpy(handle, &h, 64);
+    *dev_ptr = p;
+    return RAFTK_OK;
+}
+extern "C" int raftk_peer_free(void *dev_ptr)
+{
+    if (dev_ptr) CUDA_TRY(cudaFree(dev_ptr));
+    return RAFTK_OK;
+}
+extern "C" int raftk_peer_open(const unsigned char handle[64], void **dev_ptr)
+{
+    if (!dev_ptr || !handle) return set_err(RAFTK_EINVAL, "peer_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RAFTK_OK;
+}
+extern "C" int raftk_peer_close(void *dev_ptr)
+{
+    if (dev_ptr) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return RAFTK_OK;
+}
+
+static int validate_peers(const raftk_peers *p)
+{
+    if (!p) return set_err(RAFTK_EINVAL, "null peers");
+    if (p->n_ranks < 1 || p->n_ranks > RAFTK_MAX_PEERS || p->rank < 0 || p->rank >= p->n_ranks)
+        return set_err(RAFTK_EINVAL, "peers: 1 <= n_ranks <= RAFTK_MAX_PEERS and 0 <= rank < n_ranks");
+    for (int r = 0; r < p->n_ranks; r++)
+        if (!p->gathered[r] || !p->flags[r]) return set_err(RAFTK_EINVAL, "peers: gathered / flags pointer missing for a rank");
+    return 0;
+}
+
+extern "C" int raftk_solve_dynamics_gather_dev(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o,
+                                               const raftk_outputs *out, const raftk_peers *peers, void *workspace,
+                                               size_t workspace_bytes, void *stream)
+{
+    if (!out || !out->Xi || !out->status || !o) return set_err(RAFTK_EINVAL, "Xi, status and opts are required");
+    int rc = validate_peers(peers);
+    if (rc) return rc;
+    if (!d || !c) return set_err(RAFTK_EINVAL, "null designs/cases");
+    if ((size_t)d->n_designs * c->n_cases * 6 * d->nw > peers->block_elems)
+        return set_err(RAFTK_EINVAL, "peers.block_elems is smaller than this rank's response block");
+    if (out->Xi != peers->gathered[peers->rank] + 2 * (size_t)peers->rank * peers->block_elems)
+        return set_err(RAFTK_EINVAL, "outputs.Xi must be this rank's block of its own gathered array");
+    if (d->n_qtf_w > 0 && !c->F_2nd) return set_err(RAFTK_EINVAL, "gather solve: pass cases.F_2nd precomputed (raftk_second_order_force_dev)");
+    return run(d, c, o, out, nullptr, 0, true, workspace, workspace_bytes, (cudaStream_t)stream, peers);
+}
+
+extern "C" int raftk_peer_barrier_dev(const raftk_peers *peers, int32_t *timeout_flag, void *stream)
+{
+    int rc = validate_peers(peers);
+    if (rc) return rc;
+    if (peers->epoch == 0) return set_err(RAFTK_EINVAL, "peers.epoch must be > 0");
+    PeerFlags F;
+    F.n = peers->n_ranks; F.rank = peers->rank; F.epoch = peers->epoch;
+    for (int p = 0; p < RAFTK_MAX_PEERS; p++) F.flags[p] = p < peers->n_ranks ? peers->flags[p] : nullptr;
+    k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(F, timeout_flag);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RAFTK_OK;
+}
+
 // ---- farm system solve ----------------------------------------------------------------------------
 extern "C" int raftk_system_solve_dev(int32_t n, int32_t nw, int32_t nrhs, double *Z, double *F, int32_t *info, void *stream)
 {
     if (n <= 0 || nw <= 0 || nrhs <= 0 || !Z || !F) return set_err(RAFTK_EINVAL, "bad system-solve arguments");
     const size_t smem = (size_t)n * (n + nrhs) * sizeof(double2);
     if (smem > 227 * 1024) return set_err(RAFTK_EINVAL, "system too large for the shared-memory solver (n*(n+nrhs)*16 B > 227 KB)");
-    static std::mutex mu;
-    static size_t smem_set = 48 * 1024;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if (smem > smem_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_system_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set = smem;
-        }
-    }
+    static SmemOptIn opt(48 * 1024);
+    CUDA_TRY(opt.ensure(k_system_solve, smem));
     k_system_solve<<<nw, 128, smem, (cudaStream_t)stream>>>(n, nrhs, reinterpret_cast<double2 *>(Z), reinterpret_cast<double2 *>(F), info);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -574,7 +651,7 @@ struct Arena {
     }
     void *take(size_t bytes) { void *p = base + used; used += align_up(bytes, 256); return p; }
 };
-static Arena g_arena;
+static Arena g_arena[RAFTK_MAX_DEV];       // one per device: the *_host paths run on whichever device is current
 static std::mutex g_arena_mu;
 
 // Small input arrays (grid, member/node tables, case table: ~30 arrays of a few KB) are gathered in one pinned
@@ -587,7 +664,7 @@ struct Stager {
     bool ensure()
     {
         if (host) return true;
-        if (cudaHostAlloc(&host, SMALL_REGION, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); host = nullptr; return false; }
+        if (cudaHostAlloc(&host, SMALL_REGION, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); host = nullptr; return false; }
         return true;
     }
 };
@@ -660,8 +737,8 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     if (mode != 0) wb = chunk_bytes((int)nD, (int)nC, d->max_nodes, (int)nw);   // single chunk required
     else { FPlan fp; if (fused_plan(d, (int)(nD * nC), o ? o->cluster_size : 0, true, fp)) wb = raftk_solve_workspace_bytes(d, (int32_t)nC); }
     const size_t total = SMALL_REGION + in_bytes(d, c) + obytes + align_up(wb, 256) + 4096;
-    if (g_arena.reserve(total)) return set_err(RAFTK_ENOMEM, "device arena allocation failed");
-    Arena &A = g_arena;
+    Arena &A = g_arena[cur_dev()];
+    if (A.reserve(total)) return set_err(RAFTK_ENOMEM, "device arena allocation failed");
     A.used = SMALL_REGION;                   // [0, SMALL_REGION) mirrors the pinned staging block
     g_stage.ensure();
     g_stage.used = 0;

@@ -27,6 +27,11 @@ struct FusedParams {
     double2 *F0g;            // [units][6][nw] linear excitation kept in global memory (frees 96 B/bin of smem), or NULL
     double *lin_g;           // [units][NCOEF*max_nodes + 36] linearisation hand-over primary -> secondary wave trains, or NULL
     int phase;               // -1: every case is its own primary; 0: run primaries only; 1: run secondaries only
+    // multi-GPU exchange fused into the epilogue (raftk_solve_dynamics_gather_dev): every finished unit's Xi / status
+    // is also stored into the other ranks' gathered arrays through peer-mapped pointers (NVLink)
+    int n_peers, peer_rank;
+    double2 *peer_Xi[RAFTK_MAX_PEERS];    // [p]: this rank's block inside rank p's gathered array, same indexing as Xi_out
+    int *peer_status[RAFTK_MAX_PEERS];    // [p]: likewise for status, or NULL
 };
 
 #define IMEM_STRIDE 6      // ints per member: node start, node end, circular, (spare), z-class, (spare)
@@ -333,6 +338,10 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
             else { S.xi[(2 * a) * nwl + t] = P.xi_start; S.xi[(2 * a + 1) * nwl + t] = 0.0; }
         }
     }
+    if (plan_overflow) {          // no pass will run: never hand back whatever the output buffer held before
+        for (int t = tid; t < nloc; t += T)
+            for (int a = 0; a < 6; a++) P.Xi_out[ogl + (size_t)a * nw + f_begin + t] = make_double2(0.0, 0.0);
+    }
     __syncthreads();
 
     const double *Aw = D.A_w ? D.A_w + (size_t)d * 36 * nw : nullptr;
@@ -638,6 +647,28 @@ k_rao_fused(DesignsDev D, CasesDev Cs, FusedParams P)
     if (P.status && rank == 0 && tid == 0) {
         int *st = P.status + ((size_t)d * Cs.nC + c) * 4;
         st[0] = secondary ? 0 : passes; st[1] = secondary ? 1 : converged; st[2] = flags; st[3] = secondary ? prim + 1 : 0;
+    }
+    if (P.n_peers > 1) {
+        // the unit is final: push this CTA's slice of Xi to every peer.  Each thread re-reads the values it stored itself
+        // in the last pass (L2 hits); the peer stores are fire-and-forget and overlap the units still iterating.
+        for (int t = tid; t < nloc; t += T) {
+            const int i = f_begin + t;
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                const size_t o_ = ogl + (size_t)a * nw + i;
+                const double2 v = P.Xi_out[o_];
+                for (int p = 0; p < P.n_peers; p++)
+                    if (p != P.peer_rank) P.peer_Xi[p][o_] = v;
+            }
+        }
+        if (rank == 0 && tid == 0) {
+            const size_t so = ((size_t)d * Cs.nC + c) * 4;
+            for (int p = 0; p < P.n_peers; p++)
+                if (p != P.peer_rank && P.peer_status[p]) {
+                    int *st = P.peer_status[p] + so;
+                    st[0] = secondary ? 0 : passes; st[1] = secondary ? 1 : converged; st[2] = flags; st[3] = secondary ? prim + 1 : 0;
+                }
+        }
     }
     if (CS > 1) cluster.sync();
 }

@@ -141,3 +141,28 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters)
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+
+// ------------------------------------------------------------------------------------------------
+// K6: cross-GPU arrival barrier of the fused exchange (raftk_peer_barrier_dev).  Thread p tells rank p that this
+// rank's stores of `epoch` are complete (they were issued by earlier kernels of this stream, so they are performed
+// before this kernel starts; the release store orders the flag behind them at system scope), then waits for
+// rank p's flag in the local copy.  Bounded spin: a dead peer sets *timeout_flag instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------
+struct PeerFlags { int n, rank; unsigned epoch; unsigned *flags[RAFTK_MAX_PEERS]; };
+
+__global__ void k_peer_barrier(PeerFlags F, int *timeout_flag)
+{
+    const int p = threadIdx.x;
+    if (p >= F.n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(F.flags[p] + F.rank), "r"(F.epoch) : "memory");
+    const unsigned *mine = F.flags[F.rank] + p;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int)(v - F.epoch) >= 0) break;
+        if (clock64() - t0 > 8000000000LL) { if (timeout_flag) *timeout_flag = 1; break; }     // ~4 s at 1.9 GHz
+        __nanosleep(200);
+    }
+}

@@ -134,8 +134,7 @@ class Model:
         if "primary" in table:                                              # secondary trains share their primary's B_drag
             o["B_drag"] = o["B_drag"][:, table["primary"]]
         st = o["status"][:, first]                                          # [nFOWT, nC, 4] (train 0 of every case)
-        if np.any(st[..., 2] & 1):
-            raise Exception("Nan detected in response vector Xi.")          # raft_model.py:1098-1099
+        solver.raise_on_flags(st)                                           # raft_model.py:1089 (LinAlgError), :1098-1099 (NaN)
         w = self.w
         for i, f in enumerate(self.fowtList):
             P = f.pack()

@@ -45,6 +45,9 @@ class DesignBatch:
         for P in packed:
             if len(P["w"]) != self.nw or float(P["depth"]) != self.depth:
                 raise ValueError("all designs of a batch must share the frequency grid and water depth")
+            if P is not P0 and (not np.array_equal(np.asarray(P["w"], dtype=_F8), self.w) or float(P["rho"]) != self.rho
+                                or float(P["g"]) != self.g):
+                raise ValueError("all designs of a batch must share the frequency values, water density and g")
             nm = len(P["mem_circ"])
             frames.append(np.concatenate([P["mem_q"], P["mem_p1"], P["mem_p2"]], axis=1).reshape(nm, 9))
             rAs.append(np.asarray(P["mem_rA"], dtype=_F8).reshape(nm, 3))
@@ -83,14 +86,19 @@ class DesignBatch:
             a["B_w"] = np.ascontiguousarray(np.stack([np.asarray(P["B_w"], dtype=_F8).reshape(36, self.nw) if h else z
                                                       for P, h in zip(packed, have_w)]))
         self.n_bem_head = 0
-        if "X_BEM" in P0 and P0["X_BEM"] is not None:
-            heads = np.ascontiguousarray(P0["bem_headings"], dtype=_F8)
+        have_x = [P.get("X_BEM") is not None for P in packed]
+        if any(have_x):
+            # designs without BEM excitation in a mixed batch (strip-theory platform next to potMod ones) get zero tables
+            Px = packed[have_x.index(True)]
+            heads = np.ascontiguousarray(Px["bem_headings"], dtype=_F8)
             self.n_bem_head = len(heads)
-            for P in packed:
-                if "X_BEM" not in P or len(P["bem_headings"]) != self.n_bem_head:
+            for P, h in zip(packed, have_x):
+                if h and not np.array_equal(np.asarray(P["bem_headings"], dtype=_F8), heads):
                     raise ValueError("all designs of a batch must share the BEM heading list")
+            zx = np.zeros([self.n_bem_head, 6, self.nw], dtype=np.complex128)
             a["bem_headings"] = heads
-            a["X_BEM"] = np.ascontiguousarray(np.stack([np.asarray(P["X_BEM"], dtype=np.complex128) for P in packed]))
+            a["X_BEM"] = np.ascontiguousarray(np.stack([np.asarray(P["X_BEM"], dtype=np.complex128) if h else zx
+                                                        for P, h in zip(packed, have_x)]))
             a["bem_xyh"] = np.ascontiguousarray(np.array(
                 [[float(P.get("x_ref", 0.0)), float(P.get("y_ref", 0.0)), float(P.get("heading_adjust", 0.0))] for P in packed],
                 dtype=_F8))
@@ -121,6 +129,23 @@ class DesignBatch:
         self.max_nodes = max(1, max_nodes)
         self.max_members = max(1, max_members)
         self.max_w_classes, self.max_h_classes, self.max_z_classes = self._step_classes(packed)
+
+    @classmethod
+    def from_tables(cls, arrays, n_designs, depth, rho, g, dw, max_nodes, max_members, classes):
+        """DesignBatch straight from CSR tables (``raft_b200.batch_builder``): ``arrays`` holds the raftk_designs columns
+        (member_offset, mem_*, node_*, M0/B0/C0, w, k); ``classes`` = (max_w, max_h, max_z) step-class hints."""
+        self = cls.__new__(cls)
+        self.arrays = a = dict(arrays)
+        self.n_designs = int(n_designs)
+        self.w, self.k = a["w"], a["k"]
+        self.nw = len(self.w)
+        self.depth, self.rho, self.g, self.dw = float(depth), float(rho), float(g), float(dw)
+        self.n_bem_head = self.n_qtf_w = self.n_qtf_head = self.qtf_shared = 0
+        self.n_members_total = int(a["member_offset"][-1])
+        self.n_nodes_total = int(a["mem_node_start"][-1])
+        self.max_nodes, self.max_members = int(max_nodes), int(max_members)
+        self.max_w_classes, self.max_h_classes, self.max_z_classes = (int(c) for c in classes)
+        return self
 
     @staticmethod
     def _step_classes(packed):
@@ -241,7 +266,30 @@ def solve_dynamics(batch, cases, n_iter=10, tol=0.01, xi_start=0.0, cluster_size
     o = RaftkSolveOpts(int(n_iter), int(cluster_size), float(tol), float(xi_start))
     os_ = _out_struct(outs, lambda a: a.ctypes.data)
     check(lib.raftk_solve_dynamics_host(C.byref(d), C.byref(c), C.byref(o), C.byref(os_)))
+    if np.any(outs["status"][..., 2] & FLAG_PLAN):
+        # the device deduplicated more distinct node spacings than the host-side hint allowed for (near-tolerance
+        # chains): those units ran no pass and hold zeros.  Re-run with worst-case table sizes (hint 0).
+        d.max_w_classes = d.max_h_classes = d.max_z_classes = 0
+        check(lib.raftk_solve_dynamics_host(C.byref(d), C.byref(c), C.byref(o), C.byref(os_)))
+        if np.any(outs["status"][..., 2] & FLAG_PLAN):
+            raise _lib.RaftkError("step-class tables overflowed even with worst-case sizes")
     return outs
+
+
+FLAG_NAN, FLAG_SINGULAR, FLAG_PLAN = 1, 2, 4        # include/raftk.h RAFTK_FLAG_*
+
+
+def raise_on_flags(status):
+    """Translate the status flags of solved units into the reference's exceptions: NaN in the response ->
+    ``Exception("Nan detected in response vector Xi.")`` (raft_model.py:1098-1099); a singular impedance ->
+    ``numpy.linalg.LinAlgError`` (what ``np.linalg.solve`` raises at raft_model.py:1089)."""
+    fl = np.asarray(status)[..., 2]
+    if np.any(fl & FLAG_PLAN):
+        raise _lib.RaftkError("fused solver: step-class tables overflowed the hint; outputs of those units are zero")
+    if np.any(fl & FLAG_SINGULAR) and not np.any(fl & FLAG_NAN):
+        raise np.linalg.LinAlgError("Singular matrix")
+    if np.any(fl & FLAG_NAN):
+        raise Exception("Nan detected in response vector Xi.")
 
 
 def hydro_excitation(batch, cases, want=("F_iner", "F_BEM", "zeta")):
@@ -292,7 +340,10 @@ def solve_dynamics_slender(packed, cases, n_iter=10, tol=0.01, xi_start=0.0, clu
     """Model.solveDynamics with potSecOrder 1 (raft_model.py:1052-1142) for every (design, case): (A) the drag-linearisation
     loop without second-order forces; (B) where it converged: motion RAOs -> slender-body QTF on the second-order grid ->
     difference-frequency force -> the loop continues from the SAME iterate with the force added and its counter reset
-    (at most n_iter more passes).  Units whose loop (A) did not converge keep its result, like the reference.
+    (the reference sets iiter = 0 and the loop header increments it to 1, raft_model.py:1106-1131, so loop (B) runs at
+    most n_iter passes: it is launched with n_iter - 1, i.e. max_pass = n_iter).  Units whose loop (A) did not converge
+    keep its result and get no QTF / second-order force (zeros), like the reference, which never computes them there.
+    n_iter = 0 is rejected: the reference would still add F_2nd to the final system response (documented deviation).
     ``packed``: list of packed designs carrying ``qs_*`` tables on one second-order grid; ``cases``: CaseTable (single
     wave train per case).  Extra outputs: F_2nd, F_2nd_mean, qtf [nD,nC,nw2,nw2,6]."""
     if isinstance(packed, dict):
@@ -339,7 +390,7 @@ def solve_dynamics_slender(packed, cases, n_iter=10, tol=0.01, xi_start=0.0, clu
     okf = ok[:, :, None, None]
     out["F_2nd"] = np.where(okf, F2["F_2nd"], 0.0)
     out["F_2nd_mean"] = np.where(ok[:, :, None], F2["F_2nd_mean"], 0.0)
-    out["qtf"] = qtf
+    out["qtf"] = np.where(ok[:, :, None, None, None], qtf, 0.0)
     return out
 
 
@@ -482,9 +533,10 @@ def pinned_empty(shape, dtype):
 class DeviceSession:
     """Tables, workspace and outputs resident in HBM (torch tensors); kernels on torch's current stream."""
 
-    def __init__(self, batch, cases, device=None, want=("Xi", "status", "B_drag"), workspace_bytes=None, tables=False):
+    def __init__(self, batch, cases, device=None, want=("Xi", "status", "B_drag"), workspace_bytes=None, tables=False, out_tensors=None):
         """``tables=True`` sizes the workspace for ``excitation()`` / ``linearization()`` (global wave tables);
-        the default covers ``solve()`` only (the fused solver keeps its tables on chip)."""
+        the default covers ``solve()`` only (the fused solver keeps its tables on chip).  ``out_tensors``: outputs the
+        caller already owns (name -> tensor of the documented shape), e.g. this rank's block of a peer-shared array."""
         import torch
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -505,7 +557,11 @@ class DeviceSession:
                           B_drag=([nD, nC, 6, 6], torch.float64), F_drag=([nD, nC, 6, nw], torch.complex128),
                           F_iner=([nD, nC, 6, nw], torch.complex128), F_BEM=([nD, nC, 6, nw], torch.complex128),
                           zeta=([nC, nw], torch.float64))
-            self.out = {k: torch.zeros(shapes[k][0], dtype=shapes[k][1], device=self.device) for k in want}
+            given = dict(out_tensors or {})
+            for k, t in given.items():
+                if tuple(t.shape) != tuple(shapes[k][0]) or t.dtype != shapes[k][1] or not t.is_contiguous():
+                    raise ValueError("out_tensors[%r] must be a contiguous %s tensor of shape %s" % (k, shapes[k][1], shapes[k][0]))
+            self.out = {k: (given[k] if k in given else torch.zeros(shapes[k][0], dtype=shapes[k][1], device=self.device)) for k in want}
             self.o_struct = _out_struct(self.out, lambda t: t.data_ptr())
 
     def _stream(self):
@@ -519,6 +575,16 @@ class DeviceSession:
                                                C.byref(self.o_struct), self.workspace.data_ptr(), self.workspace_bytes,
                                                self._stream()))
         return self.out
+
+    def solve_gather(self, peers, o_struct=None, n_iter=10, tol=0.01, xi_start=0.0, cluster_size=0, timeout_flag=None):
+        """``solve`` with the multi-GPU exchange fused into the kernel (``raft_b200.sweep.PeerExchange``): every finished
+        unit is stored into all ranks' gathered arrays over NVLink, then the stream waits for the peers' arrival flags."""
+        o = RaftkSolveOpts(int(n_iter), int(cluster_size), float(tol), float(xi_start))
+        os_ = self.o_struct if o_struct is None else o_struct
+        with self.torch.cuda.device(self.device):
+            check(lib.raftk_solve_dynamics_gather_dev(C.byref(self.d_struct), C.byref(self.c_struct), C.byref(o), C.byref(os_),
+                                                      C.byref(peers), self.workspace.data_ptr(), self.workspace_bytes, self._stream()))
+            check(lib.raftk_peer_barrier_dev(C.byref(peers), timeout_flag, self._stream()))
 
     def second_order_force(self):
         """Enqueue FOWT.calcHydroForce_2ndOrd for all units -> out['F_2nd'], out['F_2nd_mean'] (async)."""

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SYMBOLS) == declared
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.raftk_version() == 120
+    assert _lib.lib.raftk_version() == 130
 
 
 def test_struct_layout_matches_header(tmp_path):
