@@ -340,6 +340,59 @@ def fixture_flexible(name, yaml_path, pickles):
     print("%-28s nDOF=%3d Ns=%3d  %.1f s  %.0f KB" % (name, int(P["gen_nDOF"]), len(P["node_ls"]), time.time() - t0, os.path.getsize(path) / 1024))
 
 
+def fixture_farm(name, yaml_path, nw, max_freq, cases, seed=5):
+    """Coupled 6N-DOF farm (raft_model.py:1164-1236) run by the UNMODIFIED reference: SURVEY.md 8c recipe -- array rows with
+    turbineID = mooringID = 0, array_mooring dropped, ``model.ms`` replaced by an object whose getCoupledStiffnessA returns a
+    seeded SPD array-mooring stiffness, moorMod 0.  Stores every FOWT's packed tables (P<i>_*), the coupling matrix and
+    Model.Xi [nH+1, 6N, nw] per case."""
+    import yaml
+    t0 = time.time()
+    with open(yaml_path) as f:
+        design = yaml.load(f, Loader=yaml.FullLoader)
+    for k in ("turbine", "turbines", "mooring", "array_mooring"):
+        design.pop(k, None)
+    design["platform"]["potSecOrder"] = 0
+    ks = design["array"]["keys"]
+    for row in design["array"]["data"]:
+        row[ks.index("turbineID")] = 0
+        row[ks.index("mooringID")] = 0
+    design["settings"]["max_freq"] = float(max_freq)
+    design["settings"]["min_freq"] = float(max_freq) / nw
+    model = rh.build_model(design)
+    n = model.nDOF
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(n, n)) * 2e4
+    C_arr = A @ A.T / n + np.diag([5e4] * n)
+
+    class _MS:
+        def getCoupledStiffnessA(self, lines_only=True):
+            return C_arr
+    model.ms, model.moorMod = _MS(), 0
+    out = dict(C_array=C_arr, n_fowt=np.int32(model.nFOWT), n_iter=np.int32(int(model.nIter)), xi_start=np.float64(model.XiStart),
+               cases=np.array(cases, dtype=float), array_xyh=np.array([[f.x_ref, f.y_ref, f.heading_adjust] for f in model.fowtList], dtype=float))
+    plat = {k: v for k, v in design["platform"].items() if k not in ("hydroPath",)}
+    DESIGNS[name] = _plain(dict(settings=design.get("settings", {}), site=design["site"], platform=plat, array=design["array"]))
+    counters = [count_passes(f) for f in model.fowtList]
+    Xi, passes = [], []
+    for (Hs, Tp, beta) in cases:
+        for c, _ in counters:
+            c[0] = 0
+        x = rh.solve_dynamics(model, rh.make_case(Hs, Tp, beta))
+        Xi.append(np.array(x))
+        passes.append([c[0] for c, _ in counters])
+    for f, (_, orig) in zip(model.fowtList, counters):
+        f.calcHydroLinearization = orig
+    out["ref_run_Xi"] = np.array(Xi)                                   # [nCases, nH+1, 6N, nw]
+    out["ref_run_passes"] = np.array(passes, dtype=np.int32)           # [nCases, nFOWT]
+    for i, f in enumerate(model.fowtList):
+        P = packer.pack_fowt(f)
+        out.update({"P%d_%s" % (i, k): np.asarray(v) for k, v in P.items()})
+        out["C_moor%d" % i] = np.array(f.C_moor)
+        out["A_hydro_morison%d" % i] = np.array(f.A_hydro_morison)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("%s: %d FOWTs, nw %d, %d cases, passes %s (%.1f s)" % (name, model.nFOWT, model.nw, len(cases), passes, time.time() - t0))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -384,6 +437,9 @@ def main():
     if not args.only or args.only in "slender_VolturnUS-S":
         fixture_slender("slender_VolturnUS-S", os.path.join(td, "VolturnUS-S.yaml"), os.path.join(td, "VolturnUS-S_true_calcQTF_slenderBody.pkl"),
                         solve_cases=[(6.0, 12.0, 30.0), (2.0, 7.5, -75.0), (9.0, 15.0, 160.0)])
+    if not args.only or args.only in "farm_VolturnUS-S_farm_nw48":
+        fixture_farm("farm_VolturnUS-S_farm_nw48", os.path.join(REF, "designs", "VolturnUS-S_farm.yaml"), nw=48, max_freq=0.1024,
+                     cases=[(6.0, 12.0, 0.0), (3.5, 9.0, 40.0), (8.0, 14.0, -120.0)])
     if not args.only or args.only in "turb_VolturnUS-S":
         fixture_turbine("turb_VolturnUS-S", os.path.join(td, "VolturnUS-S.yaml"))
     if not args.only:
@@ -397,9 +453,12 @@ def main():
         np.savez_compressed(os.path.join(OUT, "wamit_marin_semi.npz"), A=A, B=B, w1=w1, Re=Re.astype(np.float64),
                             Im=Im.astype(np.float64), w3=w3, heads=heads, qtf_rows=qtf_rows.astype(np.float32))
         print("wamit_marin_semi.npz %.0f KB" % (os.path.getsize(os.path.join(OUT, "wamit_marin_semi.npz")) / 1024))
-        import json
-        with open(os.path.join(OUT, "designs.json"), "w") as f:
-            json.dump(DESIGNS, f, indent=0, sort_keys=True)
+    import json
+    dj = os.path.join(OUT, "designs.json")
+    merged = json.load(open(dj)) if (args.only and os.path.exists(dj)) else {}
+    merged.update(DESIGNS)                                   # --only: refresh that fixture's entry, keep the others
+    with open(dj, "w") as f:
+        json.dump(merged, f, indent=0, sort_keys=True)
 
 
 if __name__ == "__main__":
