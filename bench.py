@@ -367,8 +367,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     if args.workload in ("farm", "flex"):
-        from raft_b200 import workloads
-        workloads.bench_special(args, rank, world, dev)
+        import bench_extra
+        bench_extra.bench_special(args, rank, world, dev)
         if world > 1:
             dist.destroy_process_group()
         return

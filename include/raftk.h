@@ -144,7 +144,15 @@ typedef struct raftk_solve_opts {
     int32_t cluster_size;    /* CTAs per (design,case): 0 = auto, else 1,2,4,8                  */
     double tol;              /* 0.01                                                            */
     double xi_start;         /* settings.XiStart                                                */
+    int32_t flags;           /* RAFTK_SOLVE_* bits, 0 = none                                    */
+    int32_t _pad0;
 } raftk_solve_opts;
+
+/* raftk_solve_opts.flags.  REUSE_PLAN (raftk_*_dev only): the caller asserts that the design tables, the case count and the
+ * workspace are exactly those of its previous solve call -- the per-design plan blobs (step classes, staged tables: a
+ * pre-pass over the designs like the reference's calcHydroConstants, independent of the load cases' sea states) are then
+ * still in the workspace and k_fused_plan is not launched again. */
+enum { RAFTK_SOLVE_REUSE_PLAN = 1 };
 
 /* Outputs.  Any pointer may be NULL (that output is skipped) except Xi/status where noted. */
 typedef struct raftk_outputs {
@@ -348,6 +356,32 @@ int raftk_solve_dynamics_host(const raftk_designs *d, const raftk_cases *c, cons
 int raftk_system_solve_dev(int32_t n, int32_t nw, int32_t nrhs, double *Z, double *F, int32_t *info,
                            void *stream);
 int raftk_system_solve_host(int32_t n, int32_t nw, int32_t nrhs, double *Z, double *F, int32_t *info);
+
+/*
+ * Farm system response computed on the device from the per-FOWT solves (raft_model.py:1164-1236): the designs of the
+ * batch are the N FOWTs of the array (each at its own x_ref / y_ref), the drag linearisation of every FOWT runs as in
+ * raftk_solve_dynamics_*, then for every case and frequency
+ *     Z_sys = blockdiag_i( -w^2 (M0_i + A_w,i) + i w (B0_i + B_drag_i + B_w,i) + C0_i ) + ( -w^2 M_arr + i w B_arr + C_arr )
+ *     Xi_sys = Z_sys^-1 [ F_BEM_i + F_iner_i + F_drag_i (+ F_2nd_i) ]_i
+ * M_arr / B_arr / C_arr: array-level mooring matrices [6N,6N] row-major (model.ms.getCoupledStiffnessA for moorMod 0/1;
+ * getCoupledDynamicMatrices for moorMod 2), any may be NULL.  Xi_sys complex [nC, 6N, nw] (Model.Xi[ih] per case / train),
+ * info [nC, nw]: 0, or k+1 of the first zero pivot (numpy.linalg.inv raises LinAlgError there).
+ * _dev: `solved` holds the DEVICE outputs of a preceding raftk_solve_dynamics_dev of the same (d, c): B_drag, F_drag, F_iner
+ * (and F_BEM when the designs carry BEM excitation) are required.  _host: one call does both steps from host buffers;
+ * `out` may request any of the per-FOWT outputs as usual.
+ */
+typedef struct raftk_farm {
+    int32_t n_fowt;          /* must equal designs.n_designs                                    */
+    int32_t _pad0;
+    const double *M_arr, *B_arr, *C_arr;
+    double *Xi_sys;
+    int32_t *info;
+} raftk_farm;
+
+int raftk_farm_response_dev(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *solved, const raftk_farm *f,
+                            void *stream);
+int raftk_solve_dynamics_farm_host(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o,
+                                   const raftk_outputs *out, const raftk_farm *f);
 
 /*
  * Response statistics of FOWT.saveTurbineOutputs (raft_fowt.py:2299-2353) as reductions over Xi:

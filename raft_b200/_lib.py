@@ -43,7 +43,8 @@ class RaftkCases(C.Structure):
 
 
 class RaftkSolveOpts(C.Structure):
-    _fields_ = [("n_iter", C.c_int32), ("cluster_size", C.c_int32), ("tol", C.c_double), ("xi_start", C.c_double)]
+    _fields_ = [("n_iter", C.c_int32), ("cluster_size", C.c_int32), ("tol", C.c_double), ("xi_start", C.c_double),
+                ("flags", C.c_int32), ("_pad0", C.c_int32)]
 
 
 class RaftkOutputs(C.Structure):
@@ -60,6 +61,12 @@ class RaftkPeers(C.Structure):
     _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint32), ("_pad0", C.c_int32),
                 ("block_elems", C.c_size_t), ("gathered", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS),
                 ("status", C.c_void_p * MAX_PEERS)]
+
+
+class RaftkFarm(C.Structure):
+    """include/raftk.h raftk_farm: array-level matrices and outputs of the coupled 6N-DOF system response."""
+    _fields_ = [("n_fowt", C.c_int32), ("_pad0", C.c_int32), ("M_arr", C.c_void_p), ("B_arr", C.c_void_p), ("C_arr", C.c_void_p),
+                ("Xi_sys", C.c_void_p), ("info", C.c_void_p)]
 
 
 SLENDER_ARRAYS = ("w", "k", "mem_q", "mem_p1", "mem_p2", "mem_mcf", "mem_wl", "mem_r_int", "mem_a_wl", "mem_rwl", "mem_R_wl", "mem_node_start",
@@ -95,6 +102,7 @@ SYMBOLS = [
     "raftk_fp64_peak_gflops",
     "raftk_peer_alloc", "raftk_peer_free", "raftk_peer_open", "raftk_peer_close",
     "raftk_solve_dynamics_gather_dev", "raftk_peer_barrier_dev",
+    "raftk_farm_response_dev", "raftk_solve_dynamics_farm_host",
 ]
 
 
@@ -165,6 +173,10 @@ def _load():
     lib.raftk_solve_dynamics_gather_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkSolveOpts), P(RaftkOutputs), P(RaftkPeers),
                                                     C.c_void_p, C.c_size_t, C.c_void_p]
     lib.raftk_peer_barrier_dev.argtypes = [P(RaftkPeers), C.c_void_p, C.c_void_p]
+    lib.raftk_farm_response_dev.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkOutputs), P(RaftkFarm), C.c_void_p]
+    lib.raftk_solve_dynamics_farm_host.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkSolveOpts), P(RaftkOutputs), P(RaftkFarm)]
+    lib.raftk_farm_response_dev.restype = C.c_int
+    lib.raftk_solve_dynamics_farm_host.restype = C.c_int
     for fn in ("raftk_peer_alloc", "raftk_peer_open", "raftk_peer_free", "raftk_peer_close", "raftk_solve_dynamics_gather_dev",
                "raftk_peer_barrier_dev"):
         getattr(lib, fn).restype = C.c_int

@@ -129,6 +129,7 @@ extern "C" long long raftk_launch_count(void) { return g_launches; }
 #include "raftk_common.cuh"
 #include "raftk_tables.cuh"
 #include "raftk_fused.cuh"
+#include "raftk_fused2.cuh"
 #include "raftk_qtf.cuh"
 #include "raftk_slender.cuh"
 #include "raftk_general.cuh"
@@ -408,6 +409,102 @@ static int run_fused(const raftk_designs *d, const raftk_cases *c, const raftk_s
     return fused_launch<256>(D, C, P, pl, units, st);
 }
 
+// ---- fused2 (two bins per thread, TMA-staged plan blob) planner / launcher --------------------------------------------
+struct F2Plan { int CS, nwl, nchunk, maxW, maxH, maxZ; size_t smem, blob, o_lin, o_E, o_A, o_plan, ws_bytes; };
+
+static bool fused2_plan(const raftk_designs *d, int n_cases, int requested_cs, F2Plan &pl)
+{
+    if (getenv("RAFTK_FORCE_V1") || getenv("RAFTK_FUSED_GEN1")) return false;      // A/B: first-generation fused kernel
+    if (d->max_nodes <= 0 || d->max_members <= 0) return false;
+    int cs;
+    if (requested_cs == 1 || requested_cs == 2 || requested_cs == 4 || requested_cs == 8) cs = requested_cs;
+    else { cs = 1; while (cs < 8 && (d->nw + cs - 1) / cs > 2 * F2_T) cs <<= 1; }
+    pl.CS = cs;
+    pl.nwl = (d->nw + cs - 1) / cs;
+    // two bins per thread pay when most threads own two: 192 < bins per CTA <= 256; otherwise the one-bin kernel runs
+    if (pl.nwl > 2 * F2_T || pl.nwl <= (3 * F2_T) / 2) return false;
+    pl.nchunk = (d->max_nodes + CHUNK_NODES - 1) / CHUNK_NODES;
+    pl.maxW = d->max_w_classes > 0 ? d->max_w_classes : d->max_nodes;
+    pl.maxH = d->max_h_classes > 0 ? d->max_h_classes : d->max_nodes;
+    pl.maxZ = d->max_z_classes > 0 ? std::min(d->max_z_classes, d->max_members) : d->max_members;
+    pl.smem = fused2_smem_bytes(d->max_members, d->max_nodes, pl.nchunk, pl.nwl, pl.maxW, pl.maxH, pl.maxZ);
+    if (pl.smem > (size_t)113 * 1024) return false;                               // two CTAs per SM
+    const size_t units = (size_t)d->n_designs * n_cases;
+    pl.blob = (size_t)plan_layout(d->max_members, d->max_nodes, pl.maxW, pl.maxH, pl.maxZ).total;
+    size_t o = align_up(units * 6 * d->nw * sizeof(double2), 256);                 // F0 (same place as the first-generation kernel)
+    pl.o_lin = o; o += align_up(units * ((size_t)NCOEF * d->max_nodes + 36) * sizeof(double), 256);
+    pl.o_E = o; o += align_up(units * (size_t)d->max_members * d->nw * sizeof(double2), 256);
+    pl.o_A = o; o += align_up(units * (size_t)pl.maxZ * d->nw * sizeof(double2), 256);
+    pl.o_plan = o; o += align_up((size_t)d->n_designs * pl.blob * sizeof(double), 256);
+    pl.ws_bytes = o;
+    return true;
+}
+
+static int run_fused2(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o, const raftk_outputs *out,
+                      const F2Plan &pl, void *workspace, cudaStream_t st, const raftk_peers *peers)
+{
+    prof_begin_call();
+    DesignsDev D = to_dev(d, d->max_nodes, d->max_members);
+    CasesDev C = to_dev(c);
+    char *ws = static_cast<char *>(workspace);
+    FusedParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_iter = o->n_iter; P.CS = pl.CS; P.nwl = pl.nwl; P.maxW = pl.maxW; P.maxH = pl.maxH; P.maxZ = pl.maxZ;
+    P.tol = o->tol; P.xi_start = o->xi_start;
+    P.Xi_out = reinterpret_cast<double2 *>(out->Xi);
+    P.Fdrag_out = reinterpret_cast<double2 *>(out->F_drag);
+    P.Finer_out = reinterpret_cast<double2 *>(out->F_iner);
+    P.Fbem_out = reinterpret_cast<double2 *>(out->F_BEM);
+    P.Bdrag_out = out->B_drag; P.zeta_out = out->zeta; P.status = out->status;
+    P.Xilast_out = reinterpret_cast<double2 *>(out->Xi_last);
+    P.Xi_init = reinterpret_cast<const double2 *>(c->Xi_init);
+    P.F0g = reinterpret_cast<double2 *>(ws);
+    P.lin_g = nullptr; P.phase = -1;
+    P.Eg = reinterpret_cast<double2 *>(ws + pl.o_E);
+    P.Ag = reinterpret_cast<double2 *>(ws + pl.o_A);
+    double *plan = reinterpret_cast<double *>(ws + pl.o_plan);
+    P.plan = plan; P.plan_stride = pl.blob;
+    if (peers && peers->n_ranks > 1) {
+        P.n_peers = peers->n_ranks; P.peer_rank = peers->rank;
+        const size_t units_per_rank = peers->block_elems / ((size_t)6 * d->nw);
+        for (int p = 0; p < peers->n_ranks; p++) {
+            P.peer_Xi[p] = reinterpret_cast<double2 *>(peers->gathered[p]) + (size_t)peers->rank * peers->block_elems;
+            P.peer_status[p] = peers->status[p] ? peers->status[p] + (size_t)peers->rank * units_per_rank * 4 : nullptr;
+        }
+    }
+    if (!(o->flags & RAFTK_SOLVE_REUSE_PLAN)) {
+        ProfScope ps(st, 0);
+        const size_t psm = (3 * (size_t)d->max_nodes + d->max_members) * sizeof(double) + (2 * (size_t)d->max_nodes + 2 * d->max_members) * sizeof(int);
+        k_fused_plan<<<d->n_designs, 128, psm, st>>>(D, plan, pl.blob, pl.maxW, pl.maxH, pl.maxZ, pl.nwl);
+        g_launches++;
+    }
+    static SmemOptIn opt;
+    CUDA_TRY(opt.ensure(k_rao_fused2, pl.smem));
+    const int units = d->n_designs * c->n_cases;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)((size_t)units * pl.CS), 1, 1);
+    cfg.blockDim = dim3(F2_T, 1, 1);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pl.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const int nphase = c->primary ? 2 : 1;
+    if (c->primary) P.lin_g = reinterpret_cast<double *>(ws + pl.o_lin);
+    for (int phase = 0; phase < nphase; phase++) {
+        P.phase = c->primary ? phase : -1;
+        {
+            ProfScope ps(st, 2);
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, k_rao_fused2, D, C, P));
+        }
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return RAFTK_OK;
+}
+
 static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o, const raftk_outputs *out,
                const double *Xi_in, int mode /*0 solve, 1 linearise, 2 excitation only*/, bool do_excitation,
                void *workspace, size_t wbytes, cudaStream_t st, const raftk_peers *peers = nullptr)
@@ -416,6 +513,9 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
     if (rc) return rc;
     const int nD = d->n_designs, nC = c->n_cases, nw = d->nw;
     if (mode == 0) {                                   // fused on-chip solver when the slice fits in shared memory
+        F2Plan f2;
+        if (fused2_plan(d, nC, o ? o->cluster_size : 0, f2) && workspace && wbytes >= f2.ws_bytes)
+            return run_fused2(d, c, o, out, f2, workspace, st, peers);
         FPlan fp;
         const bool have_ws = workspace && wbytes >= (size_t)nD * nC * 6 * nw * sizeof(double2);
         if (fused_plan(d, nD * nC, o ? o->cluster_size : 0, have_ws, fp)) return run_fused(d, c, o, out, fp, workspace, wbytes, st, peers);
@@ -503,6 +603,8 @@ static int run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_o
 extern "C" size_t raftk_solve_workspace_bytes(const raftk_designs *d, int32_t n_cases)
 {
     if (!d || d->n_designs <= 0 || n_cases <= 0) return 0;
+    F2Plan f2;
+    if (fused2_plan(d, n_cases, 0, f2)) return f2.ws_bytes;
     FPlan fp;
     if (d->max_nodes > 0 && d->max_members > 0 && fused_plan(d, d->n_designs * n_cases, 0, true, fp))
         return align_up((size_t)d->n_designs * n_cases * 6 * d->nw * sizeof(double2), 256)
@@ -629,6 +731,44 @@ extern "C" int raftk_system_solve_dev(int32_t n, int32_t nw, int32_t nrhs, doubl
     return RAFTK_OK;
 }
 
+static int farm_launch(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *solved, const raftk_farm *f, cudaStream_t st)
+{
+    if (!d || !c || !solved || !f) return set_err(RAFTK_EINVAL, "farm response: null argument");
+    if (f->n_fowt != d->n_designs || f->n_fowt < 1) return set_err(RAFTK_EINVAL, "farm response: farm.n_fowt must equal designs.n_designs");
+    if (!solved->B_drag || !solved->F_drag || !solved->F_iner || !f->Xi_sys)
+        return set_err(RAFTK_EINVAL, "farm response needs B_drag, F_drag, F_iner of the per-FOWT solve and farm.Xi_sys");
+    if (d->n_bem_head > 0 && !solved->F_BEM) return set_err(RAFTK_EINVAL, "farm response: the designs carry BEM excitation, F_BEM is required");
+    const int n = 6 * f->n_fowt;
+    const size_t smem = (size_t)n * (n + 1) * sizeof(double2);
+    if (smem > 227 * 1024) return set_err(RAFTK_EINVAL, "farm too large for the shared-memory solver (6N (6N+1) 16 B > 227 KB: N <= 19)");
+    if (c->n_cases > 65535) return set_err(RAFTK_EINVAL, "farm response: more than 65535 cases per call");
+    static SmemOptIn opt(48 * 1024);
+    CUDA_TRY(opt.ensure(k_farm_response, smem));
+    DesignsDev D = to_dev(d, d->max_nodes, d->max_members);
+    CasesDev C = to_dev(c);
+    FarmParams P;
+    P.N = f->n_fowt; P.nC = c->n_cases; P.nw = d->nw;
+    P.B_drag = solved->B_drag;
+    P.F_drag = reinterpret_cast<const double2 *>(solved->F_drag);
+    P.F_iner = reinterpret_cast<const double2 *>(solved->F_iner);
+    P.F_BEM = d->n_bem_head > 0 ? reinterpret_cast<const double2 *>(solved->F_BEM) : nullptr;
+    P.M_arr = f->M_arr; P.B_arr = f->B_arr; P.C_arr = f->C_arr;
+    P.Xi = reinterpret_cast<double2 *>(f->Xi_sys); P.info = f->info;
+    {
+        ProfScope ps(st, 1);
+        k_farm_response<<<dim3(d->nw, c->n_cases), 128, smem, st>>>(D, C, P);
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RAFTK_OK;
+}
+
+extern "C" int raftk_farm_response_dev(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *solved, const raftk_farm *f,
+                                       void *stream)
+{
+    return farm_launch(d, c, solved, f, (cudaStream_t)stream);
+}
+
 // ---- host-pointer front ends -------------------------------------------------------------------------
 // temporary device allocation released on every exit path of the small *_host wrappers
 struct DevBuf {
@@ -718,7 +858,7 @@ static size_t in_bytes(const raftk_designs *d, const raftk_cases *c)
 }
 
 static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o, const raftk_outputs *out,
-                    const double *Xi_in, int mode)
+                    const double *Xi_in, int mode, const raftk_farm *farm = nullptr)
 {
     int rc = validate(d, c);
     if (rc) return rc;
@@ -733,9 +873,17 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     const bool qtf_solve = (mode == 0 && d->n_qtf_w > 0 && !c->F_2nd);   // potSecOrder 2: compute the force on the device first
     if (qtf_solve) obytes += align_up(resp / 2, 256) + align_up(nD * nC * 48, 256);
     if (Xi_in) obytes += align_up(resp, 256);
+    if (farm) {
+        // the system response reads the per-FOWT loads on the device: those buffers exist even when the caller does not want them back
+        obytes += 4 * align_up(resp, 256) + align_up(nD * nC * 288, 256) + align_up(nC * nw * 4, 256) + 3 * align_up(36 * nD * nD * 8, 256);
+    }
     size_t wb = raftk_workspace_bytes(d, (int32_t)nC);
     if (mode != 0) wb = chunk_bytes((int)nD, (int)nC, d->max_nodes, (int)nw);   // single chunk required
-    else { FPlan fp; if (fused_plan(d, (int)(nD * nC), o ? o->cluster_size : 0, true, fp)) wb = raftk_solve_workspace_bytes(d, (int32_t)nC); }
+    else {
+        F2Plan f2; FPlan fp;
+        if (fused2_plan(d, (int)nC, o ? o->cluster_size : 0, f2)) wb = f2.ws_bytes;
+        else if (fused_plan(d, (int)(nD * nC), o ? o->cluster_size : 0, true, fp)) wb = raftk_solve_workspace_bytes(d, (int32_t)nC);
+    }
     const size_t total = SMALL_REGION + in_bytes(d, c) + obytes + align_up(wb, 256) + 4096;
     Arena &A = g_arena[cur_dev()];
     if (A.reserve(total)) return set_err(RAFTK_ENOMEM, "device arena allocation failed");
@@ -776,6 +924,15 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
         dd.qtf = up(A, d->qtf, (d->qtf_shared == 1 ? 1 : (d->qtf_shared == 2 ? nD * nC : nD)) * (size_t)d->n_qtf_w * d->n_qtf_w * d->n_qtf_head * 12, st, e);
     }
     const double *Xi_in_d = up(A, Xi_in, Xi_in ? nD * nC * 6 * nw * 2 : 0, st, e);
+    raftk_farm fd;
+    memset(&fd, 0, sizeof(fd));
+    if (farm) {                                           // array-level matrices: staged with the other small inputs
+        fd = *farm;
+        const size_t nn = 36 * nD * nD;
+        fd.M_arr = up(A, farm->M_arr, farm->M_arr ? nn : 0, st, e);
+        fd.B_arr = up(A, farm->B_arr, farm->B_arr ? nn : 0, st, e);
+        fd.C_arr = up(A, farm->C_arr, farm->C_arr ? nn : 0, st, e);
+    }
     {
         cudaError_t r = flush_small(A, st);
         if (r != cudaSuccess) e = r;
@@ -785,10 +942,10 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
     memset(&od, 0, sizeof(od));
     if (out->Xi) od.Xi = static_cast<double *>(A.take(resp));
     if (out->status) od.status = static_cast<int32_t *>(A.take(nD * nC * 16));
-    if (out->B_drag) od.B_drag = static_cast<double *>(A.take(nD * nC * 288));
-    if (out->F_drag) od.F_drag = static_cast<double *>(A.take(resp));
-    if (out->F_iner) od.F_iner = static_cast<double *>(A.take(resp));
-    if (out->F_BEM) od.F_BEM = static_cast<double *>(A.take(resp));
+    if (out->B_drag || farm) od.B_drag = static_cast<double *>(A.take(nD * nC * 288));
+    if (out->F_drag || farm) od.F_drag = static_cast<double *>(A.take(resp));
+    if (out->F_iner || farm) od.F_iner = static_cast<double *>(A.take(resp));
+    if (out->F_BEM || (farm && d->n_bem_head > 0)) od.F_BEM = static_cast<double *>(A.take(resp));
     if (out->zeta) od.zeta = static_cast<double *>(A.take(nC * nw * 8));
     if (out->Xi_last) od.Xi_last = static_cast<double *>(A.take(resp));
     if (qtf_solve) {
@@ -806,11 +963,18 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
         if (!rc) rc = run(&dd, &cc, nullptr, &od, Xi_in_d, 1, false, ws, wb, st);
     }
     if (rc) return rc;
+    if (farm) {
+        fd.Xi_sys = static_cast<double *>(A.take(resp));
+        fd.info = farm->info ? static_cast<int32_t *>(A.take(nC * nw * 4)) : nullptr;
+        rc = farm_launch(&dd, &cc, &od, &fd, st);
+        if (rc) return rc;
+    }
     auto down = [&](void *h, const void *dv, size_t n) { if (h && dv) { cudaError_t r = cudaMemcpyAsync(h, dv, n, cudaMemcpyDeviceToHost, st); if (r != cudaSuccess) e = r; } };
     down(out->Xi, od.Xi, resp); down(out->status, od.status, nD * nC * 16); down(out->B_drag, od.B_drag, nD * nC * 288);
     down(out->F_drag, od.F_drag, resp); down(out->F_iner, od.F_iner, resp); down(out->F_BEM, od.F_BEM, resp);
     down(out->zeta, od.zeta, nC * nw * 8);
     down(out->F_2nd, od.F_2nd, resp / 2); down(out->F_2nd_mean, od.F_2nd_mean, nD * nC * 48); down(out->Xi_last, od.Xi_last, resp);
+    if (farm) { down(farm->Xi_sys, fd.Xi_sys, resp); down(farm->info, fd.info, nC * nw * 4); }
     cudaError_t se = cudaStreamSynchronize(st);
     if (e != cudaSuccess || se != cudaSuccess)
         return set_err(RAFTK_ECUDA, "kernel/D2H: %s", cudaGetErrorString(se != cudaSuccess ? se : e));
@@ -830,6 +994,15 @@ extern "C" int raftk_solve_dynamics_host(const raftk_designs *d, const raftk_cas
 {
     if (!out || !out->Xi || !out->status || !o) return set_err(RAFTK_EINVAL, "Xi, status and opts are required");
     return host_run(d, c, o, out, nullptr, 0);
+}
+
+extern "C" int raftk_solve_dynamics_farm_host(const raftk_designs *d, const raftk_cases *c, const raftk_solve_opts *o,
+                                              const raftk_outputs *out, const raftk_farm *f)
+{
+    if (!out || !out->Xi || !out->status || !o) return set_err(RAFTK_EINVAL, "Xi, status and opts are required");
+    if (!f || !f->Xi_sys) return set_err(RAFTK_EINVAL, "farm.Xi_sys is required");
+    if (d && f->n_fowt != d->n_designs) return set_err(RAFTK_EINVAL, "farm response: farm.n_fowt must equal designs.n_designs");
+    return host_run(d, c, o, out, nullptr, 0, f);
 }
 
 extern "C" int raftk_second_order_force_host(const raftk_designs *d, const raftk_cases *c, const raftk_outputs *out)
@@ -917,6 +1090,14 @@ extern "C" int raftk_general_solve_dynamics_dev(const raftk_general *g, const ra
     cudaStream_t st = (cudaStream_t)stream;
     double2 *X = reinterpret_cast<double2 *>(Xi);
     const unsigned fb = (unsigned)((g->nw + 127) / 128);
+    // blocked LU (panel + row block in shared memory); RAFTK_GEN_UNBLOCKED=1 keeps the first, column-at-a-time kernel for A/B runs
+    const size_t lu_smem = ((size_t)g->n_dof * GB + (size_t)GB * (g->n_dof + 1)) * sizeof(double2);
+    const bool blocked = !getenv("RAFTK_GEN_UNBLOCKED") && lu_smem <= 110 * 1024;
+    if (blocked) {
+        static SmemOptIn opt(48 * 1024);
+        CUDA_TRY(opt.ensure(k_gen_solve_blocked, lu_smem));
+    }
+    prof_begin_call();
     k_gen_init<<<(unsigned)nC, 256, 0, st>>>(D, W, o->xi_start);
     if (g->n_nodes > 0) k_gen_wave<<<dim3(fb, g->n_nodes, (unsigned)nC), 128, 0, st>>>(D, C, W);
     k_gen_project<<<dim3(fb, g->n_dof, (unsigned)nC), 128, 0, st>>>(D, W, W.F_iner, 0);
@@ -925,7 +1106,13 @@ extern "C" int raftk_general_solve_dynamics_dev(const raftk_general *g, const ra
         if (g->n_nodes > 0) k_gen_node_pass<<<dim3(g->n_nodes, (unsigned)nC), 128, 0, st>>>(D, W);
         k_gen_bdrag<<<dim3(g->n_dof, (unsigned)nC), 128, 0, st>>>(D, W);
         k_gen_project<<<dim3(fb, g->n_dof, (unsigned)nC), 128, 0, st>>>(D, W, W.F_drag, 1);
-        k_gen_solve<<<dim3(g->nw, (unsigned)nC), 256, 0, st>>>(D, W, X, o->tol);
+        if (blocked) {
+            ProfScope ps(st, 2);
+            k_gen_solve_blocked<<<dim3(g->nw, (unsigned)nC), 256, lu_smem, st>>>(D, W, X, o->tol);
+        } else {
+            ProfScope ps(st, 2);
+            k_gen_solve<<<dim3(g->nw, (unsigned)nC), 256, 0, st>>>(D, W, X, o->tol);
+        }
         k_gen_relax<<<(unsigned)nC, 256, 0, st>>>(D, W, X);
         g_launches += 5;
     }

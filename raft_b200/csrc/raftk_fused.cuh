@@ -29,6 +29,9 @@ struct FusedParams {
     int phase;               // -1: every case is its own primary; 0: run primaries only; 1: run secondaries only
     // multi-GPU exchange fused into the epilogue (raftk_solve_dynamics_gather_dev): every finished unit's Xi / status
     // is also stored into the other ranks' gathered arrays through peer-mapped pointers (NVLink)
+    // k_rao_fused2 only: per-design plan blobs (k_fused_plan), member base phases / depth pairs in the workspace
+    const double *plan; size_t plan_stride;
+    double2 *Eg, *Ag;
     int n_peers, peer_rank;
     double2 *peer_Xi[RAFTK_MAX_PEERS];    // [p]: this rank's block inside rank p's gathered array, same indexing as Xi_out
     int *peer_status[RAFTK_MAX_PEERS];    // [p]: likewise for status, or NULL

@@ -1,6 +1,6 @@
-// raftk_general.cuh -- STAGED, NOT YET VALIDATED ON HARDWARE: Model.solveDynamics for FOWTs with generalised degrees
-// of freedom (flexible members, nDOF up to a few hundred; raft_fowt.py:1854-1857, 1886-1888, 1913-1929 and
-// raft_model.py:1052-1142) -- correctness-first kernels for the next row of SURVEY.md 8(f)  (included by raftk.cu only).
+// raftk_general.cuh -- Model.solveDynamics for FOWTs with generalised degrees of freedom (flexible members, nDOF up to 256;
+// raft_fowt.py:1854-1857, 1886-1888, 1913-1929 and raft_model.py:1052-1142)  (included by raftk.cu only).  Validated on
+// B200 against the reference's 150-DOF VolturnUS-S-flexible run (tests/test_general_dofs.py).
 //
 // The checker (oracle/raft_oracle.c: ro_general_*) is pinned to the reference's VolturnUS-S-flexible pickles and a 150-DOF
 // solveDynamics run; these kernels restate the same bookkeeping: every strip node j carries the 6 x n block Tn_j of fowt.T
@@ -283,6 +283,169 @@ __global__ void __launch_bounds__(256) k_gen_solve(GenDev D, GenWork W, double2 
             double2 v = A[(size_t)r * nc + b];
             v.x -= l.x * ak.x - l.y * ak.y; v.y -= l.x * ak.y + l.y * ak.x;
             A[(size_t)r * nc + b] = v;
+        }
+        __syncthreads();
+    }
+    // back substitution on the last column
+    for (int k = n - 1; k >= 0; k--) {
+        if (tid == 0) {
+            const double2 a = A[(size_t)k * nc + k], b = A[(size_t)k * nc + n];
+            const double dd = a.x * a.x + a.y * a.y;
+            A[(size_t)k * nc + n] = make_double2((b.x * a.x + b.y * a.y) / dd, (b.y * a.x - b.x * a.y) / dd);
+        }
+        __syncthreads();
+        const double2 x = A[(size_t)k * nc + n];
+        for (int r = tid; r < k; r += 256) {
+            const double2 a = A[(size_t)r * nc + k];
+            double2 b = A[(size_t)r * nc + n];
+            b.x -= a.x * x.x - a.y * x.y; b.y -= a.x * x.y + a.y * x.x;
+            A[(size_t)r * nc + n] = b;
+        }
+        __syncthreads();
+    }
+    int notconv = 0, nan = 0;
+    for (int a = tid; a < n; a += 256) {
+        const double2 x = A[(size_t)a * nc + n], l = W.XiLast[((size_t)c * n + a) * nw + i];
+        Xi[((size_t)c * n + a) * nw + i] = x;
+        if (isnan(x.x) || isnan(x.y)) nan = 1;
+        const double dx = x.x - l.x, dy = x.y - l.y;
+        if (!(sqrt(dx * dx + dy * dy) / (sqrt(x.x * x.x + x.y * x.y) + tol) < tol)) notconv = 1;     // raft_model.py:1101-1102
+    }
+    if (notconv) atomicOr(&W.flags[4 * c + 1], 1);
+    if (nan || bad) atomicOr(&W.flags[4 * c + 3], 1);
+}
+
+// k_gen_solve_blocked: grid (nw, nC), block 256.  Same system, same pivot rule and the same elimination order as
+// k_gen_solve, organised as a blocked right-looking LU (LAPACK zgetrf's structure) so that the work is done on chip:
+//   per block of GB columns:  panel (rows kb.., GB columns) factored in SHARED memory with partial pivoting; its row swaps
+//   applied to the rest of the rows; the GB x (rest) row block solved against the unit-lower panel head in shared memory;
+//   trailing update A22 -= L21 U12 with a 4 x 2 register tile per thread -- every A22 element is loaded once, receives its
+//   GB rank-1 contributions IN ELIMINATION ORDER (k ascending, the rounding sequence of the unblocked algorithm) and is
+//   stored once.  Traffic to the L2-resident matrix drops by GB (16) against the unblocked kernel's one pass per column;
+//   9 Mflop per 150 x 150 system then run from registers and shared memory.
+#define GB 16
+__global__ void __launch_bounds__(256, 2) k_gen_solve_blocked(GenDev D, GenWork W, double2 *Xi, double tol)
+{
+    extern __shared__ __align__(16) double smem_raw[];
+    __shared__ double pv[8];
+    __shared__ int pi_[8];
+    __shared__ double2 piv;
+    __shared__ int prow, bad;
+    __shared__ int pivrow[GB];
+    const int i = blockIdx.x, c = blockIdx.y, tid = threadIdx.x, n = D.n, nw = D.nw, nc = n + 1;
+    if (W.flags[4 * c]) return;
+    double2 *P = reinterpret_cast<double2 *>(smem_raw);          // panel  [n][GB]   (rows kb.. stored from 0)
+    double2 *U = P + (size_t)n * GB;                             // row block [GB][nc]
+    double2 *A = W.Z + ((size_t)c * nw + i) * (size_t)n * nc;
+    const double w = D.w[i], w2 = w * w;
+    const double *Bd = W.B_drag + (size_t)c * n * n;
+    for (int t = tid; t < n * n; t += 256) {
+        const int a = t / n, b = t % n;
+        A[(size_t)a * nc + b] = make_double2(fma(-w2, D.M[t], D.C[t]), w * (D.B[t] + Bd[t]));       // raft_model.py:1086
+    }
+    for (int a = tid; a < n; a += 256) {
+        const double2 f1 = W.F_iner[((size_t)c * n + a) * nw + i], f2 = W.F_drag[((size_t)c * n + a) * nw + i];
+        A[(size_t)a * nc + n] = make_double2(f1.x + f2.x, f1.y + f2.y);
+    }
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    for (int kb = 0; kb < n; kb += GB) {
+        const int nb = min(GB, n - kb), m = n - kb;
+        // ---- 1. panel into shared memory ------------------------------------------------------------------------
+        for (int t = tid; t < m * nb; t += 256) { const int r = t / nb, j = t % nb; P[r * GB + j] = A[(size_t)(kb + r) * nc + kb + j]; }
+        __syncthreads();
+        // ---- 2. unblocked LU of the panel (pivot on |re| + |im|, first maximum wins, like izamax) ---------------------
+        for (int j = 0; j < nb; j++) {
+            double best = -1.0; int bi = j;
+            for (int r = j + tid; r < m; r += 256) { const double2 v = P[r * GB + j]; const double mg = fabs(v.x) + fabs(v.y); if (mg > best) { best = mg; bi = r; } }
+            for (int o = 16; o >= 1; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if ((tid & 31) == 0) { pv[tid >> 5] = best; pi_[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                double b0 = pv[0]; int r0 = pi_[0];
+                for (int t = 1; t < 8; t++) if (pv[t] > b0 || (pv[t] == b0 && pi_[t] < r0)) { b0 = pv[t]; r0 = pi_[t]; }
+                prow = r0; pivrow[j] = r0;
+                if (!(b0 > 0.0)) bad = 1;
+            }
+            __syncthreads();
+            const int p = prow;
+            if (p != j && tid < nb) { const double2 t1 = P[j * GB + tid]; P[j * GB + tid] = P[p * GB + tid]; P[p * GB + tid] = t1; }
+            __syncthreads();
+            if (tid == 0) { const double2 a = P[j * GB + j]; const double dd = a.x * a.x + a.y * a.y; piv = make_double2(a.x / dd, -a.y / dd); }
+            __syncthreads();
+            const double2 ip = piv;
+            for (int r = j + 1 + tid; r < m; r += 256) { const double2 a = P[r * GB + j]; P[r * GB + j] = make_double2(a.x * ip.x - a.y * ip.y, a.x * ip.y + a.y * ip.x); }
+            __syncthreads();
+            const int cols = nb - j - 1;
+            for (int t = tid; t < (m - j - 1) * cols; t += 256) {
+                const int r = j + 1 + t / cols, b = j + 1 + t % cols;
+                const double2 l = P[r * GB + j], ak = P[j * GB + b];
+                double2 v = P[r * GB + b];
+                v.x -= l.x * ak.x - l.y * ak.y; v.y -= l.x * ak.y + l.y * ak.x;
+                P[r * GB + b] = v;
+            }
+            __syncthreads();
+        }
+        // ---- 3. panel back to the matrix; its row swaps applied, in order, to the columns outside the panel -------
+        for (int t = tid; t < m * nb; t += 256) { const int r = t / nb, j = t % nb; A[(size_t)(kb + r) * nc + kb + j] = P[r * GB + j]; }
+        for (int col = tid; col < nc; col += 256) {
+            if (col >= kb && col < kb + nb) continue;
+            for (int j = 0; j < nb; j++) {
+                const int p = pivrow[j];
+                if (p != j) { const double2 t1 = A[(size_t)(kb + j) * nc + col]; A[(size_t)(kb + j) * nc + col] = A[(size_t)(kb + p) * nc + col]; A[(size_t)(kb + p) * nc + col] = t1; }
+            }
+        }
+        __syncthreads();
+        // ---- 4. row block U12 = L11^-1 A12 (unit lower triangular solve per column, elimination order) -----------------
+        const int c0 = kb + nb, ncol = nc - c0;
+        for (int t = tid; t < nb * ncol; t += 256) { const int j = t / ncol, b = t % ncol; U[j * nc + b] = A[(size_t)(kb + j) * nc + c0 + b]; }
+        __syncthreads();
+        for (int b = tid; b < ncol; b += 256) {
+            for (int j = 0; j < nb; j++) {
+                const double2 uj = U[j * nc + b];
+                for (int r = j + 1; r < nb; r++) {
+                    const double2 l = P[r * GB + j];
+                    double2 v = U[r * nc + b];
+                    v.x -= l.x * uj.x - l.y * uj.y; v.y -= l.x * uj.y + l.y * uj.x;
+                    U[r * nc + b] = v;
+                }
+            }
+        }
+        __syncthreads();
+        for (int t = tid; t < nb * ncol; t += 256) { const int j = t / ncol, b = t % ncol; A[(size_t)(kb + j) * nc + c0 + b] = U[j * nc + b]; }
+        // ---- 5. trailing update A22 -= L21 U12: 4 x 2 register tile per thread, contributions in elimination order --
+        const int m2 = m - nb;
+        const int tr = (m2 + 3) / 4, tc = (ncol + 1) / 2;
+        for (int t = tid; t < tr * tc; t += 256) {
+            const int r0 = 4 * (t / tc), b0 = 2 * (t % tc);
+            double2 acc[4][2];
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 2; y++)
+                    acc[x][y] = (r0 + x < m2 && b0 + y < ncol) ? A[(size_t)(c0 + r0 + x) * nc + c0 + b0 + y] : make_double2(0.0, 0.0);
+            for (int j = 0; j < nb; j++) {
+                double2 l[4], u[2];
+#pragma unroll
+                for (int x = 0; x < 4; x++) l[x] = P[min(nb + r0 + x, m - 1) * GB + j];
+#pragma unroll
+                for (int y = 0; y < 2; y++) u[y] = U[j * nc + min(b0 + y, ncol - 1)];
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 2; y++) {
+                        acc[x][y].x -= l[x].x * u[y].x - l[x].y * u[y].y;
+                        acc[x][y].y -= l[x].x * u[y].y + l[x].y * u[y].x;
+                    }
+            }
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 2; y++)
+                    if (r0 + x < m2 && b0 + y < ncol) A[(size_t)(c0 + r0 + x) * nc + c0 + b0 + y] = acc[x][y];
         }
         __syncthreads();
     }

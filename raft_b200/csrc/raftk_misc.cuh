@@ -5,17 +5,12 @@
 // K3: dense complex solve per frequency (farm system response).  One CTA per frequency, matrix in
 // shared memory, LU with partial pivoting, nrhs right-hand sides.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_system_solve(int n, int nrhs, double2 *Z, double2 *F, int *info)
+// LU with partial pivoting (|re| + |im| metric, as LAPACK izamax) of the augmented system A [n][nc] (nc = n + nrhs) held in
+// shared memory, then back substitution of every right-hand side in place.  All threads of the CTA call it; returns k + 1
+// of the first zero pivot (0 = none) to thread 0.
+__device__ __forceinline__ int lu_solve_smem(double2 *A, int n, int nc, int nrhs, int *piv_s, double2 *rinv_s)
 {
-    extern __shared__ __align__(16) double smem_raw[];
-    double2 *A = reinterpret_cast<double2 *>(smem_raw);              // [n][n+nrhs] augmented
-    __shared__ int piv_s;
-    __shared__ double2 rinv_s;
-    const int iw = blockIdx.x, tid = threadIdx.x, nc = n + nrhs;
-    double2 *Zg = Z + (size_t)iw * n * n, *Fg = F + (size_t)iw * n * nrhs;
-    for (int t = tid; t < n * n; t += blockDim.x) A[(t / n) * nc + (t % n)] = Zg[t];
-    for (int t = tid; t < n * nrhs; t += blockDim.x) A[(t / nrhs) * nc + n + (t % nrhs)] = Fg[t];
-    __syncthreads();
+    const int tid = threadIdx.x;
     int bad = 0;
     for (int k = 0; k < n; k++) {
         if (tid < 32) {                                              // pivot search by warp 0
@@ -30,18 +25,18 @@ __global__ void __launch_bounds__(128) k_system_solve(int n, int nrhs, double2 *
                 if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
             }
             if (tid == 0) {
-                piv_s = p;
+                *piv_s = p;
                 const double2 pv = A[p * nc + k];
                 const double den = pv.x * pv.x + pv.y * pv.y;
-                rinv_s = (den > 0.0) ? make_double2(pv.x / den, -pv.y / den) : make_double2(0.0, 0.0);
-                if (!(den > 0.0)) bad = k + 1;
+                *rinv_s = (den > 0.0) ? make_double2(pv.x / den, -pv.y / den) : make_double2(0.0, 0.0);
+                if (!(den > 0.0) && bad == 0) bad = k + 1;
             }
         }
         __syncthreads();
-        const int p = piv_s;
+        const int p = *piv_s;
         if (p != k) for (int t = tid; t < nc; t += blockDim.x) { const double2 tmp = A[k * nc + t]; A[k * nc + t] = A[p * nc + t]; A[p * nc + t] = tmp; }
         __syncthreads();
-        const double2 ri = rinv_s;
+        const double2 ri = *rinv_s;
         for (int r = k + 1 + tid; r < n; r += blockDim.x) {
             const double2 v = A[r * nc + k];
             A[r * nc + k] = make_double2(v.x * ri.x - v.y * ri.y, v.x * ri.y + v.y * ri.x);
@@ -71,8 +66,79 @@ __global__ void __launch_bounds__(128) k_system_solve(int n, int nrhs, double2 *
         }
     }
     __syncthreads();
+    return bad;
+}
+
+__global__ void __launch_bounds__(128) k_system_solve(int n, int nrhs, double2 *Z, double2 *F, int *info)
+{
+    extern __shared__ __align__(16) double smem_raw[];
+    double2 *A = reinterpret_cast<double2 *>(smem_raw);              // [n][n+nrhs] augmented
+    __shared__ int piv_s;
+    __shared__ double2 rinv_s;
+    const int iw = blockIdx.x, tid = threadIdx.x, nc = n + nrhs;
+    double2 *Zg = Z + (size_t)iw * n * n, *Fg = F + (size_t)iw * n * nrhs;
+    for (int t = tid; t < n * n; t += blockDim.x) A[(t / n) * nc + (t % n)] = Zg[t];
+    for (int t = tid; t < n * nrhs; t += blockDim.x) A[(t / nrhs) * nc + n + (t % nrhs)] = Fg[t];
+    __syncthreads();
+    const int bad = lu_solve_smem(A, n, nc, nrhs, &piv_s, &rinv_s);
     for (int t = tid; t < n * nrhs; t += blockDim.x) Fg[t] = A[(t / nrhs) * nc + n + (t % nrhs)];
     if (tid == 0 && info) info[iw] = bad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b: farm system response straight from the per-FOWT solves (raft_model.py:1164-1236), one CTA per (frequency, case):
+// Z_sys = blockdiag_i(-w^2 (M0_i + A_w,i) + i w (B0_i + B_drag_i + B_w,i) + C0_i) + (-w^2 M_arr + i w B_arr + C_arr),
+// F = F_BEM_i + F_iner_i + F_drag_i (+ F_2nd_i) stacked, Xi_sys = Z_sys^-1 F.  Everything is read from device-resident
+// outputs of the drag-linearisation solve: no host assembly of Z, no per-case transfer of nw n^2 complex numbers.
+// ------------------------------------------------------------------------------------------------
+struct FarmParams {
+    int N, nC, nw;
+    const double *B_drag;                       // [N][nC][36]
+    const double2 *F_drag, *F_iner, *F_BEM;     // [N][nC][6][nw]; F_BEM may be NULL
+    const double *M_arr, *B_arr, *C_arr;        // [6N][6N] or NULL
+    double2 *Xi;                                // [nC][6N][nw]
+    int *info;                                  // [nC][nw] or NULL
+};
+
+__global__ void __launch_bounds__(128) k_farm_response(DesignsDev D, CasesDev Cs, FarmParams P)
+{
+    extern __shared__ __align__(16) double smem_raw[];
+    double2 *A = reinterpret_cast<double2 *>(smem_raw);              // [n][n+1]
+    __shared__ int piv_s;
+    __shared__ double2 rinv_s;
+    const int iw = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    const int n = 6 * P.N, nc = n + 1, nw = P.nw;
+    const double w = D.w[iw], w2 = w * w;
+    const int cp = Cs.primary ? Cs.primary[c] : c;                   // secondary wave trains use their primary's damping
+    for (int t = tid; t < n * n; t += blockDim.x) {
+        const int a = t / n, b = t % n, i = a / 6, j = b / 6;
+        double zr = 0.0, zi = 0.0;
+        if (i == j) {
+            const int e = 6 * (a - 6 * i) + (b - 6 * j);
+            double M = D.M0[(size_t)i * 36 + e], B = D.B0[(size_t)i * 36 + e] + P.B_drag[((size_t)i * P.nC + cp) * 36 + e];
+            if (D.A_w) { M += D.A_w[((size_t)i * 36 + e) * nw + iw]; B += D.B_w[((size_t)i * 36 + e) * nw + iw]; }
+            zr = fma(-w2, M, D.C0[(size_t)i * 36 + e]);
+            zi = w * B;
+        }
+        if (P.C_arr) zr += P.C_arr[t];
+        if (P.M_arr) zr -= w2 * P.M_arr[t];
+        if (P.B_arr) zi += w * P.B_arr[t];
+        A[a * nc + b] = make_double2(zr, zi);
+    }
+    for (int a = tid; a < n; a += blockDim.x) {
+        const int i = a / 6, e = a - 6 * i;
+        const size_t o = (((size_t)i * P.nC + c) * 6 + e) * nw + iw;
+        double2 f = P.F_drag[o];
+        const double2 g = P.F_iner[o];
+        f.x += g.x; f.y += g.y;
+        if (P.F_BEM) { const double2 h = P.F_BEM[o]; f.x += h.x; f.y += h.y; }
+        if (Cs.F_2nd) f.x += Cs.F_2nd[o];
+        A[a * nc + n] = f;
+    }
+    __syncthreads();
+    const int bad = lu_solve_smem(A, n, nc, 1, &piv_s, &rinv_s);
+    for (int a = tid; a < n; a += blockDim.x) P.Xi[((size_t)c * n + a) * nw + iw] = A[a * nc + n];
+    if (tid == 0 && P.info) P.info[(size_t)c * nw + iw] = bad;
 }
 
 // ------------------------------------------------------------------------------------------------

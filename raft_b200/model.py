@@ -31,7 +31,8 @@ class Model:
             mats = matrices if isinstance(matrices, (list, tuple)) else [matrices] * len(rows)
             for i, row in enumerate(rows):
                 info = dict(zip(keys, row))
-                d_i = dict(site=design["site"], platform=design["platforms"][int(info["platformID"]) - 1])
+                plats = design["platforms"] if "platforms" in design else [design["platform"]]     # raft_model.py:86-101
+                d_i = dict(site=design["site"], platform=plats[int(info["platformID"]) - 1])
                 self.fowtList.append(FOWT(d_i, self.w, depth=self.depth, x_ref=info["x_location"], y_ref=info["y_location"],
                                           heading_adjust=info.get("heading_adjust", 0), matrices=mats[i], k=self.k))
                 self.coords.append([info["x_location"], info["y_location"]])
@@ -61,8 +62,10 @@ class Model:
         return self.Xi
 
     # raft_model.py:264-433 (dynamics part) ---------------------------------------------------------------------
-    def analyzeCases(self, cases=None, tol=0.01, display=0):
-        """All load cases in ONE batched GPU call.  ``cases``: list of case dicts (default: the design's table).
+    def analyzeCases(self, display=0, meshDir=None, RAO_plot=False, cases=None, tol=0.01):
+        """All load cases in ONE batched GPU call.  Positional arguments as the reference's
+        ``analyzeCases(display=0, meshDir=..., RAO_plot=False)`` (raft_model.py:264; meshDir / RAO_plot concern the BEM mesh
+        and plotting, outside this path and ignored); ``cases=``: list of case dicts (default: the design's table).
         Fills results['freq_rad'], results['Xi'] [nCases, nDOF, nw], results['status'] [nCases, nFOWT, 4]."""
         if cases is None:
             keys = self.design["cases"]["keys"]
@@ -130,7 +133,13 @@ class Model:
         else:
             if batch.n_qtf_w:                                               # potSecOrder 2 (raft_model.py:1035-1038)
                 want += ("F_2nd", "F_2nd_mean")
-            o = solver.solve_dynamics(batch, ct, n_iter=self.nIter, tol=tol, xi_start=self.XiStart, want=want)
+            if self.nFOWT > 1 and self.C_array is not None:
+                # coupled array: per-FOWT linearisation + block assembly + 6N x 6N solve in one device call (raft_model.py:1164-1216)
+                o = solver.solve_dynamics_farm(batch, ct, C_arr=self.C_array, n_iter=self.nIter, tol=tol, xi_start=self.XiStart, want=want)
+                if np.any(o["info"]):
+                    raise np.linalg.LinAlgError("Singular matrix")          # np.linalg.inv at raft_model.py:1191
+            else:
+                o = solver.solve_dynamics(batch, ct, n_iter=self.nIter, tol=tol, xi_start=self.XiStart, want=want)
         if "primary" in table:                                              # secondary trains share their primary's B_drag
             o["B_drag"] = o["B_drag"][:, table["primary"]]
         st = o["status"][:, first]                                          # [nFOWT, nC, 4] (train 0 of every case)
@@ -151,8 +160,10 @@ class Model:
             f.Z = -w ** 2 * M + 1j * w * B + P["C0"][:, :, None]             # raft_model.py:1086, 1155 (last case)
         nT = ct.n_cases
         Xi_all = np.moveaxis(o["Xi"], 0, 1).reshape(nT, self.nDOF, self.nw)  # [nTrains, 6N, nw]
-        if self.nFOWT > 1 and self.C_array is not None:
-            # coupled system: Z_sys = blockdiag(Z_i) + C_array; F = Z_i Xi_i  (raft_model.py:1164-1216)
+        if "Xi_sys" in o:
+            Xi_all = o["Xi_sys"]                                            # coupled system response, computed on the device
+        elif self.nFOWT > 1 and self.C_array is not None:
+            # (slender-body QTF path) coupled system: Z_sys = blockdiag(Z_i) + C_array; F = Z_i Xi_i  (raft_model.py:1164-1216)
             Xi_all = self._couple(o, nT)
         Xi_trains = [Xi_all[owner == ic] for ic in range(nC)]
         return dict(Xi=Xi_all[first], Xi_trains=Xi_trains, status=np.moveaxis(st, 0, 1), Xi_all=Xi_all, owner=owner)

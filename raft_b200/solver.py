@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import RaftkCases, RaftkDesigns, RaftkGeneral, RaftkOutputs, RaftkSlender, RaftkSolveOpts, check, lib
+from ._lib import RaftkCases, RaftkDesigns, RaftkFarm, RaftkGeneral, RaftkOutputs, RaftkSlender, RaftkSolveOpts, check, lib
 
 _F8 = np.float64
 _I4 = np.int32
@@ -263,7 +263,7 @@ def solve_dynamics(batch, cases, n_iter=10, tol=0.01, xi_start=0.0, cluster_size
     outs = out if out is not None else _alloc_outputs(batch.n_designs, cases.n_cases, batch.nw, want)
     d = batch.struct(_host_ptr(batch.arrays))
     c = cases.struct(_host_ptr(cases.arrays))
-    o = RaftkSolveOpts(int(n_iter), int(cluster_size), float(tol), float(xi_start))
+    o = RaftkSolveOpts(int(n_iter), int(cluster_size), float(tol), float(xi_start), 0, 0)
     os_ = _out_struct(outs, lambda a: a.ctypes.data)
     check(lib.raftk_solve_dynamics_host(C.byref(d), C.byref(c), C.byref(o), C.byref(os_)))
     if np.any(outs["status"][..., 2] & FLAG_PLAN):
@@ -273,6 +273,38 @@ def solve_dynamics(batch, cases, n_iter=10, tol=0.01, xi_start=0.0, cluster_size
         check(lib.raftk_solve_dynamics_host(C.byref(d), C.byref(c), C.byref(o), C.byref(os_)))
         if np.any(outs["status"][..., 2] & FLAG_PLAN):
             raise _lib.RaftkError("step-class tables overflowed even with worst-case sizes")
+    return outs
+
+
+def solve_dynamics_farm(batch, cases, C_arr=None, M_arr=None, B_arr=None, n_iter=10, tol=0.01, xi_start=0.0, cluster_size=0,
+                        want=("Xi", "status", "B_drag")):
+    """Coupled farm response (raft_model.py:1164-1236), host buffers in/out, ONE call: the designs of ``batch`` are the N
+    FOWTs of the array; every FOWT's drag linearisation runs as in ``solve_dynamics``, then the 6N x 6N system
+    blockdiag(Z_i) + (-w^2 M_arr + i w B_arr + C_arr) is assembled and solved per (case, frequency) on the device.
+    -> the per-FOWT output dict plus ``Xi_sys`` complex [nC, 6N, nw] and ``info`` [nC, nw] (k+1 of a zero pivot)."""
+    N, nC, nw = batch.n_designs, cases.n_cases, batch.nw
+    n = 6 * N
+    want = tuple(dict.fromkeys(tuple(want) + ("Xi", "status")))
+    outs = _alloc_outputs(N, nC, nw, want)
+    mats = {}
+    for nm, v in (("M_arr", M_arr), ("B_arr", B_arr), ("C_arr", C_arr)):
+        if v is not None:
+            a = np.ascontiguousarray(v, dtype=_F8)
+            if a.shape != (n, n):
+                raise ValueError("%s must be [%d, %d]" % (nm, n, n))
+            mats[nm] = a
+    outs["Xi_sys"] = np.zeros([nC, n, nw], dtype=np.complex128)
+    outs["info"] = np.zeros([nC, nw], dtype=_I4)
+    f = RaftkFarm()
+    f.n_fowt = N
+    for nm in ("M_arr", "B_arr", "C_arr"):
+        setattr(f, nm, mats[nm].ctypes.data if nm in mats else None)
+    f.Xi_sys, f.info = outs["Xi_sys"].ctypes.data, outs["info"].ctypes.data
+    d = batch.struct(_host_ptr(batch.arrays))
+    c = cases.struct(_host_ptr(cases.arrays))
+    o = RaftkSolveOpts(int(n_iter), int(cluster_size), float(tol), float(xi_start), 0, 0)
+    os_ = _out_struct(outs, lambda a: a.ctypes.data)
+    check(lib.raftk_solve_dynamics_farm_host(C.byref(d), C.byref(c), C.byref(o), C.byref(os_), C.byref(f)))
     return outs
 
 
@@ -394,9 +426,64 @@ def solve_dynamics_slender(packed, cases, n_iter=10, tol=0.01, xi_start=0.0, clu
     return out
 
 
+def _general_struct(P, M, B, Cm, ptr_of):
+    """raftk_general for a packed flexible design; ``ptr_of(name, array)`` returns the address to store (host or device)."""
+    n, nw, Ns = int(P["gen_nDOF"]), len(P["w"]), len(P["node_ls"])
+    g = RaftkGeneral()
+    g.n_dof, g.nw, g.n_nodes = n, nw, Ns
+    g.depth, g.rho, g.dw = float(P["depth"]), float(P["rho"]), float(P["dw"])
+    mem = np.asarray(P["node_mem"], dtype=np.int64)
+    frame = np.concatenate([np.asarray(P["mem_q"])[mem], np.asarray(P["mem_p1"])[mem], np.asarray(P["mem_p2"])[mem]], axis=1) if Ns else np.zeros([0, 9])
+    cd = np.stack([np.asarray(P["node_a_q"]) * np.asarray(P["node_Cd_q"]), np.asarray(P["node_a_p1"]) * np.asarray(P["node_Cd_p1"]),
+                   np.asarray(P["node_a_p2"]) * np.asarray(P["node_Cd_p2"]), np.asarray(P["node_a_End"]) * np.asarray(P["node_Cd_End"])], axis=1) if Ns else np.zeros([0, 4])
+    arrays = dict(w=P["w"], k=P["k"], node_r=P["node_r"], node_frame=frame, node_circ=np.asarray(P["mem_circ"], dtype=_I4)[mem] if Ns else np.zeros(0, dtype=_I4),
+                  node_Imat=P["node_Imat"], node_a_i=P["node_a_i"], node_cd=cd, Tn=P["gen_Tn"], rr=P["gen_rr"], M=M, B=B, C=Cm)
+    if P.get("node_Imat_w") is not None:
+        arrays["node_Imat_w"] = np.ascontiguousarray(P["node_Imat_w"], dtype=np.complex128)
+    for name in _lib.GENERAL_ARRAYS:
+        if name not in arrays:
+            setattr(g, name, None)
+            continue
+        a = np.ascontiguousarray(arrays[name], dtype=_I4 if name == "node_circ" else (np.complex128 if name == "node_Imat_w" else _F8))
+        setattr(g, name, ptr_of(name, a))
+    return g
+
+
+class GeneralSession:
+    """Generalised-DOF solve with tables, workspace and outputs resident in HBM (torch tensors), kernels on torch's current
+    stream: ``solve()`` enqueues raftk_general_solve_dynamics_dev -> (Xi [nC,nDOF,nw] complex, status [nC,4])."""
+
+    def __init__(self, P, M, B, Cm, cases, device=None):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.keep = {}
+
+        def to_dev(name, a):
+            t = torch.from_numpy(a.view(np.float64) if a.dtype == np.complex128 else a).to(self.device)
+            self.keep[name] = t
+            return t.data_ptr()
+        with torch.cuda.device(self.device):
+            self.g = _general_struct(P, M, B, Cm, to_dev)
+            self.ct = {k: torch.from_numpy(v).to(self.device) for k, v in cases.arrays.items()}
+            self.c_struct = cases.struct(lambda name: self.ct[name].data_ptr())
+            n, nw, nC = int(P["gen_nDOF"]), len(P["w"]), cases.n_cases
+            self.workspace_bytes = int(lib.raftk_general_workspace_bytes(C.byref(self.g), nC))
+            self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+            self.Xi = torch.zeros([nC, n, nw], dtype=torch.complex128, device=self.device)
+            self.status = torch.zeros([nC, 4], dtype=torch.int32, device=self.device)
+
+    def solve(self, n_iter=10, tol=0.01, xi_start=0.0):
+        o = RaftkSolveOpts(int(n_iter), 0, float(tol), float(xi_start), 0, 0)
+        with self.torch.cuda.device(self.device):
+            check(lib.raftk_general_solve_dynamics_dev(C.byref(self.g), C.byref(self.c_struct), C.byref(o), self.Xi.data_ptr(), self.status.data_ptr(),
+                                                       self.workspace.data_ptr(), self.workspace_bytes, self.torch.cuda.current_stream(self.device).cuda_stream))
+        return self.Xi, self.status
+
+
 def general_solve_dynamics(P, M, B, Cm, cases, n_iter=10, tol=0.01, xi_start=0.0):
-    """STAGED -- not yet validated on hardware.  Model.solveDynamics for one FOWT with generalised degrees of freedom
-    (flexible members): ``P`` from ``packer.pack_general_dofs`` (node tables + ``gen_Tn``, ``gen_rr``), constant system
+    """Model.solveDynamics for one FOWT with generalised degrees of freedom (flexible members), host buffers:
+    ``P`` from ``packer.pack_general_dofs`` (node tables + ``gen_Tn``, ``gen_rr``), constant system
     matrices ``M, B, Cm`` [nDOF,nDOF], ``cases`` a CaseTable -> (Xi complex [nC,nDOF,nw], status [nC,4])."""
     n, nw, Ns = int(P["gen_nDOF"]), len(P["w"]), len(P["node_ls"])
     keep = {}
@@ -423,7 +510,7 @@ def general_solve_dynamics(P, M, B, Cm, cases, n_iter=10, tol=0.01, xi_start=0.0
     Xi = np.zeros([nC, n, nw], dtype=np.complex128)
     st = np.zeros([nC, 4], dtype=_I4)
     c = cases.struct(_host_ptr(cases.arrays))
-    o = RaftkSolveOpts(int(n_iter), 0, float(tol), float(xi_start))
+    o = RaftkSolveOpts(int(n_iter), 0, float(tol), float(xi_start), 0, 0)
     check(lib.raftk_general_solve_dynamics_host(C.byref(g), C.byref(c), C.byref(o), Xi.ctypes.data, st.ctypes.data))
     return Xi, st
 
@@ -567,9 +654,17 @@ class DeviceSession:
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
+    def _opts(self, n_iter, tol, xi_start, cluster_size):
+        """Solve options; from the second call with the same cluster size on, the per-design plan blobs that the first call
+        left in the session's workspace are reused (the session owns tables and workspace, so they cannot have changed)."""
+        key = int(cluster_size)
+        o = RaftkSolveOpts(int(n_iter), key, float(tol), float(xi_start), 1 if getattr(self, "_plan_key", None) == key else 0, 0)
+        self._plan_key = key
+        return o
+
     def solve(self, n_iter=10, tol=0.01, xi_start=0.0, cluster_size=0):
         """Enqueue Model.solveDynamics for all units on the current stream; returns the output dict (async)."""
-        o = RaftkSolveOpts(int(n_iter), int(cluster_size), float(tol), float(xi_start))
+        o = self._opts(n_iter, tol, xi_start, cluster_size)
         with self.torch.cuda.device(self.device):
             check(lib.raftk_solve_dynamics_dev(C.byref(self.d_struct), C.byref(self.c_struct), C.byref(o),
                                                C.byref(self.o_struct), self.workspace.data_ptr(), self.workspace_bytes,
@@ -579,12 +674,35 @@ class DeviceSession:
     def solve_gather(self, peers, o_struct=None, n_iter=10, tol=0.01, xi_start=0.0, cluster_size=0, timeout_flag=None):
         """``solve`` with the multi-GPU exchange fused into the kernel (``raft_b200.sweep.PeerExchange``): every finished
         unit is stored into all ranks' gathered arrays over NVLink, then the stream waits for the peers' arrival flags."""
-        o = RaftkSolveOpts(int(n_iter), int(cluster_size), float(tol), float(xi_start))
+        o = self._opts(n_iter, tol, xi_start, cluster_size)
         os_ = self.o_struct if o_struct is None else o_struct
         with self.torch.cuda.device(self.device):
             check(lib.raftk_solve_dynamics_gather_dev(C.byref(self.d_struct), C.byref(self.c_struct), C.byref(o), C.byref(os_),
                                                       C.byref(peers), self.workspace.data_ptr(), self.workspace_bytes, self._stream()))
             check(lib.raftk_peer_barrier_dev(C.byref(peers), timeout_flag, self._stream()))
+
+    def farm_response(self, C_arr=None, M_arr=None, B_arr=None):
+        """Enqueue the coupled 6N-DOF system response of the LAST ``solve`` (the session's designs are the FOWTs of the
+        array; it must have been created with want including B_drag, F_drag, F_iner [+ F_BEM]).  -> (Xi_sys [nC,6N,nw], info)."""
+        torch = self.torch
+        N, nC, nw = self.batch.n_designs, self.cases.n_cases, self.batch.nw
+        n = 6 * N
+        if not hasattr(self, "_farm"):
+            with torch.cuda.device(self.device):
+                mats = {nm: (torch.from_numpy(np.ascontiguousarray(v, dtype=_F8)).to(self.device) if v is not None else None)
+                        for nm, v in (("M_arr", M_arr), ("B_arr", B_arr), ("C_arr", C_arr))}
+                xi = torch.zeros([nC, n, nw], dtype=torch.complex128, device=self.device)
+                info = torch.zeros([nC, nw], dtype=torch.int32, device=self.device)
+            f = RaftkFarm()
+            f.n_fowt = N
+            for nm, t in mats.items():
+                setattr(f, nm, t.data_ptr() if t is not None else None)
+            f.Xi_sys, f.info = xi.data_ptr(), info.data_ptr()
+            self._farm = (f, mats, xi, info)
+        f, _, xi, info = self._farm
+        with torch.cuda.device(self.device):
+            check(lib.raftk_farm_response_dev(C.byref(self.d_struct), C.byref(self.c_struct), C.byref(self.o_struct), C.byref(f), self._stream()))
+        return xi, info
 
     def second_order_force(self):
         """Enqueue FOWT.calcHydroForce_2ndOrd for all units -> out['F_2nd'], out['F_2nd_mean'] (async)."""

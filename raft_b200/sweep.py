@@ -302,6 +302,7 @@ class ShardedSolve:
             dst = self.sess.ct[name[5:]] if name.startswith("case:") else self.sess.dt[name]
             dst.copy_(h, non_blocking=True)
             h2d += h.numel() * h.element_size()
+        self.sess._plan_key = None                     # fresh tables from the host: the per-design plan is rebuilt
         g, s = self.step(**kw)
         xi_h.copy_(g[self.rank], non_blocking=True)
         st_h.copy_(s[self.rank], non_blocking=True)

@@ -13,7 +13,7 @@ TABLE_KEYS = ["mem_q", "mem_p1", "mem_p2", "mem_rA", "node_r", "node_ls", "node_
               "node_in_q", "node_in_p1", "node_in_p2", "node_pa", "node_a_i", "node_Imat", "k", "w"]
 
 
-@pytest.mark.parametrize("name", sorted(DESIGNS))
+@pytest.mark.parametrize("name", sorted(n for n in DESIGNS if not n.startswith("farm_")))
 def test_builder_matches_reference_tables(name):
     """raft_b200.member/fowt rebuild, from the design dict alone, the tables packed from the reference's objects
     (strip discretisation, frames, node positions, drag/inertia coefficients, MacCamy-Fuchs, A_hydro_morison)."""

@@ -197,7 +197,7 @@ def test_model_api_vs_reference_run(name, solver):
         assert response_err(Xi[0], G["ref_run_solve_Xi"][i]) < RTOL
     # all cases of the fixture in one batched analyzeCases call
     cases = [dict(wave_spectrum="JONSWAP", wave_height=h, wave_period=t, wave_heading=b) for h, t, b in G["ref_run_solve_cases"]]
-    res = model.analyzeCases(cases)
+    res = model.analyzeCases(cases=cases)
     assert np.array_equal(res["status"][:, 0, 0], G["ref_run_solve_passes"])
     assert response_err(res["Xi"], G["ref_run_solve_Xi"]) < RTOL
     # fowt.Z left behind = impedance of the last pass (raft_model.py:1155): Z Xi = F_BEM + F_iner + F_drag
@@ -310,7 +310,7 @@ def test_response_stats_vs_reference_formulas(solver):
     assert relerr(sd, np.sqrt(0.5 * np.sum(np.abs(Xd) ** 2, axis=-1))) < 1e-14
     assert relerr(psd, 0.5 * np.abs(Xd) ** 2 / dw) < 1e-14
     model, G, P = _model_from_golden("cfg1_OC3spar")
-    res = model.analyzeCases([dict(wave_spectrum="JONSWAP", wave_height=2.0, wave_period=8.0, wave_heading=0.0)])
+    res = model.analyzeCases(cases=[dict(wave_spectrum="JONSWAP", wave_height=2.0, wave_period=8.0, wave_heading=0.0)])
     m = res["case_metrics"][0][0]
     ref = G["ref_run_solve_Xi"][0]
     assert abs(m["surge_std"] - np.sqrt(0.5 * np.sum(np.abs(ref[0]) ** 2))) < 1e-10 * m["surge_std"]
@@ -319,7 +319,7 @@ def test_response_stats_vs_reference_formulas(solver):
     tr = G["ref_run_trains"]
     case = dict(wave_spectrum=["JONSWAP"] * len(tr), wave_height=list(tr[:, 0]), wave_period=list(tr[:, 1]),
                 wave_heading=list(tr[:, 2]), wave_gamma=[0.0] * len(tr))
-    m = model.analyzeCases([case])["case_metrics"][0][0]
+    m = model.analyzeCases(0, None, False, cases=[case])["case_metrics"][0][0]
     ref = np.concatenate([G["ref_run_trains_Xi"], np.zeros_like(G["ref_run_trains_Xi"][:1])])      # [nWaves+1, 6, nw]
     dw = P["w"][1] - P["w"][0]
     assert abs(m["heave_std"] - np.sqrt(0.5 * np.sum(np.abs(ref[:, 2]) ** 2))) < 1e-10 * m["heave_std"]
@@ -564,7 +564,7 @@ def test_second_order_model_api_from_files(solver, tmp_path):
     f = model.fowtList[0]
     assert f.potSecOrder == 2 and np.array_equal(f.qtf, P["qtf"])
     cases = [dict(wave_spectrum="JONSWAP", wave_height=h, wave_period=tp, wave_heading=b) for h, tp, b in G["ref_run_solve_cases"]]
-    res = model.analyzeCases(cases)
+    res = model.analyzeCases(cases=cases)
     assert np.array_equal(res["status"][:, 0, 0], G["ref_run_solve_passes"])
     assert response_err(res["Xi"], G["ref_run_solve_Xi"]) < RTOL
     assert relerr(f.Fhydro_2nd[0].real, G["ref_run_F2nd"][-1]) < RTOL and relerr(f.Fhydro_2nd_mean[0], G["ref_run_F2nd_mean"][-1]) < RTOL
@@ -665,7 +665,7 @@ def test_model_api_turbine_channels(solver):
         tr = z["ref_run_case%d_trains" % ic]
         cases.append(dict(wave_spectrum=["JONSWAP"] * len(tr), wave_height=list(tr[:, 0]), wave_period=list(tr[:, 1]),
                           wave_heading=list(tr[:, 2]), wave_gamma=[0.0] * len(tr)))
-    res = model.analyzeCases(cases)
+    res = model.analyzeCases(cases=cases)
     for ic in range(3):
         m = res["case_metrics"][ic][0]
         for nm in ("surge", "pitch", "yaw", "AxRNA", "AyRNA", "AzRNA", "Mbase"):
@@ -763,7 +763,7 @@ def test_slender_model_api(solver):
     for a in range(6):
         assert relerr(q[..., a], z["ref_pickle_qtf"][..., a]) < 1e-9, a
     cases = [dict(wave_spectrum="JONSWAP", wave_height=h_, wave_period=t_, wave_heading=b_) for h_, t_, b_ in z["ref_run_solve_cases"]]
-    res = model.analyzeCases(cases)
+    res = model.analyzeCases(cases=cases)
     assert np.array_equal(res["status"][:, 0, 0], z["ref_run_solve_passes"])
     assert response_err(res["Xi"], z["ref_run_solve_Xi"]) < 1e-9
     assert relerr(f.Fhydro_2nd[0].real, z["ref_run_solve_F2nd"][-1]) < 1e-9

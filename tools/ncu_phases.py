@@ -8,6 +8,7 @@ rep = sys.argv[1]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "raft_b200", "csrc", "libraftk.so")
 kern = sys.argv[3] if len(sys.argv) > 3 else "k_rao_fusedILi128"
+FUSED = "raftk_fused2.cuh" if "fused2" in kern else "raftk_fused.cuh"
 srcdir = os.path.dirname(so)
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL)
@@ -26,7 +27,7 @@ for l in sass:
     if m:
         off2line[int(m.group(1), 16)] = (cur, m.group(2))
 # phase markers: find line numbers of comment anchors in the fused source
-fsrc = open(os.path.join(srcdir, "raftk_fused.cuh")).read().split("\n")
+fsrc = open(os.path.join(srcdir, FUSED)).read().split("\n")
 def find(s):
     for i, l in enumerate(fsrc):
         if s in l:
@@ -37,6 +38,12 @@ marks = [("stage+classes", 1), ("prologue", find("prologue per frequency")), ("p
          ("coefficients+B_drag", find("= linearised coefficients per node")), ("part2 walk", find("= pass part 2")),
          ("assembly", find("double ar[6][6], ai[6][6];")), ("solve6 call+conv", find("const bool ok = solve6")),
          ("flags/cluster sync", find("passes++;"))]
+if "fused2" in kern:
+    marks = [("stage (TMA blob)", 1), ("prologue", find("prologue per frequency")), ("part1 walk", find("= pass part 1")),
+             ("part1 warp reduce", find("warp sum of the 30 accumulators")), ("cross-warp/cluster reduce", find("for (int t = tid; t < nchunk * 32; t += T) {")),
+             ("coefficients+B_drag", find("= linearised coefficients per node")), ("part2 walk", find("= pass part 2")),
+             ("park+assembly", find("bin B's drag excitation waits")), ("solve6 call+conv", find("const bool ok = solve6")),
+             ("flags/cluster sync", find("passes++;")), ("epilogue", find("if (P.status && rank == 0 && tid == 0)"))]
 marks = [(n, l) for n, l in marks if l]
 out = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv"], text=True, stderr=subprocess.DEVNULL)
 rows = [r for r in csv.reader(out.split("\n")) if r]
@@ -46,8 +53,8 @@ stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued
 base = int(rows[2][ia], 16)
 agg = collections.defaultdict(lambda: collections.Counter())
 tot = totex = 0
-kstart = find("k_rao_fused(DesignsDev D")
-cur_ph = "stage+classes"
+kstart = find("k_rao_fused2(DesignsDev D") if "fused2" in kern else find("k_rao_fused(DesignsDev D")
+cur_ph, cur_idx, seen_later = marks[0][0], 0, False
 for r in rows[2:]:
     try:
         off = int(r[ia], 16) - base
@@ -55,8 +62,15 @@ for r in rows[2:]:
         continue
     (ln, op) = off2line.get(off, (None, "?"))
     # inlined helpers (proj, solve6, depth_funcs ...) inherit the phase of the surrounding kernel-body code (address order)
-    if ln is not None and ln[0] == "raftk_fused.cuh" and ln[1] >= kstart:
-        cur_ph = [n for n, l in marks if l <= ln[1]][-1]
+    if ln is not None and ln[0] == FUSED and ln[1] >= kstart:
+        # phases are laid out in source order; instructions that carry an EARLIER line (rematerialised pointers, hoisted
+        # rank / parameter reads) stay with the phase they sit in
+        cand = [k for k, (n, l) in enumerate(marks) if l <= ln[1]][-1]
+        if cand > 0 or not seen_later:          # stage-phase lines after the prologue began are rematerialised address arithmetic
+            cur_idx = cand
+        if cand > 0:
+            seen_later = True
+        cur_ph = marks[cur_idx][0]
     ph = cur_ph
     if ln is not None and ln[0] == "raftk_common.cuh" and ln[1] > 84:
         ph = "solve6 (LU)"

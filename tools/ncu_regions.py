@@ -9,6 +9,7 @@ rep, kern = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "raft_b200", "csrc", "libraftk.so")
+SRCDIR = os.path.join(ROOT, "raft_b200", "csrc")
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
