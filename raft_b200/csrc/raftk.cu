@@ -770,13 +770,6 @@ extern "C" int raftk_farm_response_dev(const raftk_designs *d, const raftk_cases
 }
 
 // ---- host-pointer front ends -------------------------------------------------------------------------
-// temporary device allocation released on every exit path of the small *_host wrappers
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    template <class T> T *as() const { return static_cast<T *>(p); }
-};
-#define DEV_ALLOC(buf, bytes) CUDA_TRY(cudaMalloc(&(buf).p, (bytes)))
 
 struct Arena {
     char *base = nullptr; size_t cap = 0, used = 0;
@@ -793,6 +786,19 @@ struct Arena {
 };
 static Arena g_arena[RAFTK_MAX_DEV];       // one per device: the *_host paths run on whichever device is current
 static std::mutex g_arena_mu;
+
+// Device scratch of the small *_host wrappers (statistics, system solve, second-order force, slender-body QTF, generalised
+// DOFs): one grow-only block per device, bump-allocated per call -- no cudaMalloc / cudaFree on the call path once the
+// high-water mark has been reached (no hidden allocation per call).
+static Arena g_scratch[RAFTK_MAX_DEV];
+static std::mutex g_scratch_mu;
+struct ScratchCall {
+    std::unique_lock<std::mutex> lk;
+    Arena &A;
+    ScratchCall() : lk(g_scratch_mu), A(g_scratch[cur_dev()]) { A.used = 0; }
+    bool reserve(size_t total) { return A.reserve(total + 4096) == 0; }
+    template <class T> T *take(size_t bytes) { return static_cast<T *>(A.take(bytes)); }
+};
 
 // Small input arrays (grid, member/node tables, case table: ~30 arrays of a few KB) are gathered in one pinned
 // staging block and sent with a single copy into a reserved region at the head of the arena; only large arrays
@@ -1018,8 +1024,9 @@ extern "C" int raftk_second_order_force_host(const raftk_designs *d, const raftk
     const size_t o_w = take(nw * 8), o_qw = take(n2 * 8), o_qh = take(nh * 8), o_q = take(qb);
     const size_t o_hs = take(nC * 8), o_tp = take(nC * 8), o_ga = take(nC * 8), o_be = take(nC * 8), o_sp = take(nC * 4);
     const size_t o_ze = take(c->zeta ? nC * nw * 8 : 0), o_f = take(fb), o_m = take(mb);
-    char *base = nullptr;
-    CUDA_TRY(cudaMalloc(&base, total));
+    ScratchCall sc;
+    if (!sc.reserve(total)) return set_err(RAFTK_ENOMEM, "second-order force: device scratch allocation failed");
+    char *base = sc.take<char>(total);
     cudaError_t e = cudaSuccess;
     auto h2d = [&](size_t off, const void *h, size_t n) { if (h && n) { cudaError_t r = cudaMemcpy(base + off, h, n, cudaMemcpyHostToDevice); if (r != cudaSuccess) e = r; } };
     h2d(o_w, d->w, nw * 8); h2d(o_qw, d->qtf_w, n2 * 8); h2d(o_qh, d->qtf_heads, nh * 8); h2d(o_q, d->qtf, qb);
@@ -1039,7 +1046,6 @@ extern "C" int raftk_second_order_force_host(const raftk_designs *d, const raftk
         e = cudaMemcpy(out->F_2nd, base + o_f, fb, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && out->F_2nd_mean) e = cudaMemcpy(out->F_2nd_mean, base + o_m, mb, cudaMemcpyDeviceToHost);
     }
-    cudaFree(base);
     if (e != cudaSuccess) return set_err(RAFTK_ECUDA, "second-order force: %s", cudaGetErrorString(e));
     return rc;
 }
@@ -1144,9 +1150,9 @@ extern "C" int raftk_general_solve_dynamics_host(const raftk_general *g, const r
     add(c->beta_deg, nC * 8, (const void **)&cc.beta_deg); add(c->spec, nC * 4, (const void **)&cc.spec); add(c->zeta, nC * nw * 8, (const void **)&cc.zeta);
     const size_t o_xi = take(nC * n * nw * 16), o_st = take(nC * 16);
     const size_t wb = raftk_general_workspace_bytes(g, (int32_t)nC), o_ws = take(wb);
-    DevBuf buf;
-    DEV_ALLOC(buf, total);
-    char *base = buf.as<char>();
+    ScratchCall sc;
+    if (!sc.reserve(total)) return set_err(RAFTK_ENOMEM, "general solve: device scratch allocation failed");
+    char *base = sc.take<char>(total);
     for (auto &it : items) { CUDA_TRY(cudaMemcpy(base + it.off, it.h, it.nb, cudaMemcpyHostToDevice)); *it.slot = base + it.off; }
     int rc = raftk_general_solve_dynamics_dev(&gg, &cc, o, reinterpret_cast<double *>(base + o_xi), reinterpret_cast<int32_t *>(base + o_st),
                                               base + o_ws, wb, nullptr);
@@ -1231,8 +1237,9 @@ extern "C" int raftk_qtf_slender_host(const raftk_slender *s, int32_t n_cases, c
     add(s->M_struc, 288, (const void **)&dd.M_struc);
     const size_t o_beta = take(nC * 8), o_xi = take(nC * 6 * nw * 16), o_q = take(nC * nw * nw * 6 * 16);
     const size_t wb = raftk_qtf_slender_workspace_bytes(s, n_cases), o_ws = take(wb);
-    char *base = nullptr;
-    CUDA_TRY(cudaMalloc(&base, total));
+    ScratchCall sc;
+    if (!sc.reserve(total)) return set_err(RAFTK_ENOMEM, "slender-body QTF: device scratch allocation failed");
+    char *base = sc.take<char>(total);
     cudaError_t e = cudaSuccess;
     for (auto &it : items) {
         if (it.h && it.n) { cudaError_t r = cudaMemcpy(base + it.off, it.h, it.n, cudaMemcpyHostToDevice); if (r != cudaSuccess) e = r; }
@@ -1245,7 +1252,6 @@ extern "C" int raftk_qtf_slender_host(const raftk_slender *s, int32_t n_cases, c
                                    reinterpret_cast<double *>(base + o_q), base + o_ws, wb, nullptr);
         if (!rc) e = cudaMemcpy(qtf, base + o_q, nC * nw * nw * 6 * 16, cudaMemcpyDeviceToHost);
     }
-    cudaFree(base);
     if (e != cudaSuccess) return set_err(RAFTK_ECUDA, "slender-body QTF: %s", cudaGetErrorString(e));
     return rc;
 }
@@ -1254,13 +1260,15 @@ extern "C" int raftk_system_solve_host(int32_t n, int32_t nw, int32_t nrhs, doub
 {
     if (n <= 0 || nw <= 0 || nrhs <= 0 || !Z || !F) return set_err(RAFTK_EINVAL, "bad system-solve arguments");
     const size_t zb = (size_t)nw * n * n * 16, fb = (size_t)nw * n * nrhs * 16, ib = (size_t)nw * 4;
-    DevBuf dZ, dF, dI;
-    DEV_ALLOC(dZ, zb); DEV_ALLOC(dF, fb); DEV_ALLOC(dI, ib);
-    CUDA_TRY(cudaMemcpy(dZ.p, Z, zb, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dF.p, F, fb, cudaMemcpyHostToDevice));
-    int rc = raftk_system_solve_dev(n, nw, nrhs, dZ.as<double>(), dF.as<double>(), dI.as<int32_t>(), nullptr);
+    ScratchCall sc;
+    if (!sc.reserve(align_up(zb, 256) + align_up(fb, 256) + align_up(ib, 256))) return set_err(RAFTK_ENOMEM, "system solve: device scratch allocation failed");
+    double *dZ = sc.take<double>(zb), *dF = sc.take<double>(fb);
+    int32_t *dI = sc.take<int32_t>(ib);
+    CUDA_TRY(cudaMemcpy(dZ, Z, zb, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dF, F, fb, cudaMemcpyHostToDevice));
+    int rc = raftk_system_solve_dev(n, nw, nrhs, dZ, dF, dI, nullptr);
     if (!rc) {
-        CUDA_TRY(cudaMemcpy(F, dF.p, fb, cudaMemcpyDeviceToHost));
-        if (info) CUDA_TRY(cudaMemcpy(info, dI.p, ib, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(F, dF, fb, cudaMemcpyDeviceToHost));
+        if (info) CUDA_TRY(cudaMemcpy(info, dI, ib, cudaMemcpyDeviceToHost));
     }
     return rc;
 }
@@ -1280,14 +1288,14 @@ extern "C" int raftk_response_stats_host(int32_t n_units, int32_t nw, double dw,
 {
     if (n_units <= 0 || nw <= 0 || !Xi || !sd || !(dw > 0.0)) return set_err(RAFTK_EINVAL, "bad response-stats arguments");
     const size_t xb = (size_t)n_units * 6 * nw * 16, sb = (size_t)n_units * 6 * 8, pb = (size_t)n_units * 6 * nw * 8;
-    DevBuf dX, dS, dP;
-    DEV_ALLOC(dX, xb); DEV_ALLOC(dS, sb);
-    if (psd) DEV_ALLOC(dP, pb);
-    CUDA_TRY(cudaMemcpy(dX.p, Xi, xb, cudaMemcpyHostToDevice));
-    int rc = raftk_response_stats_dev(n_units, nw, dw, rot_deg, dX.as<double>(), dS.as<double>(), dP.as<double>(), nullptr);
+    ScratchCall sc;
+    if (!sc.reserve(align_up(xb, 256) + align_up(sb, 256) + align_up(pb, 256))) return set_err(RAFTK_ENOMEM, "response stats: device scratch allocation failed");
+    double *dX = sc.take<double>(xb), *dS = sc.take<double>(sb), *dP = psd ? sc.take<double>(pb) : nullptr;
+    CUDA_TRY(cudaMemcpy(dX, Xi, xb, cudaMemcpyHostToDevice));
+    int rc = raftk_response_stats_dev(n_units, nw, dw, rot_deg, dX, dS, dP, nullptr);
     if (!rc) {
-        CUDA_TRY(cudaMemcpy(sd, dS.p, sb, cudaMemcpyDeviceToHost));
-        if (psd) CUDA_TRY(cudaMemcpy(psd, dP.p, pb, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(sd, dS, sb, cudaMemcpyDeviceToHost));
+        if (psd) CUDA_TRY(cudaMemcpy(psd, dP, pb, cudaMemcpyDeviceToHost));
     }
     return rc;
 }
@@ -1314,17 +1322,17 @@ extern "C" int raftk_channel_stats_host(int32_t n_designs, int32_t n_cases, int3
     const size_t rows = (size_t)n_designs * n_cases * n_ch;
     const size_t cb = (size_t)n_designs * n_ch * 6 * nw * 16, xb = (size_t)n_designs * n_cases * 6 * nw * 16;
     const size_t sb = rows * 8, pb = rows * nw * 8, ab = rows * nw * 16;
-    DevBuf dC, dX, dS, dP, dA;
-    DEV_ALLOC(dC, cb); DEV_ALLOC(dX, xb); DEV_ALLOC(dS, sb);
-    if (psd) DEV_ALLOC(dP, pb);
-    if (amp) DEV_ALLOC(dA, ab);
-    CUDA_TRY(cudaMemcpy(dC.p, coef, cb, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dX.p, Xi, xb, cudaMemcpyHostToDevice));
-    int rc = raftk_channel_stats_dev(n_designs, n_cases, n_ch, nw, dw, dC.as<double>(), dX.as<double>(), dS.as<double>(), dP.as<double>(),
-                                     dA.as<double>(), nullptr);
+    ScratchCall sc;
+    if (!sc.reserve(align_up(cb, 256) + align_up(xb, 256) + align_up(sb, 256) + align_up(pb, 256) + align_up(ab, 256)))
+        return set_err(RAFTK_ENOMEM, "channel stats: device scratch allocation failed");
+    double *dC = sc.take<double>(cb), *dX = sc.take<double>(xb), *dS = sc.take<double>(sb);
+    double *dP = psd ? sc.take<double>(pb) : nullptr, *dA = amp ? sc.take<double>(ab) : nullptr;
+    CUDA_TRY(cudaMemcpy(dC, coef, cb, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(dX, Xi, xb, cudaMemcpyHostToDevice));
+    int rc = raftk_channel_stats_dev(n_designs, n_cases, n_ch, nw, dw, dC, dX, dS, dP, dA, nullptr);
     if (!rc) {
-        CUDA_TRY(cudaMemcpy(sd, dS.p, sb, cudaMemcpyDeviceToHost));
-        if (psd) CUDA_TRY(cudaMemcpy(psd, dP.p, pb, cudaMemcpyDeviceToHost));
-        if (amp) CUDA_TRY(cudaMemcpy(amp, dA.p, ab, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(sd, dS, sb, cudaMemcpyDeviceToHost));
+        if (psd) CUDA_TRY(cudaMemcpy(psd, dP, pb, cudaMemcpyDeviceToHost));
+        if (amp) CUDA_TRY(cudaMemcpy(amp, dA, ab, cudaMemcpyDeviceToHost));
     }
     return rc;
 }

@@ -201,6 +201,15 @@ class FOWT:
             raise RuntimeError("calcHydroLinearization must be called first")
         if ih == 0:
             return self.F_hydro_drag
-        # Bmat comes from train 0 (raft_member.py:2128-2152).  Stand-alone evaluation for a secondary train is not
-        # exposed; Model.solveDynamics handles multi-train cases inside the solver (cases.primary of the C ABI).
-        raise NotImplementedError("use Model.solveDynamics for cases with several wave trains")
+        if ih < 0 or ih >= self._cases.n_cases:
+            raise IndexError("wave train %d of %d" % (ih, self._cases.n_cases))
+        # Bmat comes from train 0's linearisation about the Xi of the last calcHydroLinearization (raft_member.py:2128-2152):
+        # one pass of the solver with train ih declared a secondary train of train 0 (cases.primary) and the loop started
+        # at that Xi evaluates F = sum_nodes Bmat u[ih] with exactly those per-node coefficients.
+        a = self._cases.arrays
+        table = {k: a[k][[0, ih]] for k in ("Hs", "Tp", "gamma", "beta_deg", "spec")}
+        table["primary"] = np.zeros(2, dtype=np.int32)
+        Xi0 = np.broadcast_to(self._Xi_lin, (1, 2, 6, self.nw))
+        out = solver.solve_dynamics(self._get_batch(), solver.CaseTable(table, Xi_init=Xi0), n_iter=0, want=("Xi", "status", "F_drag"))
+        self.F_hydro_drag = out["F_drag"][0, 1]
+        return self.F_hydro_drag

@@ -221,6 +221,30 @@ def test_fowt_api_vs_reference_run(solver):
         f.calcHydroExcitation(dict(wave_spectrum="bogus", wave_heading=0, wave_period=10, wave_height=2))
 
 
+def test_fowt_drag_excitation_of_secondary_train(solver, oracle):
+    """FOWT.calcDragExcitation(ih > 0) (raft_fowt.py:1940-1957, raft_member.py:2128-2152): the drag load of wave train ih with
+    the Bmat that calcHydroLinearization(Xi) left behind for train 0, against the oracle's Bmat applied to train ih's kinematics."""
+    model, G, P = _model_from_golden("cfg2_VolturnUS-S_nw64")
+    f = model.fowtList[0]
+    trains = [(6.0, 12.0, 30.0), (2.5, 7.0, -100.0), (1.0, 16.0, 170.0)]
+    f.calcHydroExcitation(dict(wave_spectrum=["JONSWAP"] * 3, wave_height=[t[0] for t in trains], wave_period=[t[1] for t in trains],
+                               wave_heading=[t[2] for t in trains], wave_gamma=[0.0] * 3))
+    rng = np.random.default_rng(4)
+    Xi = (rng.normal(size=(6, model.nw)) + 1j * rng.normal(size=(6, model.nw))) * np.array([1, 1, 1, 0.02, 0.02, 0.02])[:, None]
+    B = f.calcHydroLinearization(Xi)
+    od = oracle.OracleDesign(P)
+    u = [oracle.calc_hydro_excitation(od, 0, Hs, Tp, 0.0, beta)[3] for Hs, Tp, beta in trains]
+    Bmat, B_o, F0_o = oracle.calc_hydro_linearization(od, u[0], Xi)
+    assert relerr(B, B_o) < RTOL and relerr(f.calcDragExcitation(0), F0_o) < RTOL
+    for ih in (1, 2):
+        F = np.zeros([6, model.nw], dtype=complex)
+        for j in range(od.Ns):
+            fj = np.einsum("ab,bw->aw", Bmat[j], u[ih][j])                       # translateForce3to6DOF: [f ; r x f]
+            F[:3] += fj
+            F[3:] += np.cross(P["node_r"][j] - P["prp"], fj.T).T
+        assert relerr(f.calcDragExcitation(ih), F) < RTOL, ih
+
+
 def test_sweep_single_gpu_vs_oracle(solver, oracle):
     """Synthetic geometry variants (ragged node counts) in one batch: every design against the oracle."""
     import json, os
