@@ -437,16 +437,19 @@ def measure(args, designs, cs, cfg, rank, world, dev, full):
 
     for _ in range(args.warmup):
         step()
+    # everything with a variable host cost (NVML initialisation of the clock sampler: several ms, different on every rank;
+    # event creation) happens BEFORE the barrier that aligns the ranks -- a rank that enters the timed loop late makes every
+    # other rank wait for it in the first exchange, and that wait would be booked as step time (round 1's N = 8 number)
+    sampler = ClockSampler(local)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler.start()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
 
     # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps ----
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = solver.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     for a, b in ev:
         flush.fill_(1)                       # not timed: evicts the previous step's tables/outputs from L2
@@ -581,11 +584,12 @@ def measure(args, designs, cs, cfg, rank, world, dev, full):
     if full and not args.no_extras:
         samp2 = ClockSampler(local)
         n_rep = max(10, int(2.2e3 / max(ms / args.steps, 1e-3)))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        samp2.start()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        samp2.start()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
         a.record()
         for _ in range(n_rep):
             step()

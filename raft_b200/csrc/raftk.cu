@@ -739,11 +739,13 @@ static int farm_launch(const raftk_designs *d, const raftk_cases *c, const raftk
         return set_err(RAFTK_EINVAL, "farm response needs B_drag, F_drag, F_iner of the per-FOWT solve and farm.Xi_sys");
     if (d->n_bem_head > 0 && !solved->F_BEM) return set_err(RAFTK_EINVAL, "farm response: the designs carry BEM excitation, F_BEM is required");
     const int n = 6 * f->n_fowt;
-    const size_t smem = (size_t)n * (n + 1) * sizeof(double2);
+    const bool warp = n <= 24;                          // small systems: one warp per (frequency, case), FARM_WPC per CTA
+    const size_t smem = (size_t)(warp ? FARM_WPC : 1) * n * (n + 1) * sizeof(double2);
     if (smem > 227 * 1024) return set_err(RAFTK_EINVAL, "farm too large for the shared-memory solver (6N (6N+1) 16 B > 227 KB: N <= 19)");
     if (c->n_cases > 65535) return set_err(RAFTK_EINVAL, "farm response: more than 65535 cases per call");
-    static SmemOptIn opt(48 * 1024);
-    CUDA_TRY(opt.ensure(k_farm_response, smem));
+    static SmemOptIn opt_w(48 * 1024), opt_b(48 * 1024);
+    if (warp) CUDA_TRY(opt_w.ensure(k_farm_response<true>, smem));
+    else CUDA_TRY(opt_b.ensure(k_farm_response<false>, smem));
     DesignsDev D = to_dev(d, d->max_nodes, d->max_members);
     CasesDev C = to_dev(c);
     FarmParams P;
@@ -756,7 +758,8 @@ static int farm_launch(const raftk_designs *d, const raftk_cases *c, const raftk
     P.Xi = reinterpret_cast<double2 *>(f->Xi_sys); P.info = f->info;
     {
         ProfScope ps(st, 1);
-        k_farm_response<<<dim3(d->nw, c->n_cases), 128, smem, st>>>(D, C, P);
+        if (warp) k_farm_response<true><<<dim3((d->nw + FARM_WPC - 1) / FARM_WPC, c->n_cases), 32 * FARM_WPC, smem, st>>>(D, C, P);
+        else k_farm_response<false><<<dim3(d->nw, c->n_cases), 256, smem, st>>>(D, C, P);
     }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1114,7 +1117,7 @@ extern "C" int raftk_general_solve_dynamics_dev(const raftk_general *g, const ra
         k_gen_project<<<dim3(fb, g->n_dof, (unsigned)nC), 128, 0, st>>>(D, W, W.F_drag, 1);
         if (blocked) {
             ProfScope ps(st, 2);
-            k_gen_solve_blocked<<<dim3(g->nw, (unsigned)nC), 256, lu_smem, st>>>(D, W, X, o->tol);
+            k_gen_solve_blocked<<<dim3(g->nw, (unsigned)nC), GT, lu_smem, st>>>(D, W, X, o->tol);
         } else {
             ProfScope ps(st, 2);
             k_gen_solve<<<dim3(g->nw, (unsigned)nC), 256, 0, st>>>(D, W, X, o->tol);

@@ -323,14 +323,14 @@ __global__ void __launch_bounds__(256) k_gen_solve(GenDev D, GenWork W, double2 
 //   GB rank-1 contributions IN ELIMINATION ORDER (k ascending, the rounding sequence of the unblocked algorithm) and is
 //   stored once.  Traffic to the L2-resident matrix drops by GB (16) against the unblocked kernel's one pass per column;
 //   9 Mflop per 150 x 150 system then run from registers and shared memory.
-#define GB 16
-__global__ void __launch_bounds__(256, 2) k_gen_solve_blocked(GenDev D, GenWork W, double2 *Xi, double tol)
+#define GB 8
+#define GT 128
+__global__ void __launch_bounds__(GT, 4) k_gen_solve_blocked(GenDev D, GenWork W, double2 *Xi, double tol)
 {
     extern __shared__ __align__(16) double smem_raw[];
-    __shared__ double pv[8];
-    __shared__ int pi_[8];
-    __shared__ double2 piv;
-    __shared__ int prow, bad;
+    __shared__ double pv[GT / 32];
+    __shared__ int pi_[GT / 32];
+    __shared__ int bad;
     __shared__ int pivrow[GB];
     const int i = blockIdx.x, c = blockIdx.y, tid = threadIdx.x, n = D.n, nw = D.nw, nc = n + 1;
     if (W.flags[4 * c]) return;
@@ -339,11 +339,11 @@ __global__ void __launch_bounds__(256, 2) k_gen_solve_blocked(GenDev D, GenWork 
     double2 *A = W.Z + ((size_t)c * nw + i) * (size_t)n * nc;
     const double w = D.w[i], w2 = w * w;
     const double *Bd = W.B_drag + (size_t)c * n * n;
-    for (int t = tid; t < n * n; t += 256) {
+    for (int t = tid; t < n * n; t += GT) {
         const int a = t / n, b = t % n;
         A[(size_t)a * nc + b] = make_double2(fma(-w2, D.M[t], D.C[t]), w * (D.B[t] + Bd[t]));       // raft_model.py:1086
     }
-    for (int a = tid; a < n; a += 256) {
+    for (int a = tid; a < n; a += GT) {
         const double2 f1 = W.F_iner[((size_t)c * n + a) * nw + i], f2 = W.F_drag[((size_t)c * n + a) * nw + i];
         A[(size_t)a * nc + n] = make_double2(f1.x + f2.x, f1.y + f2.y);
     }
@@ -352,46 +352,47 @@ __global__ void __launch_bounds__(256, 2) k_gen_solve_blocked(GenDev D, GenWork 
     for (int kb = 0; kb < n; kb += GB) {
         const int nb = min(GB, n - kb), m = n - kb;
         // ---- 1. panel into shared memory ------------------------------------------------------------------------
-        for (int t = tid; t < m * nb; t += 256) { const int r = t / nb, j = t % nb; P[r * GB + j] = A[(size_t)(kb + r) * nc + kb + j]; }
+        for (int t = tid; t < m * nb; t += GT) { const int r = t / nb, j = t % nb; P[r * GB + j] = A[(size_t)(kb + r) * nc + kb + j]; }
         __syncthreads();
         // ---- 2. unblocked LU of the panel (pivot on |re| + |im|, first maximum wins, like izamax) ---------------------
         for (int j = 0; j < nb; j++) {
             double best = -1.0; int bi = j;
-            for (int r = j + tid; r < m; r += 256) { const double2 v = P[r * GB + j]; const double mg = fabs(v.x) + fabs(v.y); if (mg > best) { best = mg; bi = r; } }
+            for (int r = j + tid; r < m; r += GT) { const double2 v = P[r * GB + j]; const double mg = fabs(v.x) + fabs(v.y); if (mg > best) { best = mg; bi = r; } }
             for (int o = 16; o >= 1; o >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
             if ((tid & 31) == 0) { pv[tid >> 5] = best; pi_[tid >> 5] = bi; }
             __syncthreads();
-            if (tid == 0) {
-                double b0 = pv[0]; int r0 = pi_[0];
-                for (int t = 1; t < 8; t++) if (pv[t] > b0 || (pv[t] == b0 && pi_[t] < r0)) { b0 = pv[t]; r0 = pi_[t]; }
-                prow = r0; pivrow[j] = r0;
-                if (!(b0 > 0.0)) bad = 1;
-            }
+            // every thread finishes the reduction itself (same winner everywhere) and reads the pivot before rows move
+            double b0 = pv[0]; int p = pi_[0];
+#pragma unroll
+            for (int t = 1; t < GT / 32; t++) if (pv[t] > b0 || (pv[t] == b0 && pi_[t] < p)) { b0 = pv[t]; p = pi_[t]; }
+            const double2 a = P[p * GB + j];
+            const double dd = a.x * a.x + a.y * a.y;
+            const double2 ip = make_double2(a.x / dd, -a.y / dd);
+            if (tid == 0) { pivrow[j] = p; if (!(b0 > 0.0)) bad = 1; }
             __syncthreads();
-            const int p = prow;
             if (p != j && tid < nb) { const double2 t1 = P[j * GB + tid]; P[j * GB + tid] = P[p * GB + tid]; P[p * GB + tid] = t1; }
             __syncthreads();
-            if (tid == 0) { const double2 a = P[j * GB + j]; const double dd = a.x * a.x + a.y * a.y; piv = make_double2(a.x / dd, -a.y / dd); }
-            __syncthreads();
-            const double2 ip = piv;
-            for (int r = j + 1 + tid; r < m; r += 256) { const double2 a = P[r * GB + j]; P[r * GB + j] = make_double2(a.x * ip.x - a.y * ip.y, a.x * ip.y + a.y * ip.x); }
-            __syncthreads();
+            // multipliers and the update of the panel's remaining columns in one sweep: thread per row
             const int cols = nb - j - 1;
-            for (int t = tid; t < (m - j - 1) * cols; t += 256) {
-                const int r = j + 1 + t / cols, b = j + 1 + t % cols;
-                const double2 l = P[r * GB + j], ak = P[j * GB + b];
-                double2 v = P[r * GB + b];
-                v.x -= l.x * ak.x - l.y * ak.y; v.y -= l.x * ak.y + l.y * ak.x;
-                P[r * GB + b] = v;
+            for (int r = j + 1 + tid; r < m; r += GT) {
+                const double2 v = P[r * GB + j];
+                const double2 l = make_double2(v.x * ip.x - v.y * ip.y, v.x * ip.y + v.y * ip.x);
+                P[r * GB + j] = l;
+                for (int b = 0; b < cols; b++) {
+                    const double2 ak = P[j * GB + j + 1 + b];
+                    double2 x = P[r * GB + j + 1 + b];
+                    x.x -= l.x * ak.x - l.y * ak.y; x.y -= l.x * ak.y + l.y * ak.x;
+                    P[r * GB + j + 1 + b] = x;
+                }
             }
             __syncthreads();
         }
         // ---- 3. panel back to the matrix; its row swaps applied, in order, to the columns outside the panel -------
-        for (int t = tid; t < m * nb; t += 256) { const int r = t / nb, j = t % nb; A[(size_t)(kb + r) * nc + kb + j] = P[r * GB + j]; }
-        for (int col = tid; col < nc; col += 256) {
+        for (int t = tid; t < m * nb; t += GT) { const int r = t / nb, j = t % nb; A[(size_t)(kb + r) * nc + kb + j] = P[r * GB + j]; }
+        for (int col = tid; col < nc; col += GT) {
             if (col >= kb && col < kb + nb) continue;
             for (int j = 0; j < nb; j++) {
                 const int p = pivrow[j];
@@ -401,9 +402,9 @@ __global__ void __launch_bounds__(256, 2) k_gen_solve_blocked(GenDev D, GenWork 
         __syncthreads();
         // ---- 4. row block U12 = L11^-1 A12 (unit lower triangular solve per column, elimination order) -----------------
         const int c0 = kb + nb, ncol = nc - c0;
-        for (int t = tid; t < nb * ncol; t += 256) { const int j = t / ncol, b = t % ncol; U[j * nc + b] = A[(size_t)(kb + j) * nc + c0 + b]; }
+        for (int t = tid; t < nb * ncol; t += GT) { const int j = t / ncol, b = t % ncol; U[j * nc + b] = A[(size_t)(kb + j) * nc + c0 + b]; }
         __syncthreads();
-        for (int b = tid; b < ncol; b += 256) {
+        for (int b = tid; b < ncol; b += GT) {
             for (int j = 0; j < nb; j++) {
                 const double2 uj = U[j * nc + b];
                 for (int r = j + 1; r < nb; r++) {
@@ -415,11 +416,11 @@ __global__ void __launch_bounds__(256, 2) k_gen_solve_blocked(GenDev D, GenWork 
             }
         }
         __syncthreads();
-        for (int t = tid; t < nb * ncol; t += 256) { const int j = t / ncol, b = t % ncol; A[(size_t)(kb + j) * nc + c0 + b] = U[j * nc + b]; }
+        for (int t = tid; t < nb * ncol; t += GT) { const int j = t / ncol, b = t % ncol; A[(size_t)(kb + j) * nc + c0 + b] = U[j * nc + b]; }
         // ---- 5. trailing update A22 -= L21 U12: 4 x 2 register tile per thread, contributions in elimination order --
         const int m2 = m - nb;
         const int tr = (m2 + 3) / 4, tc = (ncol + 1) / 2;
-        for (int t = tid; t < tr * tc; t += 256) {
+        for (int t = tid; t < tr * tc; t += GT) {
             const int r0 = 4 * (t / tc), b0 = 2 * (t % tc);
             double2 acc[4][2];
 #pragma unroll
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(256, 2) k_gen_solve_blocked(GenDev D, GenWork 
         }
         __syncthreads();
         const double2 x = A[(size_t)k * nc + n];
-        for (int r = tid; r < k; r += 256) {
+        for (int r = tid; r < k; r += GT) {
             const double2 a = A[(size_t)r * nc + k];
             double2 b = A[(size_t)r * nc + n];
             b.x -= a.x * x.x - a.y * x.y; b.y -= a.x * x.y + a.y * x.x;
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(256, 2) k_gen_solve_blocked(GenDev D, GenWork 
         __syncthreads();
     }
     int notconv = 0, nan = 0;
-    for (int a = tid; a < n; a += 256) {
+    for (int a = tid; a < n; a += GT) {
         const double2 x = A[(size_t)a * nc + n], l = W.XiLast[((size_t)c * n + a) * nw + i];
         Xi[((size_t)c * n + a) * nw + i] = x;
         if (isnan(x.x) || isnan(x.y)) nan = 1;

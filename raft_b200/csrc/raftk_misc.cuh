@@ -5,91 +5,181 @@
 // K3: dense complex solve per frequency (farm system response).  One CTA per frequency, matrix in
 // shared memory, LU with partial pivoting, nrhs right-hand sides.
 // ------------------------------------------------------------------------------------------------
-// LU with partial pivoting (|re| + |im| metric, as LAPACK izamax) of the augmented system A [n][nc] (nc = n + nrhs) held in
-// shared memory, then back substitution of every right-hand side in place.  All threads of the CTA call it; returns k + 1
-// of the first zero pivot (0 = none) to thread 0.
-__device__ __forceinline__ int lu_solve_smem(double2 *A, int n, int nc, int nrhs, int *piv_s, double2 *rinv_s)
+// Dense complex LU in shared memory, shared by the system-solve kernels.  A [n][nc] is the augmented system (nc = n + nrhs),
+// partial pivoting on |re| + |im| with the first maximum winning (LAPACK izamax), right-hand sides eliminated along.
+// A "group" of gsize threads (a warp when WARP, else the whole CTA) works on one system; gtid is the thread's index in it.
+template <bool WARP> __device__ __forceinline__ void gsync() { if (WARP) __syncwarp(); else __syncthreads(); }
+
+// one elimination step on column col: pivot search over rows col..n-1, swap of the full rows, multipliers.  Returns via *bad.
+template <bool WARP>
+__device__ __forceinline__ void lu_pivot_step(double2 *A, int n, int nc, int col, int gtid, int gsize, int *piv_s, double2 *rinv_s, int *bad_s)
 {
-    const int tid = threadIdx.x;
-    int bad = 0;
+    if (gtid < 32) {
+        double best = -1.0; int p = col;
+        for (int r = col + gtid; r < n; r += 32) {
+            const double t = fabs(A[r * nc + col].x) + fabs(A[r * nc + col].y);
+            if (t > best) { best = t; p = r; }
+        }
+        for (int o = 16; o >= 1; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int op = __shfl_xor_sync(0xffffffffu, p, o);
+            if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+        }
+        if (gtid == 0) {
+            *piv_s = p;
+            const double2 pv = A[p * nc + col];
+            const double den = pv.x * pv.x + pv.y * pv.y;
+            *rinv_s = (den > 0.0) ? make_double2(pv.x / den, -pv.y / den) : make_double2(0.0, 0.0);
+            if (!(den > 0.0) && *bad_s == 0) *bad_s = col + 1;
+        }
+    }
+    gsync<WARP>();
+    const int p = *piv_s;
+    if (p != col) for (int t = gtid; t < nc; t += gsize) { const double2 tmp = A[col * nc + t]; A[col * nc + t] = A[p * nc + t]; A[p * nc + t] = tmp; }
+    gsync<WARP>();
+    const double2 ri = *rinv_s;
+    for (int r = col + 1 + gtid; r < n; r += gsize) {
+        const double2 v = A[r * nc + col];
+        A[r * nc + col] = make_double2(v.x * ri.x - v.y * ri.y, v.x * ri.y + v.y * ri.x);
+    }
+    gsync<WARP>();
+}
+
+// back substitution of every right-hand side, row by row from the bottom, the column updates spread over the group
+template <bool WARP>
+__device__ __forceinline__ void lu_back_subst(double2 *A, int n, int nc, int nrhs, int gtid, int gsize)
+{
+    for (int r = n - 1; r >= 0; r--) {
+        const double2 pv = A[r * nc + r];
+        const double den = pv.x * pv.x + pv.y * pv.y;
+        for (int rh = gtid; rh < nrhs; rh += gsize) {
+            const double2 s = A[r * nc + n + rh];
+            A[r * nc + n + rh] = make_double2((s.x * pv.x + s.y * pv.y) / den, (s.y * pv.x - s.x * pv.y) / den);
+        }
+        gsync<WARP>();
+        for (int t = gtid; t < r * nrhs; t += gsize) {
+            const int rr = t / nrhs, rh = t - rr * nrhs;
+            const double2 a = A[rr * nc + r], x = A[r * nc + n + rh];
+            double2 b = A[rr * nc + n + rh];
+            b.x -= a.x * x.x - a.y * x.y; b.y -= a.x * x.y + a.y * x.x;
+            A[rr * nc + n + rh] = b;
+        }
+        gsync<WARP>();
+    }
+}
+
+// column-at-a-time LU (small systems: one warp per system, or any size with one CTA per system)
+template <bool WARP>
+__device__ __forceinline__ void lu_unblocked(double2 *A, int n, int nc, int nrhs, int gtid, int gsize, int *piv_s, double2 *rinv_s, int *bad_s)
+{
     for (int k = 0; k < n; k++) {
-        if (tid < 32) {                                              // pivot search by warp 0
-            double best = -1.0; int p = k;
-            for (int r = k + tid; r < n; r += 32) {
-                const double t = fabs(A[r * nc + k].x) + fabs(A[r * nc + k].y);
-                if (t > best) { best = t; p = r; }
-            }
-            for (int o = 16; o >= 1; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int op = __shfl_xor_sync(0xffffffffu, p, o);
-                if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
-            }
-            if (tid == 0) {
-                *piv_s = p;
-                const double2 pv = A[p * nc + k];
-                const double den = pv.x * pv.x + pv.y * pv.y;
-                *rinv_s = (den > 0.0) ? make_double2(pv.x / den, -pv.y / den) : make_double2(0.0, 0.0);
-                if (!(den > 0.0) && bad == 0) bad = k + 1;
-            }
-        }
-        __syncthreads();
-        const int p = *piv_s;
-        if (p != k) for (int t = tid; t < nc; t += blockDim.x) { const double2 tmp = A[k * nc + t]; A[k * nc + t] = A[p * nc + t]; A[p * nc + t] = tmp; }
-        __syncthreads();
-        const double2 ri = *rinv_s;
-        for (int r = k + 1 + tid; r < n; r += blockDim.x) {
-            const double2 v = A[r * nc + k];
-            A[r * nc + k] = make_double2(v.x * ri.x - v.y * ri.y, v.x * ri.y + v.y * ri.x);
-        }
-        __syncthreads();
+        lu_pivot_step<WARP>(A, n, nc, k, gtid, gsize, piv_s, rinv_s, bad_s);
         const int rows = n - k - 1, cols = nc - k - 1;
-        for (int t = tid; t < rows * cols; t += blockDim.x) {
+        for (int t = gtid; t < rows * cols; t += gsize) {
             const int r = k + 1 + t / cols, cidx = k + 1 + t % cols;
             const double2 l = A[r * nc + k], u = A[k * nc + cidx];
             double2 v = A[r * nc + cidx];
             v.x -= l.x * u.x - l.y * u.y; v.y -= l.x * u.y + l.y * u.x;
             A[r * nc + cidx] = v;
         }
+        gsync<WARP>();
+    }
+    lu_back_subst<WARP>(A, n, nc, nrhs, gtid, gsize);
+}
+
+// blocked right-looking LU (one CTA per system): panels of LB columns factored column by column, then the row block and the
+// trailing matrix receive the panel's LB rank-1 contributions from registers (4 x 2 tile per thread), in elimination order --
+// the rounding sequence of the column-at-a-time algorithm with a quarter of its shared-memory traffic.
+#define LB 8
+__device__ __forceinline__ void lu_blocked(double2 *A, int n, int nc, int nrhs, int *piv_s, double2 *rinv_s, int *bad_s)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int kb = 0; kb < n; kb += LB) {
+        const int nb = min(LB, n - kb), c0 = kb + nb;
+        for (int j = 0; j < nb; j++) {                                 // panel: pivot, swap, multipliers, update of the panel's own columns
+            const int col = kb + j;
+            lu_pivot_step<false>(A, n, nc, col, tid, T, piv_s, rinv_s, bad_s);
+            const int rows = n - col - 1, cols = c0 - col - 1;
+            for (int t = tid; t < rows * cols; t += T) {
+                const int r = col + 1 + t / cols, cidx = col + 1 + t % cols;
+                const double2 l = A[r * nc + col], u = A[col * nc + cidx];
+                double2 v = A[r * nc + cidx];
+                v.x -= l.x * u.x - l.y * u.y; v.y -= l.x * u.y + l.y * u.x;
+                A[r * nc + cidx] = v;
+            }
+            __syncthreads();
+        }
+        const int ncol = nc - c0;
+        for (int b = tid; b < ncol; b += T) {                          // row block: unit-lower triangular solve per column
+            for (int j = 0; j < nb; j++) {
+                const double2 uj = A[(kb + j) * nc + c0 + b];
+                for (int r = j + 1; r < nb; r++) {
+                    const double2 l = A[(kb + r) * nc + kb + j];
+                    double2 v = A[(kb + r) * nc + c0 + b];
+                    v.x -= l.x * uj.x - l.y * uj.y; v.y -= l.x * uj.y + l.y * uj.x;
+                    A[(kb + r) * nc + c0 + b] = v;
+                }
+            }
+        }
+        __syncthreads();
+        const int m2 = n - c0, tr = (m2 + 3) / 4, tc = (ncol + 1) / 2;
+        for (int t = tid; t < tr * tc; t += T) {                       // trailing update, 4 x 2 register tile
+            const int r0 = c0 + 4 * (t / tc), b0 = c0 + 2 * (t % tc);
+            double2 acc[4][2];
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 2; y++) acc[x][y] = A[min(r0 + x, n - 1) * nc + min(b0 + y, nc - 1)];
+            for (int j = 0; j < nb; j++) {
+                double2 l[4], u[2];
+#pragma unroll
+                for (int x = 0; x < 4; x++) l[x] = A[min(r0 + x, n - 1) * nc + kb + j];
+#pragma unroll
+                for (int y = 0; y < 2; y++) u[y] = A[(kb + j) * nc + min(b0 + y, nc - 1)];
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 2; y++) {
+                        acc[x][y].x -= l[x].x * u[y].x - l[x].y * u[y].y;
+                        acc[x][y].y -= l[x].x * u[y].y + l[x].y * u[y].x;
+                    }
+            }
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 2; y++)
+                    if (r0 + x < n && b0 + y < nc) A[(r0 + x) * nc + b0 + y] = acc[x][y];
+        }
         __syncthreads();
     }
-    // back substitution, one thread per right-hand side
-    for (int rh = tid; rh < nrhs; rh += blockDim.x) {
-        for (int r = n - 1; r >= 0; r--) {
-            double2 s = A[r * nc + n + rh];
-            for (int cidx = r + 1; cidx < n; cidx++) {
-                const double2 a = A[r * nc + cidx], x = A[cidx * nc + n + rh];
-                s.x -= a.x * x.x - a.y * x.y; s.y -= a.x * x.y + a.y * x.x;
-            }
-            const double2 pv = A[r * nc + r];
-            const double den = pv.x * pv.x + pv.y * pv.y;
-            A[r * nc + n + rh] = make_double2((s.x * pv.x + s.y * pv.y) / den, (s.y * pv.x - s.x * pv.y) / den);
-        }
-    }
-    __syncthreads();
-    return bad;
+    lu_back_subst<false>(A, n, nc, nrhs, tid, T);
 }
 
 __global__ void __launch_bounds__(128) k_system_solve(int n, int nrhs, double2 *Z, double2 *F, int *info)
 {
     extern __shared__ __align__(16) double smem_raw[];
     double2 *A = reinterpret_cast<double2 *>(smem_raw);              // [n][n+nrhs] augmented
-    __shared__ int piv_s;
+    __shared__ int piv_s, bad_s;
     __shared__ double2 rinv_s;
     const int iw = blockIdx.x, tid = threadIdx.x, nc = n + nrhs;
     double2 *Zg = Z + (size_t)iw * n * n, *Fg = F + (size_t)iw * n * nrhs;
     for (int t = tid; t < n * n; t += blockDim.x) A[(t / n) * nc + (t % n)] = Zg[t];
     for (int t = tid; t < n * nrhs; t += blockDim.x) A[(t / nrhs) * nc + n + (t % nrhs)] = Fg[t];
+    if (tid == 0) bad_s = 0;
     __syncthreads();
-    const int bad = lu_solve_smem(A, n, nc, nrhs, &piv_s, &rinv_s);
+    if (n > 24) lu_blocked(A, n, nc, nrhs, &piv_s, &rinv_s, &bad_s);
+    else lu_unblocked<false>(A, n, nc, nrhs, tid, blockDim.x, &piv_s, &rinv_s, &bad_s);
     for (int t = tid; t < n * nrhs; t += blockDim.x) Fg[t] = A[(t / nrhs) * nc + n + (t % nrhs)];
-    if (tid == 0 && info) info[iw] = bad;
+    if (tid == 0 && info) info[iw] = bad_s;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3b: farm system response straight from the per-FOWT solves (raft_model.py:1164-1236), one CTA per (frequency, case):
+// K3b: farm system response straight from the per-FOWT solves (raft_model.py:1164-1236):
 // Z_sys = blockdiag_i(-w^2 (M0_i + A_w,i) + i w (B0_i + B_drag_i + B_w,i) + C0_i) + (-w^2 M_arr + i w B_arr + C_arr),
 // F = F_BEM_i + F_iner_i + F_drag_i (+ F_2nd_i) stacked, Xi_sys = Z_sys^-1 F.  Everything is read from device-resident
 // outputs of the drag-linearisation solve: no host assembly of Z, no per-case transfer of nw n^2 complex numbers.
+// WARP = true : small systems (6N <= 24), one WARP per (frequency, case), FARM_WPC systems per CTA, no CTA-wide barriers;
+// WARP = false: one CTA per (frequency, case), blocked LU.
 // ------------------------------------------------------------------------------------------------
 struct FarmParams {
     int N, nC, nw;
@@ -99,18 +189,23 @@ struct FarmParams {
     double2 *Xi;                                // [nC][6N][nw]
     int *info;                                  // [nC][nw] or NULL
 };
+#define FARM_WPC 4
 
-__global__ void __launch_bounds__(128) k_farm_response(DesignsDev D, CasesDev Cs, FarmParams P)
+template <bool WARP>
+__global__ void __launch_bounds__(WARP ? 32 * FARM_WPC : 256) k_farm_response(DesignsDev D, CasesDev Cs, FarmParams P)
 {
     extern __shared__ __align__(16) double smem_raw[];
-    double2 *A = reinterpret_cast<double2 *>(smem_raw);              // [n][n+1]
-    __shared__ int piv_s;
-    __shared__ double2 rinv_s;
-    const int iw = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    __shared__ int piv_s[FARM_WPC], bad_s[FARM_WPC];
+    __shared__ double2 rinv_s[FARM_WPC];
     const int n = 6 * P.N, nc = n + 1, nw = P.nw;
+    const int g = WARP ? (int)(threadIdx.x >> 5) : 0, gtid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const int gsize = WARP ? 32 : (int)blockDim.x;
+    const int iw = WARP ? (int)blockIdx.x * FARM_WPC + g : (int)blockIdx.x, c = blockIdx.y;
+    if (iw >= nw) return;                                            // (warp-uniform; no CTA-wide barrier follows in the WARP variant)
+    double2 *A = reinterpret_cast<double2 *>(smem_raw) + (size_t)g * n * nc;
     const double w = D.w[iw], w2 = w * w;
     const int cp = Cs.primary ? Cs.primary[c] : c;                   // secondary wave trains use their primary's damping
-    for (int t = tid; t < n * n; t += blockDim.x) {
+    for (int t = gtid; t < n * n; t += gsize) {
         const int a = t / n, b = t % n, i = a / 6, j = b / 6;
         double zr = 0.0, zi = 0.0;
         if (i == j) {
@@ -125,20 +220,22 @@ __global__ void __launch_bounds__(128) k_farm_response(DesignsDev D, CasesDev Cs
         if (P.B_arr) zi += w * P.B_arr[t];
         A[a * nc + b] = make_double2(zr, zi);
     }
-    for (int a = tid; a < n; a += blockDim.x) {
+    for (int a = gtid; a < n; a += gsize) {
         const int i = a / 6, e = a - 6 * i;
         const size_t o = (((size_t)i * P.nC + c) * 6 + e) * nw + iw;
         double2 f = P.F_drag[o];
-        const double2 g = P.F_iner[o];
-        f.x += g.x; f.y += g.y;
-        if (P.F_BEM) { const double2 h = P.F_BEM[o]; f.x += h.x; f.y += h.y; }
+        const double2 h = P.F_iner[o];
+        f.x += h.x; f.y += h.y;
+        if (P.F_BEM) { const double2 q = P.F_BEM[o]; f.x += q.x; f.y += q.y; }
         if (Cs.F_2nd) f.x += Cs.F_2nd[o];
         A[a * nc + n] = f;
     }
-    __syncthreads();
-    const int bad = lu_solve_smem(A, n, nc, 1, &piv_s, &rinv_s);
-    for (int a = tid; a < n; a += blockDim.x) P.Xi[((size_t)c * n + a) * nw + iw] = A[a * nc + n];
-    if (tid == 0 && P.info) P.info[(size_t)c * nw + iw] = bad;
+    if (gtid == 0) bad_s[g] = 0;
+    gsync<WARP>();
+    if (WARP) lu_unblocked<true>(A, n, nc, 1, gtid, gsize, &piv_s[g], &rinv_s[g], &bad_s[g]);
+    else lu_blocked(A, n, nc, 1, &piv_s[g], &rinv_s[g], &bad_s[g]);
+    for (int a = gtid; a < n; a += gsize) P.Xi[((size_t)c * n + a) * nw + iw] = A[a * nc + n];
+    if (gtid == 0 && P.info) P.info[(size_t)c * nw + iw] = bad_s[g];
 }
 
 // ------------------------------------------------------------------------------------------------

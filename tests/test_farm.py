@@ -82,3 +82,18 @@ def test_farm_baseline_size_vs_oracle(oracle):
         Xo = oracle.system_response(Zs + z["C_array"][None], F).T
         err = max(response_err(out["Xi_sys"][c, 6 * i:6 * i + 6], Xo[6 * i:6 * i + 6]) for i in range(2))
         assert err < 1e-9, err           # the checker goes through the explicit inverse like the reference (cond ~1e5)
+
+
+@pytest.mark.parametrize("N", [4, 5])
+def test_farm_larger_arrays_vs_oracle(N, oracle):
+    """6N = 24 (last size on the warp-per-system kernel) and 6N = 30 (blocked LU, one CTA per system) against the oracle's
+    per-FOWT solves + explicit-inverse system response."""
+    import bench_extra
+    from raft_b200 import solver
+    packs, C_arr, _ = bench_extra.farm_designs(N, nw=96, max_freq=0.1024)
+    cs = _cases(np.array([[6.0, 12.0, 0.0], [3.0, 8.0, -70.0]]))
+    out = solver.solve_dynamics_farm(solver.DesignBatch(packs), solver.CaseTable(cs), C_arr=C_arr, n_iter=10)
+    Xo, passes = bench_extra._oracle_farm(packs, C_arr, cs)
+    assert np.array_equal(passes, out["status"][:, :, 0]) and not np.any(out["info"])
+    err = max(response_err(out["Xi_sys"][:, 6 * i:6 * i + 6], Xo[:, 6 * i:6 * i + 6]) for i in range(N))
+    assert err < 1e-9, err
