@@ -739,8 +739,10 @@ static int farm_launch(const raftk_designs *d, const raftk_cases *c, const raftk
         return set_err(RAFTK_EINVAL, "farm response needs B_drag, F_drag, F_iner of the per-FOWT solve and farm.Xi_sys");
     if (d->n_bem_head > 0 && !solved->F_BEM) return set_err(RAFTK_EINVAL, "farm response: the designs carry BEM excitation, F_BEM is required");
     const int n = 6 * f->n_fowt;
-    const bool warp = n <= 24;                          // small systems: one warp per (frequency, case), FARM_WPC per CTA
-    const size_t smem = (size_t)(warp ? FARM_WPC : 1) * n * (n + 1) * sizeof(double2);
+    const bool warp = n <= 48;                          // one warp per (frequency, case), wpc systems per CTA (<= ~100 KB of matrices)
+    const size_t sys_bytes = (size_t)n * (n + 1) * sizeof(double2);
+    const int wpc = warp ? (int)std::max<size_t>(1, std::min<size_t>(FARM_WPC, (100 * 1024) / sys_bytes)) : 1;
+    const size_t smem = (size_t)wpc * sys_bytes;
     if (smem > 227 * 1024) return set_err(RAFTK_EINVAL, "farm too large for the shared-memory solver (6N (6N+1) 16 B > 227 KB: N <= 19)");
     if (c->n_cases > 65535) return set_err(RAFTK_EINVAL, "farm response: more than 65535 cases per call");
     static SmemOptIn opt_w(48 * 1024), opt_b(48 * 1024);
@@ -758,7 +760,7 @@ static int farm_launch(const raftk_designs *d, const raftk_cases *c, const raftk
     P.Xi = reinterpret_cast<double2 *>(f->Xi_sys); P.info = f->info;
     {
         ProfScope ps(st, 1);
-        if (warp) k_farm_response<true><<<dim3((d->nw + FARM_WPC - 1) / FARM_WPC, c->n_cases), 32 * FARM_WPC, smem, st>>>(D, C, P);
+        if (warp) k_farm_response<true><<<dim3((d->nw + wpc - 1) / wpc, c->n_cases), 32 * wpc, smem, st>>>(D, C, P);
         else k_farm_response<false><<<dim3(d->nw, c->n_cases), 256, smem, st>>>(D, C, P);
     }
     g_launches++;

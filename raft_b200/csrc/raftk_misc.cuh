@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(128) k_system_solve(int n, int nrhs, double2 *
 // Z_sys = blockdiag_i(-w^2 (M0_i + A_w,i) + i w (B0_i + B_drag_i + B_w,i) + C0_i) + (-w^2 M_arr + i w B_arr + C_arr),
 // F = F_BEM_i + F_iner_i + F_drag_i (+ F_2nd_i) stacked, Xi_sys = Z_sys^-1 F.  Everything is read from device-resident
 // outputs of the drag-linearisation solve: no host assembly of Z, no per-case transfer of nw n^2 complex numbers.
-// WARP = true : small systems (6N <= 24), one WARP per (frequency, case), FARM_WPC systems per CTA, no CTA-wide barriers;
+// WARP = true : systems up to 6N = 48, one WARP per (frequency, case), up to FARM_WPC systems per CTA, no CTA-wide barriers
+//               (measured: at 6N = 48 the barrier-bound CTA-per-system kernel needed 10.6 ms for 65 536 systems);
 // WARP = false: one CTA per (frequency, case), blocked LU.
 // ------------------------------------------------------------------------------------------------
 struct FarmParams {
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(WARP ? 32 * FARM_WPC : 256) k_farm_response(De
     const int n = 6 * P.N, nc = n + 1, nw = P.nw;
     const int g = WARP ? (int)(threadIdx.x >> 5) : 0, gtid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
     const int gsize = WARP ? 32 : (int)blockDim.x;
-    const int iw = WARP ? (int)blockIdx.x * FARM_WPC + g : (int)blockIdx.x, c = blockIdx.y;
+    const int iw = WARP ? (int)(blockIdx.x * (blockDim.x >> 5)) + g : (int)blockIdx.x, c = blockIdx.y;
     if (iw >= nw) return;                                            // (warp-uniform; no CTA-wide barrier follows in the WARP variant)
     double2 *A = reinterpret_cast<double2 *>(smem_raw) + (size_t)g * n * nc;
     const double w = D.w[iw], w2 = w * w;

@@ -84,9 +84,9 @@ def test_farm_baseline_size_vs_oracle(oracle):
         assert err < 1e-9, err           # the checker goes through the explicit inverse like the reference (cond ~1e5)
 
 
-@pytest.mark.parametrize("N", [4, 5])
+@pytest.mark.parametrize("N", [4, 5, 9])
 def test_farm_larger_arrays_vs_oracle(N, oracle):
-    """6N = 24 (last size on the warp-per-system kernel) and 6N = 30 (blocked LU, one CTA per system) against the oracle's
+    """6N = 24, 30 (warp-per-system kernel, 4 resp. 3 systems per CTA) and 6N = 54 (blocked LU, one CTA per system) against the oracle's
     per-FOWT solves + explicit-inverse system response."""
     import bench_extra
     from raft_b200 import solver
