@@ -51,10 +51,10 @@ def build_workload(args, rank, world):
     if args.workload == "cfg2":
         P = grid.regrid(load_packed("cfg2_VolturnUS-S_nw64"), args.nw or 1024, 0.512)
         nC = args.cases or 64
-        cs_all = sea_states(2, nC * world)
-        cs = {k: v[rank * nC:(rank + 1) * nC] for k, v in cs_all.items()}
+        # weak scaling by cases: rank r draws its own sea states with seed 2 + 1000 r, so rank 0 solves the N = 1 workload at every N
+        cs = sea_states(2 + 1000 * rank, nC)
         cfg = dict(workload="cfg2: designs/VolturnUS-S.yaml (strip theory, turbine+mooring stripped, C_moor=diag(7e4,7e4,0,0,0,1.2e8)), "
-                            "%d freq bins x %d sea states per GPU, fp64, nIter=10, tol=0.01" % (len(P["w"]), nC),
+                            "%d freq bins x %d sea states per GPU (rank r: seed 2 + 1000 r), fp64, nIter=10, tol=0.01" % (len(P["w"]), nC),
                    designs_per_gpu=1, cases_per_gpu=nC, nw=len(P["w"]), submerged_nodes=int(len(P["node_ls"])))
         return [P], cs, cfg
     elif args.workload in ("cfg3", "cfg3q"):
@@ -77,8 +77,7 @@ def build_workload(args, rank, world):
             second = " + second-order forces from marin_semi.12d (potSecOrder 2)"
         f = FOWT(D, w, depth=float(z["P_depth"]), matrices=mats)
         f.calcHydroConstants()
-        cs_all = sea_states(3, nC * world)
-        cs = {k: v[rank * nC:(rank + 1) * nC] for k, v in cs_all.items()}
+        cs = sea_states(3 + 1000 * rank, nC)
         cfg = dict(workload="cfg3: examples/OC4semi-WAMIT_Coefs.yaml (potModMaster 3: BEM A/B/X tables via readHydro of marin_semi.1/.3, "
                             "drag-only strips)%s, %d freq bins x %d sea states per GPU, fp64" % (second, nw, nC),
                    designs_per_gpu=1, cases_per_gpu=nC, nw=nw)
@@ -503,6 +502,13 @@ def measure(args, designs, cs, cfg, rank, world, dev, full):
     Xi_host = sess.out["Xi"].cpu().numpy() if not args.no_parity and rank == 0 else None
     mean_passes = float(status[..., 0].mean())
     k2_ms = kms[2] / max(kn[2], 1)
+    per_rank = None
+    if world > 1:
+        # the solve kernel alone on every rank's own units (no exchange): what the slowest rank costs, as opposed to the exchange
+        mine = torch.tensor([k2_ms * kn[2] / reps, float(status[..., 0].max()), mean_passes], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = dict(solve_ms=[round(float(v[0]), 5) for v in allr], max_passes=[int(v[1]) for v in allr], mean_passes=[round(float(v[2]), 3) for v in allr])
     launches_per_step = kn[2] / reps
     Ns, Nm = batch.n_nodes_total / batch.n_designs, batch.n_members_total / batch.n_designs      # mean per design
     b_alg = algorithmic_bytes_per_solve(Ns, Nm, nC, nw, bem=batch.n_bem_head > 0)
@@ -627,6 +633,11 @@ def measure(args, designs, cs, cfg, rank, world, dev, full):
                     roofline=roofline, roofline_fp64=roofline_fp64, cpu_baseline=cpu, parity=parity)
         if exchange_check is not None:
             line["exchange_verified"] = exchange_check
+        if per_rank is not None:
+            per_rank["exchange_and_skew_ms"] = ms / args.steps - max(per_rank["solve_ms"])
+            per_rank["note"] = ("solve_ms: this rank's solve kernel(s) alone on its own units; a step lasts as long as the slowest rank (a unit's time "
+                                "follows its pass count) plus the exchange")
+            line["per_rank"] = per_rank
         if sustained is not None:
             line["sustained"] = sustained
     if sh is not None:
