@@ -18,9 +18,10 @@
  *   - *_host entry points take HOST pointers, stage through an internal device arena
  *     (grown on demand, cached per process), and are synchronous.
  *
- * Scope: rigid 6-DOF FOWTs, strip-theory members (+ optional BEM tables, + optional external QTF for
- * second-order difference-frequency forces), one wave train drives the drag linearisation
- * (raft_fowt.py:1910).  See DESIGN.md for what is out of scope.
+ * Scope: rigid 6-DOF FOWTs, strip-theory members (+ optional BEM tables, + optional external QTF or slender-body QTF for
+ * second-order difference-frequency forces), one wave train drives the drag linearisation (raft_fowt.py:1910); coupled
+ * farms (6N DOF); FOWTs with generalised degrees of freedom (flexible members) through raftk_general_*; the multi-GPU
+ * exchange of the responses fused into the solve (raftk_peers).  See DESIGN.md for what is out of scope.
  */
 #ifndef RAFTK_H
 #define RAFTK_H
@@ -274,12 +275,13 @@ int raftk_qtf_slender_dev(const raftk_slender *s, int32_t n_cases, const double 
 int raftk_qtf_slender_host(const raftk_slender *s, int32_t n_cases, const double *beta_rad, const double *Xi_rao, double *qtf);
 
 /*
- * STAGED -- compiled, restated from the pinned checker, NOT YET VALIDATED ON HARDWARE (next row of SURVEY.md 8f).
  * Model.solveDynamics for ONE FOWT with generalised degrees of freedom (flexible members, n_dof > 6; raft_fowt.py:1854-1857,
  * 1886-1888, 1913-1929; raft_model.py:1052-1142) and n_cases single-train cases.  Every submerged strip node carries the
  * 6 x n_dof block of fowt.T of its structural node (Tn) and its offset from that node (rr; zero on flexible members):
  * node motion = Tn Xi, node load -> Tn^T [f ; rr x f].  M, B, C: the constant system matrices of raft_model.py:1045-1047.
- * Xi complex [n_cases,n_dof,nw]; status [n_cases,4] = passes, converged, flags, 0.
+ * Xi complex [n_cases,n_dof,nw]; status [n_cases,4] = passes, converged, flags, 0.  The n_dof x n_dof impedance of every (case,
+ * frequency, pass) is solved by a blocked LU with partial pivoting (LAPACK's pivot rule and elimination order); validated on
+ * B200 against the reference's 150-DOF VolturnUS-S-flexible run (tests/test_general_dofs.py, 1e-10).  n_dof <= 256.
  */
 typedef struct raftk_general {
     int32_t n_dof, nw, n_nodes, _pad0;

@@ -78,7 +78,7 @@ GENERAL_ARRAYS = ("w", "k", "node_r", "node_frame", "node_circ", "node_Imat", "n
 
 
 class RaftkGeneral(C.Structure):
-    """STAGED (not yet validated on hardware): generalised degrees of freedom, include/raftk.h raftk_general."""
+    """Generalised degrees of freedom (flexible members), include/raftk.h raftk_general."""
     _fields_ = ([("n_dof", C.c_int32), ("nw", C.c_int32), ("n_nodes", C.c_int32), ("_pad0", C.c_int32),
                  ("depth", C.c_double), ("rho", C.c_double), ("dw", C.c_double)] + [(n, C.c_void_p) for n in GENERAL_ARRAYS])
 

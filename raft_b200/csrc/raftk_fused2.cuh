@@ -315,15 +315,13 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
     double2 *Eg = P.Eg + ((size_t)d * Cs.nC + c) * (size_t)NmP * nw;      // member base phases   [NmP][nw]
     double2 *Ag = P.Ag + ((size_t)d * Cs.nC + c) * (size_t)P.maxZ * nw;   // first-node depth pairs [maxZ][nw]
 
-    // ---- prologue per frequency: sea state, member bases, class factors, excitation F0 -------------------------------
+    // ---- prologue (a), per frequency: sea state, step-class factors, member base phases / depth pairs ----------------------
     for (int t = tid; t < nloc && !plan_overflow; t += T) {
         const int i = f_begin + t;
         const double w = D.w[i], k = D.k[i];
         const double zeta = zeta_f2(Cs, c, i, nw, w, D.dw);
         if (P.zeta_out && d == 0) P.zeta_out[(size_t)c * nw + i] = zeta;
         const double zw = zeta * w;
-        const bool deep = k * D.depth > 89.4;
-        const double tanh_kh = tanh(k * D.depth);
 #pragma unroll 1
         for (int x = 0; x < nW; x++) {
             double s_, c_;
@@ -343,81 +341,126 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
             depth_once(k, D.depth, s_zkey[x], &S_, &C_);
             Ag[(size_t)x * nw + i] = make_double2(0.5 * (C_ + S_), 0.5 * (C_ - S_));
         }
-        double Fr[6] = {0, 0, 0, 0, 0, 0}, Fi[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 1
         for (int m = 0; m < Nm; m++) {
             const double *o = s_mem + m * MEM_STRIDE;
-            const int j0 = s_imem[IMEM_STRIDE * m], j1 = s_imem[IMEM_STRIDE * m + 1];
-            const double ls0 = n_ls[j0];
             double se, ce;
             sincos_once(-(k * (cb * o[22] + sb * o[23])), &se, &ce);
-            double er = zw * ce, ei = zw * se;
-            Eg[(size_t)m * nw + i] = make_double2(er, ei);
-            const double2 a0 = Ag[(size_t)s_imem[IMEM_STRIDE * m + 4] * nw + i];
-            double ap = a0.x, am = a0.y;
-            const double hq = o[18], h1 = o[19], h2 = o[20];
-            double Aqr = 0, Aqi = 0, A1r = 0, A1i = 0, A2r = 0, A2i = 0, L1r = 0, L1i = 0, L2r = 0, L2i = 0;
-            for (int j = j0; j < j1; j++) {
-                {
-                    const double2 W = s_wtab[s_nodew[j] + t], H = s_htab[s_nodeh[j] + t];
-                    const double tr = fma(er, W.x, -ei * W.y); ei = fma(er, W.y, ei * W.x); er = tr;
-                    ap *= H.x; am *= H.y;
-                }
-                const double inq = n_inq[j], pa = n_pa[j];
-                double in1 = n_in1[j], in2 = n_in2[j], in1i = 0.0, in2i = 0.0;
-                if (D.node_in_p1_w) {
-                    const size_t jg = (size_t)(nbase + j);
-                    const double2 v1 = D.node_in_p1_w[jg * nw + i], v2 = D.node_in_p2_w[jg * nw + i];
-                    in1 = v1.x; in1i = v1.y; in2 = v2.x; in2i = v2.y;
-                }
-                if (inq != 0.0 || in1 != 0.0 || in2 != 0.0 || in1i != 0.0 || in2i != 0.0 || pa != 0.0) {
-                    const double ls = n_ls[j], Cc = ap + am, Sc = ap - am;
-                    double cr, ci;
-                    proj(er, ei, Cc, Sc, hq, o[2], cr, ci);
-                    double fqr = -w * inq * ci, fqi = w * inq * cr;
-                    proj(er, ei, Cc, Sc, h1, o[5], cr, ci);
-                    const double f1r = -w * (in1 * ci + in1i * cr), f1i = w * (in1 * cr - in1i * ci);
-                    proj(er, ei, Cc, Sc, h2, o[8], cr, ci);
-                    const double f2r = -w * (in2 * ci + in2i * cr), f2i = w * (in2 * cr - in2i * ci);
-                    if (pa != 0.0 && w != 0.0) {
-                        double Pd = Cc * tanh_kh;
-                        if (deep) Pd = Cc + exp_once(-k * (o[21] + (ls - ls0) * o[2] + 2.0 * D.depth));
-                        const double sc = pa * Pd / w;
-                        fqr = fma(sc, er, fqr); fqi = fma(sc, ei, fqi);
-                    }
-                    Aqr += fqr; Aqi += fqi; A1r += f1r; A1i += f1i; A2r += f2r; A2i += f2i;
-                    L1r += ls * f1r; L1i += ls * f1i; L2r += ls * f2r; L2i += ls * f2i;
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                Fr[a] += o[a] * Aqr + o[3 + a] * A1r + o[6 + a] * A2r;
-                Fi[a] += o[a] * Aqi + o[3 + a] * A1i + o[6 + a] * A2i;
-                Fr[3 + a] += o[9 + a] * Aqr + o[12 + a] * A1r + o[15 + a] * A2r + o[6 + a] * L1r - o[3 + a] * L2r;
-                Fi[3 + a] += o[9 + a] * Aqi + o[12 + a] * A1i + o[15 + a] * A2i + o[6 + a] * L1i - o[3 + a] * L2i;
-            }
-        }
-        if (P.Finer_out)
-            for (int a = 0; a < 6; a++) P.Finer_out[ogl + (size_t)a * nw + i] = make_double2(Fr[a], Fi[a]);
-        if (D.n_bem_head > 0) {
-            double Br[6], Bi[6];
-            bem_excitation(D, d, i, k, beta, sb, cb, zeta, Br, Bi);
-#pragma unroll
-            for (int a = 0; a < 6; a++) {
-                if (P.Fbem_out) P.Fbem_out[ogl + (size_t)a * nw + i] = make_double2(Br[a], Bi[a]);
-                Fr[a] += Br[a]; Fi[a] += Bi[a];
-            }
-        } else if (P.Fbem_out) {
-            for (int a = 0; a < 6; a++) P.Fbem_out[ogl + (size_t)a * nw + i] = make_double2(0.0, 0.0);
-        }
-        if (Cs.F_2nd) {
-#pragma unroll
-            for (int a = 0; a < 6; a++) Fr[a] += Cs.F_2nd[ogl + (size_t)a * nw + i];
+            Eg[(size_t)m * nw + i] = make_double2(zw * ce, zw * se);
         }
 #pragma unroll
         for (int a = 0; a < 6; a++) {
-            P.F0g[ogl + (size_t)a * nw + i] = make_double2(Fr[a], Fi[a]);
             if (P.Xi_init) { const double2 x0 = P.Xi_init[ogl + (size_t)a * nw + i]; s_xi[(2 * a) * nwl + t] = x0.x; s_xi[(2 * a + 1) * nwl + t] = x0.y; }
             else { s_xi[(2 * a) * nwl + t] = P.xi_start; s_xi[(2 * a + 1) * nwl + t] = 0.0; }
+        }
+    }
+    // the two bins of this thread: local indices t0 = tid, t1 = tid + T.  A bin beyond the slice is walked with a zero wave
+    // amplitude and a zero iterate (contributes exact zeros to the sums) and is skipped in the solve phase.
+    const bool ok0 = tid < nloc, ok1 = tid + T < nloc;
+    const int t0 = ok0 ? tid : 0, t1 = ok1 ? tid + T : t0;
+    const int ibase = nloc > 0 ? f_begin : 0;                 // a CTA beyond the grid still reads in-range table entries
+    const int i0 = ibase + t0, i1 = ibase + t1;
+    const double w0 = ok0 ? D.w[i0] : 0.0, w1 = ok1 ? D.w[i1] : 0.0;
+    const double2 *wtA = s_wtab + t0, *wtB = s_wtab + t1, *htA = s_htab + t0, *htB = s_htab + t1;
+    const double2 zero2 = make_double2(0.0, 0.0);
+
+    // ---- prologue (b): strip inertial + dynamic-pressure excitation F0, node walk of both bins interleaved -----------------
+    if (!plan_overflow) {
+        const double kA = D.k[i0], kB = D.k[i1];
+        const bool deepA = kA * D.depth > 89.4, deepB = kB * D.depth > 89.4;
+        const double thA = tanh(kA * D.depth), thB = tanh(kB * D.depth);
+        double FrA[6], FiA[6], FrB[6], FiB[6];
+#pragma unroll
+        for (int a = 0; a < 6; a++) { FrA[a] = 0.0; FiA[a] = 0.0; FrB[a] = 0.0; FiB[a] = 0.0; }
+        const bool mcf = D.node_in_p1_w != nullptr;
+        for (int m = 0; m < Nm; m++) {
+            const double *o = s_mem + m * MEM_STRIDE;
+            const int j0 = s_imem[IMEM_STRIDE * m], j1 = s_imem[IMEM_STRIDE * m + 1], zc = s_imem[IMEM_STRIDE * m + 4];
+            const double ls0 = n_ls[j0];
+            const double2 eA = ok0 ? Eg[(size_t)m * nw + i0] : zero2, eB = ok1 ? Eg[(size_t)m * nw + i1] : zero2;
+            const double2 aA = Ag[(size_t)zc * nw + i0], aB = Ag[(size_t)zc * nw + i1];
+            double erA = eA.x, eiA = eA.y, apA = aA.x, amA = aA.y, erB = eB.x, eiB = eB.y, apB = aB.x, amB = aB.y;
+            const double hq = o[18], h1 = o[19], h2 = o[20];
+            double AqrA = 0, AqiA = 0, A1rA = 0, A1iA = 0, A2rA = 0, A2iA = 0, L1rA = 0, L1iA = 0, L2rA = 0, L2iA = 0;
+            double AqrB = 0, AqiB = 0, A1rB = 0, A1iB = 0, A2rB = 0, A2iB = 0, L1rB = 0, L1iB = 0, L2rB = 0, L2iB = 0;
+            for (int j = j0; j < j1; j++) {
+                const int ow = s_nodew[j], oh = s_nodeh[j];
+                const double2 WA = wtA[ow], HA = htA[oh], WB = wtB[ow], HB = htB[oh];
+                { const double tr = fma(erA, WA.x, -eiA * WA.y); eiA = fma(erA, WA.y, eiA * WA.x); erA = tr; }
+                { const double tr = fma(erB, WB.x, -eiB * WB.y); eiB = fma(erB, WB.y, eiB * WB.x); erB = tr; }
+                apA *= HA.x; amA *= HA.y; apB *= HB.x; amB *= HB.y;
+                const double inq = n_inq[j], pa = n_pa[j], in1 = n_in1[j], in2 = n_in2[j], ls = n_ls[j];
+                if (!mcf && inq == 0.0 && in1 == 0.0 && in2 == 0.0 && pa == 0.0) continue;       // potMod strip: drag only
+#define F2_F0_NODE(ER, EI, AP, AM, WW, KK, II, TH, DEEP, AQR, AQI, A1R, A1I, A2R, A2I, L1R, L1I, L2R, L2I)                     \
+    {                                                                                                                             \
+        double i1r = in1, i1i = 0.0, i2r = in2, i2i = 0.0;                                                                        \
+        if (mcf) {                                                                                                                \
+            const size_t jg = (size_t)(nbase + j);                                                                                \
+            const double2 v1 = D.node_in_p1_w[jg * nw + II], v2 = D.node_in_p2_w[jg * nw + II];                                   \
+            i1r = v1.x; i1i = v1.y; i2r = v2.x; i2i = v2.y;                                                                        \
+        }                                                                                                                         \
+        const double Cc = AP + AM, Sc = AP - AM;                                                                                  \
+        double cr, ci;                                                                                                            \
+        proj(ER, EI, Cc, Sc, hq, o[2], cr, ci);                                                                                   \
+        double fqr = -WW * inq * ci, fqi = WW * inq * cr;                                                                         \
+        proj(ER, EI, Cc, Sc, h1, o[5], cr, ci);                                                                                   \
+        const double f1r = -WW * (i1r * ci + i1i * cr), f1i = WW * (i1r * cr - i1i * ci);                                         \
+        proj(ER, EI, Cc, Sc, h2, o[8], cr, ci);                                                                                   \
+        const double f2r = -WW * (i2r * ci + i2i * cr), f2i = WW * (i2r * cr - i2i * ci);                                         \
+        if (pa != 0.0 && WW != 0.0) {                                                                                             \
+            double Pd = Cc * TH;                                                                                                  \
+            if (DEEP) Pd = Cc + exp_once(-KK * (o[21] + (ls - ls0) * o[2] + 2.0 * D.depth));                                      \
+            const double sc = pa * Pd / WW;                                                                                       \
+            fqr = fma(sc, ER, fqr); fqi = fma(sc, EI, fqi);                                                                       \
+        }                                                                                                                         \
+        AQR += fqr; AQI += fqi; A1R += f1r; A1I += f1i; A2R += f2r; A2I += f2i;                                                   \
+        L1R += ls * f1r; L1I += ls * f1i; L2R += ls * f2r; L2I += ls * f2i;                                                       \
+    }
+                F2_F0_NODE(erA, eiA, apA, amA, w0, kA, i0, thA, deepA, AqrA, AqiA, A1rA, A1iA, A2rA, A2iA, L1rA, L1iA, L2rA, L2iA)
+                F2_F0_NODE(erB, eiB, apB, amB, w1, kB, i1, thB, deepB, AqrB, AqiB, A1rB, A1iB, A2rB, A2iB, L1rB, L1iB, L2rB, L2iB)
+#undef F2_F0_NODE
+            }
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                FrA[a] += o[a] * AqrA + o[3 + a] * A1rA + o[6 + a] * A2rA;
+                FiA[a] += o[a] * AqiA + o[3 + a] * A1iA + o[6 + a] * A2iA;
+                FrA[3 + a] += o[9 + a] * AqrA + o[12 + a] * A1rA + o[15 + a] * A2rA + o[6 + a] * L1rA - o[3 + a] * L2rA;
+                FiA[3 + a] += o[9 + a] * AqiA + o[12 + a] * A1iA + o[15 + a] * A2iA + o[6 + a] * L1iA - o[3 + a] * L2iA;
+                FrB[a] += o[a] * AqrB + o[3 + a] * A1rB + o[6 + a] * A2rB;
+                FiB[a] += o[a] * AqiB + o[3 + a] * A1iB + o[6 + a] * A2iB;
+                FrB[3 + a] += o[9 + a] * AqrB + o[12 + a] * A1rB + o[15 + a] * A2rB + o[6 + a] * L1rB - o[3 + a] * L2rB;
+                FiB[3 + a] += o[9 + a] * AqiB + o[12 + a] * A1iB + o[15 + a] * A2iB + o[6 + a] * L1iB - o[3 + a] * L2iB;
+            }
+        }
+        // per bin: optional outputs, BEM excitation, second-order forces; the sum is parked in the workspace
+#pragma unroll 1
+        for (int bsel = 0; bsel < 2; bsel++) {
+            if (!(bsel == 0 ? ok0 : ok1)) continue;
+            const int i = bsel == 0 ? i0 : i1;
+            double Fr[6], Fi[6];
+#pragma unroll
+            for (int a = 0; a < 6; a++) { Fr[a] = bsel == 0 ? FrA[a] : FrB[a]; Fi[a] = bsel == 0 ? FiA[a] : FiB[a]; }
+            if (P.Finer_out)
+                for (int a = 0; a < 6; a++) P.Finer_out[ogl + (size_t)a * nw + i] = make_double2(Fr[a], Fi[a]);
+            if (D.n_bem_head > 0) {
+                const double k = D.k[i], w = D.w[i];
+                const double zeta = zeta_f2(Cs, c, i, nw, w, D.dw);
+                double Br[6], Bi[6];
+                bem_excitation(D, d, i, k, beta, sb, cb, zeta, Br, Bi);
+#pragma unroll
+                for (int a = 0; a < 6; a++) {
+                    if (P.Fbem_out) P.Fbem_out[ogl + (size_t)a * nw + i] = make_double2(Br[a], Bi[a]);
+                    Fr[a] += Br[a]; Fi[a] += Bi[a];
+                }
+            } else if (P.Fbem_out) {
+                for (int a = 0; a < 6; a++) P.Fbem_out[ogl + (size_t)a * nw + i] = make_double2(0.0, 0.0);
+            }
+            if (Cs.F_2nd) {
+#pragma unroll
+                for (int a = 0; a < 6; a++) Fr[a] += Cs.F_2nd[ogl + (size_t)a * nw + i];
+            }
+#pragma unroll
+            for (int a = 0; a < 6; a++) P.F0g[ogl + (size_t)a * nw + i] = make_double2(Fr[a], Fi[a]);
         }
     }
     if (plan_overflow) {
@@ -440,15 +483,6 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
         __syncthreads();
     }
 
-    // the two bins of this thread: local indices t0 = tid, t1 = tid + T.  A bin beyond the slice is walked with a zero wave
-    // amplitude and a zero iterate (contributes exact zeros to the sums) and is skipped in the solve phase.
-    const bool ok0 = tid < nloc, ok1 = tid + T < nloc;
-    const int t0 = ok0 ? tid : 0, t1 = ok1 ? tid + T : t0;
-    const int ibase = nloc > 0 ? f_begin : 0;                 // a CTA beyond the grid still reads in-range table entries
-    const int i0 = ibase + t0, i1 = ibase + t1;
-    const double w0 = ok0 ? D.w[i0] : 0.0, w1 = ok1 ? D.w[i1] : 0.0;
-    const double2 *wtA = s_wtab + t0, *wtB = s_wtab + t1, *htA = s_htab + t0, *htB = s_htab + t1;
-    const double2 zero2 = make_double2(0.0, 0.0);
 
     for (int it = 0; it < max_pass; it++) {
         if (!secondary) {

@@ -178,8 +178,9 @@ __global__ void __launch_bounds__(128) k_system_solve(int n, int nrhs, double2 *
 // Z_sys = blockdiag_i(-w^2 (M0_i + A_w,i) + i w (B0_i + B_drag_i + B_w,i) + C0_i) + (-w^2 M_arr + i w B_arr + C_arr),
 // F = F_BEM_i + F_iner_i + F_drag_i (+ F_2nd_i) stacked, Xi_sys = Z_sys^-1 F.  Everything is read from device-resident
 // outputs of the drag-linearisation solve: no host assembly of Z, no per-case transfer of nw n^2 complex numbers.
-// WARP = true : systems up to 6N = 48, one WARP per (frequency, case), up to FARM_WPC systems per CTA, no CTA-wide barriers
-//               (measured: at 6N = 48 the barrier-bound CTA-per-system kernel needed 10.6 ms for 65 536 systems);
+// WARP = true : small systems (6N <= 24), one WARP per (frequency, case), up to FARM_WPC systems per CTA, no CTA-wide barriers
+//               (65 536 systems: 6N = 12 0.40 ms against 0.90 ms with a CTA per system, 6N = 24 1.38 against 2.20 ms; at 6N = 48 the
+//               warp variant is slower -- 13.6 against 10.6 ms -- with only 6 warps resident per SM);
 // WARP = false: one CTA per (frequency, case), blocked LU.
 // ------------------------------------------------------------------------------------------------
 struct FarmParams {

@@ -89,3 +89,25 @@ def test_sharded_solve_single_rank_matches_plain():
     xi_h, st_h, h2d, d2h = sh.step_host(n_iter=10)
     assert np.array_equal(xi_h.numpy(), ref["Xi"]) and np.array_equal(st_h.numpy(), ref["status"]) and h2d > 0 and d2h > 0
     sh.close()
+
+
+def test_second_device_has_its_own_library_state():
+    """A process that drives two GPUs (DeviceSession(device=...)): shared-memory opt-ins, arenas and scratch are per device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    from raft_b200 import grid, solver
+    _, P = load_golden("cfg2_VolturnUS-S_nw64")
+    Q = grid.regrid(P, 256, 0.512)
+    cs = sea_states(3, 3)
+    batch, cases = solver.DesignBatch(Q), solver.CaseTable(cs)
+    outs = []
+    for d in (0, 1):
+        sess = solver.DeviceSession(batch, cases, device=torch.device("cuda", d))
+        o = sess.solve(n_iter=10)
+        torch.cuda.synchronize(d)
+        outs.append((o["Xi"].cpu().numpy(), o["status"].cpu().numpy()))
+        with torch.cuda.device(d):
+            host = solver.solve_dynamics(batch, cases, n_iter=10)              # arena of the current device
+        assert np.array_equal(host["Xi"], outs[-1][0])
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
