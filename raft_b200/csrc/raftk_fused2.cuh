@@ -207,6 +207,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // (node walks, reductions, 6x6 LU: ~120 KB of SASS) should stay resident in the instruction cache
 __device__ __noinline__ void sincos_once(double x, double *s, double *c) { sincos(x, s, c); }
 __device__ __noinline__ double exp_once(double x) { return exp(x); }
+// two-argument forms for the thread's two bins: the two evaluations are independent, so their polynomial chains can overlap
+__device__ __noinline__ double4 sincos2_once(double x0, double x1)
+{
+    double s0, c0, s1, c1;
+    sincos(x0, &s0, &c0);
+    sincos(x1, &s1, &c1);
+    return make_double4(c0, s0, c1, s1);
+}
+__device__ __noinline__ double4 exp2pm_once(double a0, double a1) { return make_double4(exp(a0), exp(-a0), exp(a1), exp(-a1)); }
+__device__ __noinline__ double4 depth2_once(double k0, double k1, double h, double z)
+{
+    double s0, c0, p0, s1, c1, p1;
+    depth_funcs(k0, h, z, s0, c0, p0);
+    depth_funcs(k1, h, z, s1, c1, p1);
+    return make_double4(0.5 * (c0 + s0), 0.5 * (c0 - s0), 0.5 * (c1 + s1), 0.5 * (c1 - s1));
+}
 __device__ __noinline__ double jonswap_once(double w, double Hs, double Tp, double Gamma) { return jonswap(w, Hs, Tp, Gamma); }
 // sea_state_zeta (raftk_tables.cuh) with the spectrum evaluated out of line
 __device__ __forceinline__ double zeta_f2(const CasesDev &Cs, int c, int i, int nw, double w, double dw)
@@ -315,45 +331,6 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
     double2 *Eg = P.Eg + ((size_t)d * Cs.nC + c) * (size_t)NmP * nw;      // member base phases   [NmP][nw]
     double2 *Ag = P.Ag + ((size_t)d * Cs.nC + c) * (size_t)P.maxZ * nw;   // first-node depth pairs [maxZ][nw]
 
-    // ---- prologue (a), per frequency: sea state, step-class factors, member base phases / depth pairs ----------------------
-    for (int t = tid; t < nloc && !plan_overflow; t += T) {
-        const int i = f_begin + t;
-        const double w = D.w[i], k = D.k[i];
-        const double zeta = zeta_f2(Cs, c, i, nw, w, D.dw);
-        if (P.zeta_out && d == 0) P.zeta_out[(size_t)c * nw + i] = zeta;
-        const double zw = zeta * w;
-#pragma unroll 1
-        for (int x = 0; x < nW; x++) {
-            double s_, c_;
-            sincos_once(-(k * (s_wkey[2 * x] * cb + s_wkey[2 * x + 1] * sb)), &s_, &c_);
-            s_wtab[x * nwl + t] = make_double2(c_, s_);
-        }
-#pragma unroll 1
-        for (int x = 0; x < nH; x++) {
-            const double a = k * s_hkey[x];
-            s_htab[x * nwl + t] = make_double2(exp_once(a), exp_once(-a));
-        }
-        s_wtab[P.maxW * nwl + t] = make_double2(1.0, 0.0);
-        s_htab[P.maxH * nwl + t] = make_double2(1.0, 1.0);
-#pragma unroll 1
-        for (int x = 0; x < nZ; x++) {
-            double S_, C_;
-            depth_once(k, D.depth, s_zkey[x], &S_, &C_);
-            Ag[(size_t)x * nw + i] = make_double2(0.5 * (C_ + S_), 0.5 * (C_ - S_));
-        }
-#pragma unroll 1
-        for (int m = 0; m < Nm; m++) {
-            const double *o = s_mem + m * MEM_STRIDE;
-            double se, ce;
-            sincos_once(-(k * (cb * o[22] + sb * o[23])), &se, &ce);
-            Eg[(size_t)m * nw + i] = make_double2(zw * ce, zw * se);
-        }
-#pragma unroll
-        for (int a = 0; a < 6; a++) {
-            if (P.Xi_init) { const double2 x0 = P.Xi_init[ogl + (size_t)a * nw + i]; s_xi[(2 * a) * nwl + t] = x0.x; s_xi[(2 * a + 1) * nwl + t] = x0.y; }
-            else { s_xi[(2 * a) * nwl + t] = P.xi_start; s_xi[(2 * a + 1) * nwl + t] = 0.0; }
-        }
-    }
     // the two bins of this thread: local indices t0 = tid, t1 = tid + T.  A bin beyond the slice is walked with a zero wave
     // amplitude and a zero iterate (contributes exact zeros to the sums) and is skipped in the solve phase.
     const bool ok0 = tid < nloc, ok1 = tid + T < nloc;
@@ -363,6 +340,57 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
     const double w0 = ok0 ? D.w[i0] : 0.0, w1 = ok1 ? D.w[i1] : 0.0;
     const double2 *wtA = s_wtab + t0, *wtB = s_wtab + t1, *htA = s_htab + t0, *htB = s_htab + t1;
     const double2 zero2 = make_double2(0.0, 0.0);
+
+    // ---- prologue (a): sea state, step-class factors, member base phases / depth pairs; the transcendental functions of the
+    //      thread's two bins are evaluated pairwise ---------------------------------------------------------------------------
+    if (!plan_overflow && ok0) {
+        const double kA = D.k[i0], kB = D.k[i1];
+        const double zetaA = zeta_f2(Cs, c, i0, nw, D.w[i0], D.dw);
+        const double zetaB = ok1 ? zeta_f2(Cs, c, i1, nw, D.w[i1], D.dw) : 0.0;
+        if (P.zeta_out && d == 0) { P.zeta_out[(size_t)c * nw + i0] = zetaA; if (ok1) P.zeta_out[(size_t)c * nw + i1] = zetaB; }
+        const double zwA = zetaA * w0, zwB = zetaB * w1;
+#pragma unroll 1
+        for (int x = 0; x < nW; x++) {
+            const double g = s_wkey[2 * x] * cb + s_wkey[2 * x + 1] * sb;
+            const double4 v = sincos2_once(-(kA * g), -(kB * g));
+            s_wtab[x * nwl + t0] = make_double2(v.x, v.y);
+            if (ok1) s_wtab[x * nwl + t1] = make_double2(v.z, v.w);
+        }
+#pragma unroll 1
+        for (int x = 0; x < nH; x++) {
+            const double4 v = exp2pm_once(kA * s_hkey[x], kB * s_hkey[x]);
+            s_htab[x * nwl + t0] = make_double2(v.x, v.y);
+            if (ok1) s_htab[x * nwl + t1] = make_double2(v.z, v.w);
+        }
+        s_wtab[P.maxW * nwl + t0] = make_double2(1.0, 0.0);
+        s_htab[P.maxH * nwl + t0] = make_double2(1.0, 1.0);
+        if (ok1) { s_wtab[P.maxW * nwl + t1] = make_double2(1.0, 0.0); s_htab[P.maxH * nwl + t1] = make_double2(1.0, 1.0); }
+#pragma unroll 1
+        for (int x = 0; x < nZ; x++) {
+            const double4 v = depth2_once(kA, kB, D.depth, s_zkey[x]);
+            Ag[(size_t)x * nw + i0] = make_double2(v.x, v.y);
+            if (ok1) Ag[(size_t)x * nw + i1] = make_double2(v.z, v.w);
+        }
+#pragma unroll 1
+        for (int m = 0; m < Nm; m++) {
+            const double *o = s_mem + m * MEM_STRIDE;
+            const double g = cb * o[22] + sb * o[23];
+            const double4 v = sincos2_once(-(kA * g), -(kB * g));
+            Eg[(size_t)m * nw + i0] = make_double2(zwA * v.x, zwA * v.y);
+            if (ok1) Eg[(size_t)m * nw + i1] = make_double2(zwB * v.z, zwB * v.w);
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            if (P.Xi_init) {
+                const double2 x0 = P.Xi_init[ogl + (size_t)a * nw + i0];
+                s_xi[(2 * a) * nwl + t0] = x0.x; s_xi[(2 * a + 1) * nwl + t0] = x0.y;
+                if (ok1) { const double2 x1 = P.Xi_init[ogl + (size_t)a * nw + i1]; s_xi[(2 * a) * nwl + t1] = x1.x; s_xi[(2 * a + 1) * nwl + t1] = x1.y; }
+            } else {
+                s_xi[(2 * a) * nwl + t0] = P.xi_start; s_xi[(2 * a + 1) * nwl + t0] = 0.0;
+                if (ok1) { s_xi[(2 * a) * nwl + t1] = P.xi_start; s_xi[(2 * a + 1) * nwl + t1] = 0.0; }
+            }
+        }
+    }
 
     // ---- prologue (b): strip inertial + dynamic-pressure excitation F0, node walk of both bins interleaved -----------------
     if (!plan_overflow) {
@@ -488,6 +516,10 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
         if (!secondary) {
         // ================= pass part 1: sum_w |v_rel . d|^2 per node and direction, both bins interleaved ===========
         double erA = 0, eiA = 0, apA = 0, amA = 0, erB = 0, eiB = 0, apB = 0, amB = 0;      // walking state, kept across chunks
+        // member-level projections of the body velocity, -i w (d . Xi_t + (a x d) . Xi_r), per bin: computed when a member is
+        // entered at its first node and kept across a chunk boundary that falls inside the member
+        double mqrA = 0, mqiA = 0, m1rA = 0, m1iA = 0, m2rA = 0, m2iA = 0, u1rA = 0, u1iA = 0, u2rA = 0, u2iA = 0;
+        double mqrB = 0, mqiB = 0, m1rB = 0, m1iB = 0, m2rB = 0, m2iB = 0, u1rB = 0, u1iB = 0, u2rB = 0, u2iB = 0;
         for (int ch = 0; ch < nchunk; ch++) {
             double acc[32];
 #pragma unroll
@@ -500,9 +532,6 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
                     const int mcur = s_nodem[jfirst];
                     const int mstart = s_imem[IMEM_STRIDE * mcur], jlast = s_imem[IMEM_STRIDE * mcur + 1] - jc0;
                     const double *o = s_mem + mcur * MEM_STRIDE;
-                    // member-level projections of the body velocity, -i w (d . Xi_t + (a x d) . Xi_r), per bin
-                    double mqrA, mqiA, m1rA, m1iA, m2rA, m2iA, u1rA, u1iA, u2rA, u2iA;
-                    double mqrB, mqiB, m1rB, m1iB, m2rB, m2iB, u1rB, u1iB, u2rB, u2iB;
 #define F2_MEMBER_PROJ(TT, WW, OKK, MQR, MQI, M1R, M1I, M2R, M2I, U1R, U1I, U2R, U2I)                                          \
     {                                                                                                                             \
         double xr[6], xi[6];                                                                                                      \
@@ -526,8 +555,10 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
         si = o[6] * xi[3] + o[7] * xi[4] + o[8] * xi[5];                                                                          \
         U2R = WW * si; U2I = -WW * sr;                                                                                            \
     }
-                    F2_MEMBER_PROJ(t0, w0, ok0, mqrA, mqiA, m1rA, m1iA, m2rA, m2iA, u1rA, u1iA, u2rA, u2iA)
-                    F2_MEMBER_PROJ(t1, w1, ok1, mqrB, mqiB, m1rB, m1iB, m2rB, m2iB, u1rB, u1iB, u2rB, u2iB)
+                    if (jfirst == mstart) {
+                        F2_MEMBER_PROJ(t0, w0, ok0, mqrA, mqiA, m1rA, m1iA, m2rA, m2iA, u1rA, u1iA, u2rA, u2iA)
+                        F2_MEMBER_PROJ(t1, w1, ok1, mqrB, mqiB, m1rB, m1iB, m2rB, m2iB, u1rB, u1iB, u2rB, u2iB)
+                    }
 #undef F2_MEMBER_PROJ
                     const double hq = o[18], h1 = o[19], h2 = o[20], dzq = o[2], dz1 = o[5], dz2 = o[8];
                     if (jfirst == mstart) {
