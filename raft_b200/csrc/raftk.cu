@@ -967,7 +967,32 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
         cc.F_2nd = od.F_2nd;
     }
     void *ws = A.take(wb);
-    if (mode == 0) rc = run(&dd, &cc, o, &od, nullptr, 0, true, ws, wb, st);
+    // Page-locked output buffers (raftk_host_alloc / cudaHostAlloc / cudaHostRegister): the solve kernel stores every finished
+    // unit's Xi and status word straight into host memory through the unified address space -- the same epilogue that feeds
+    // peer GPUs, with the host as the "peer" -- so the device-to-host transfer overlaps the units still iterating instead of
+    // following the kernel as a separate copy.  RAFTK_NO_DIRECT_D2H=1 keeps the copy (A/B).
+    bool direct_xi = false;
+    raftk_peers hostpeer;
+    if (mode == 0 && out->Xi && !getenv("RAFTK_NO_DIRECT_D2H")) {
+        F2Plan f2; FPlan fp;
+        const bool fused = (fused2_plan(&dd, (int)nC, o ? o->cluster_size : 0, f2) && wb >= f2.ws_bytes) ||
+                           fused_plan(&dd, (int)(nD * nC), o ? o->cluster_size : 0, true, fp);
+        cudaPointerAttributes pa;
+        const bool pinned_xi = cudaPointerGetAttributes(&pa, out->Xi) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr;
+        if (!pinned_xi) cudaGetLastError();
+        if (fused && pinned_xi) {
+            memset(&hostpeer, 0, sizeof(hostpeer));
+            hostpeer.n_ranks = 2; hostpeer.rank = 0; hostpeer.epoch = 1; hostpeer.block_elems = resp / 16;
+            hostpeer.gathered[0] = od.Xi;
+            hostpeer.gathered[1] = static_cast<double *>(pa.devicePointer) - 0;          // block of "rank 0" inside the host array = its start
+            cudaPointerAttributes ps;
+            if (out->status && cudaPointerGetAttributes(&ps, out->status) == cudaSuccess && ps.type == cudaMemoryTypeHost && ps.devicePointer)
+                hostpeer.status[1] = static_cast<int32_t *>(ps.devicePointer);
+            else cudaGetLastError();
+            direct_xi = true;
+        }
+    }
+    if (mode == 0) rc = run(&dd, &cc, o, &od, nullptr, 0, true, ws, wb, st, direct_xi ? &hostpeer : nullptr);
     else if (mode == 2) rc = run(&dd, &cc, nullptr, &od, nullptr, 2, true, ws, wb, st);
     else {
         rc = run(&dd, &cc, nullptr, &od, nullptr, 2, true, ws, wb, st);
@@ -981,7 +1006,9 @@ static int host_run(const raftk_designs *d, const raftk_cases *c, const raftk_so
         if (rc) return rc;
     }
     auto down = [&](void *h, const void *dv, size_t n) { if (h && dv) { cudaError_t r = cudaMemcpyAsync(h, dv, n, cudaMemcpyDeviceToHost, st); if (r != cudaSuccess) e = r; } };
-    down(out->Xi, od.Xi, resp); down(out->status, od.status, nD * nC * 16); down(out->B_drag, od.B_drag, nD * nC * 288);
+    if (!direct_xi) down(out->Xi, od.Xi, resp);
+    if (!(direct_xi && hostpeer.status[1])) down(out->status, od.status, nD * nC * 16);
+    down(out->B_drag, od.B_drag, nD * nC * 288);
     down(out->F_drag, od.F_drag, resp); down(out->F_iner, od.F_iner, resp); down(out->F_BEM, od.F_BEM, resp);
     down(out->zeta, od.zeta, nC * nw * 8);
     down(out->F_2nd, od.F_2nd, resp / 2); down(out->F_2nd_mean, od.F_2nd_mean, nD * nC * 48); down(out->Xi_last, od.Xi_last, resp);
