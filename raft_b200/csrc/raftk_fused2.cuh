@@ -15,12 +15,38 @@
 //     the walking-state checkpoint between node chunks stays in registers.
 #pragma once
 
-#define F2_T 128                 // threads per CTA (4 warps, 2 CTAs per SM at 254 registers)
+#ifndef F2_T
+#define F2_T 128                 // threads per CTA (4 warps, 2 CTAs per SM at 254 registers); A/B: 96 (3 warps, 3 CTAs at 224)
+#endif
+#if F2_T == 96
+#define F2_KERNEL_ATTR __maxnreg__(224)
+#define F2_SMEM_LIMIT (75 * 1024)
+#else
+#define F2_KERNEL_ATTR __launch_bounds__(F2_T, 2)
+#define F2_SMEM_LIMIT (113 * 1024)
+#endif
 #define F2_TRW 8                 // values per round of the transposed warp reduction
+#ifndef F2_P2_UNROLL
+#define F2_P2_UNROLL 2           // node loop of the drag-excitation walk
+#endif
+constexpr int kP2Unroll = F2_P2_UNROLL;
+// A/B switches (profiles/r02_fused2_ab.txt)
+#ifndef F2_OPT_CONV
+#define F2_OPT_CONV 0
+#endif
+#ifndef F2_OPT_TREE
+#define F2_OPT_TREE 0
+#endif
+#ifndef F2_OPT_DSMEM
+#define F2_OPT_DSMEM 0
+#endif
+#ifndef F2_OPT_FLAGS
+#define F2_OPT_FLAGS 0
+#endif
 
 struct PlanLayout {
     int o_mem, o_node, nstr, o_mat, o_wkey, o_hkey, o_zkey, o_int, total;      // offsets / sizes in doubles
-    int i_imem, i_nodew, i_nodeh, i_nodem, i_cnt, n_int;                        // offsets in ints from o_int
+    int i_imem, i_nodew, i_nodeh, i_nodem, i_cnt, i_chunk, n_int;               // offsets in ints from o_int
 };
 
 __host__ __device__ inline PlanLayout plan_layout(int NmP, int NsP, int maxW, int maxH, int maxZ)
@@ -42,6 +68,7 @@ __host__ __device__ inline PlanLayout plan_layout(int NmP, int NsP, int maxW, in
     L.i_nodeh = q; q += NsP + 12;
     L.i_nodem = q; q += NsP + 12;
     L.i_cnt = q; q += 4;                       // nW, nH, overflow, nZ
+    L.i_chunk = q; q += 2 * ((NsP + CHUNK_NODES - 1) / CHUNK_NODES);   // per chunk of the RMS walk: direction mask, reduction-round mask
     q = (q + 3) & ~3;
     L.n_int = q;
     L.total = p + q / 2;                       // even number of doubles -> a multiple of 16 bytes
@@ -175,6 +202,33 @@ __global__ void __launch_bounds__(128) k_fused_plan(DesignsDev D, double *plan, 
         if (rep == m) { zkey[zi] = z0; atomicMax(&cnt[3], zi + 1); }
         imem[IMEM_STRIDE * m + 4] = zi;
     }
+    // drag-direction masks per chunk of CHUNK_NODES nodes.  The reference's strips carry axial drag only where a member ends
+    // or steps (Cd_End, raft_member.py:2098-2117) and transverse drag only where the strip has a length, so most nodes need
+    // one or two of the three relative-velocity projections: a direction whose coefficient is exactly zero contributes an
+    // exact zero to B_drag / F_drag and is skipped.  Node jj of a chunk: bit 3jj = axial, bit 3jj+1 = transverse.
+    // Accumulator slots of a chunk: [0,10) = transverse-1 (or axial when the node has no transverse drag), [10,20) =
+    // transverse-2, [20,30) = axial of a node that has both; the round mask says which 8-value reduction rounds hold any.
+    {
+        int *chunk_g = ib + L.i_chunk;
+        const int nchunk = (NsP + CHUNK_NODES - 1) / CHUNK_NODES;
+        for (int ch = tid; ch < nchunk; ch += T) {
+            unsigned cm = 0, slots = 0;
+            for (int jj = 0; jj < CHUNK_NODES; jj++) {
+                const int j = ch * CHUNK_NODES + jj;
+                if (j >= Ns) break;
+                const bool q = D.node_cd_q[nbase + j] != 0.0;
+                const bool p = D.node_cd_p1[nbase + j] != 0.0 || D.node_cd_p2[nbase + j] != 0.0;
+                cm |= ((q ? 1u : 0u) | (p ? 2u : 0u)) << (3 * jj);
+                if (q || p) slots |= 1u << jj;
+                if (p) slots |= 1u << (10 + jj);
+                if (q && p) slots |= 1u << (20 + jj);
+            }
+            unsigned rm = 0;
+            for (int rd = 0; rd < 4; rd++) if ((slots >> (rd * F2_TRW)) & 0xffu) rm |= 1u << rd;
+            chunk_g[2 * ch] = (int)cm;
+            chunk_g[2 * ch + 1] = (int)rm;
+        }
+    }
     __syncthreads();
     if (tid < 4) cnt_g[tid] = cnt[tid];
 }
@@ -255,11 +309,19 @@ __host__ __device__ inline size_t fused2_smem_bytes(int Nm, int NsP, int nchunk,
 // |d| < tol (|x| + tol)  <=>  d.d < (tol (|x| + tol))^2 : the convergence test of raft_model.py:1103 with one square root
 __device__ __forceinline__ bool conv_ok(double dr, double di, double xr, double xi, double tol)
 {
-    const double rhs = tol * (sqrt(fma(xr, xr, xi * xi)) + tol);
-    return fma(dr, dr, di * di) < rhs * rhs;
+    const double a = fma(dr, dr, di * di), b = fma(xr, xr, xi * xi);
+#if F2_OPT_CONV
+    // decided without the square root when a is clearly below tol^2 |x|^2 <= rhs^2 or clearly above the bound that
+    // sqrt(b) <= (b + 1) / 2 gives for rhs^2; the band in between evaluates the reference's expression itself
+    const double t2 = tol * tol;
+    if (a < 0.999 * (t2 * b)) return true;
+    if (a > 1.001 * (t2 * (b + tol * (b + 1.0) + t2))) return false;
+#endif
+    const double rhs = tol * (sqrt(b) + tol);
+    return a < rhs * rhs;
 }
 
-__global__ void __launch_bounds__(F2_T, 2)
+__global__ void F2_KERNEL_ATTR
 k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
 {
     extern __shared__ __align__(16) double smem_raw[];
@@ -287,6 +349,7 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
     const double *s_wkey = blob + L.o_wkey, *s_hkey = blob + L.o_hkey, *s_zkey = blob + L.o_zkey;
     const int *ib = reinterpret_cast<const int *>(blob + L.o_int);
     const int *s_imem = ib + L.i_imem, *s_nodew = ib + L.i_nodew, *s_nodeh = ib + L.i_nodeh, *s_nodem = ib + L.i_nodem, *s_cnt = ib + L.i_cnt;
+    const int *s_chunk = ib + L.i_chunk;
     double *p = blob + L.total;
     double *s_coef = p; p += NCOEF * (size_t)NsP;
     double *s_msum = p; p += (size_t)NmP * 8;
@@ -326,6 +389,7 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
     __syncthreads();
     const int nW = s_cnt[0], nH = s_cnt[1], nZ = s_cnt[3];
     const bool plan_overflow = s_cnt[2] != 0;
+    for (int t = tid; t < nchunk * nwarps * 32; t += T) s_wpart[t] = 0.0;      // reduction rounds without an active direction are never written
 
     const size_t ogl = ((size_t)d * Cs.nC + c) * 6 * nw;
     double2 *Eg = P.Eg + ((size_t)d * Cs.nC + c) * (size_t)NmP * nw;      // member base phases   [NmP][nw]
@@ -525,6 +589,7 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
 #pragma unroll
             for (int t = 0; t < 32; t++) acc[t] = 0.0;
             const int jc0 = ch * CHUNK_NODES;
+            const unsigned cmask = (unsigned)s_chunk[2 * ch], rmask = (unsigned)s_chunk[2 * ch + 1];
             if (jc0 < Ns) {
                 int jj = 0;
                 while (jj < CHUNK_NODES && jc0 + jj < Ns) {
@@ -570,29 +635,35 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
                     }
                     // node body, both bins: the step factors of node JJ were loaded one node earlier (C set), those of node
                     // JJ+1 are requested first (N set); sets alternate with the parity of JJ
-#define F2_NODE_BIN(ER, EI, AP, AM, CW, CH, MQR, MQI, M1R, M1I, M2R, M2I, U1R, U1I, U2R, U2I, SQ, S1, S2)                       \
-    {                                                                                                                             \
-        { const double tr = fma(ER, CW.x, -EI * CW.y); EI = fma(ER, CW.y, EI * CW.x); ER = tr; }                                  \
-        AP *= CH.x; AM *= CH.y;                                                                                                   \
-        const double Cc = AP + AM, Sc = AP - AM;                                                                                  \
-        double ar_, ai_;                                                                                                          \
-        proj_add(ER, EI, Cc, Sc, hq, dzq, MQR, MQI, ar_, ai_);                                                                    \
-        SQ = fma(ar_, ar_, ai_ * ai_);                                                                                            \
-        proj_add(ER, EI, Cc, Sc, h1, dz1, fma(ls, U2R, M1R), fma(ls, U2I, M1I), ar_, ai_);                                        \
-        S1 = fma(ar_, ar_, ai_ * ai_);                                                                                            \
-        proj_add(ER, EI, Cc, Sc, h2, dz2, fma(-ls, U1R, M2R), fma(-ls, U1I, M2I), ar_, ai_);                                      \
-        S2 = fma(ar_, ar_, ai_ * ai_);                                                                                            \
-    }
+#define F2_STEP_BIN(ER, EI, AP, AM, CW, CH, CC, SC)                                                                              \
+    { const double tr = fma(ER, CW.x, -EI * CW.y); EI = fma(ER, CW.y, EI * CW.x); ER = tr; }                                      \
+    AP *= CH.x; AM *= CH.y;                                                                                                       \
+    const double CC = AP + AM, SC = AP - AM;
+#define F2_SQ(ER, EI, CC, SC, HH, DZ, MR, MI, OUT)                                                                                \
+    { double ar_, ai_; proj_add(ER, EI, CC, SC, HH, DZ, MR, MI, ar_, ai_); OUT = fma(ar_, ar_, ai_ * ai_); }
 #define F2_P1_NODE(JJ, CWA, CHA, CWB, CHB, CL, NWA, NHA, NWB, NHB, NL)                                                           \
     {                                                                                                                             \
         const int jn = jc0 + JJ + 1;                                                                                              \
         const int ow = s_nodew[jn], oh = s_nodeh[jn];                                                                             \
         NWA = wtA[ow]; NHA = htA[oh]; NWB = wtB[ow]; NHB = htB[oh]; NL = n_ls[jn];                                                \
         const double ls = CL;                                                                                                     \
-        double qA, pA, rA_, qB, pB, rB_;                                                                                          \
-        F2_NODE_BIN(erA, eiA, apA, amA, CWA, CHA, mqrA, mqiA, m1rA, m1iA, m2rA, m2iA, u1rA, u1iA, u2rA, u2iA, qA, pA, rA_)        \
-        F2_NODE_BIN(erB, eiB, apB, amB, CWB, CHB, mqrB, mqiB, m1rB, m1iB, m2rB, m2iB, u1rB, u1iB, u2rB, u2iB, qB, pB, rB_)        \
-        acc[3 * JJ + 0] += qA + qB; acc[3 * JJ + 1] += pA + pB; acc[3 * JJ + 2] += rA_ + rB_;                                     \
+        F2_STEP_BIN(erA, eiA, apA, amA, CWA, CHA, CcA, ScA)                                                                       \
+        F2_STEP_BIN(erB, eiB, apB, amB, CWB, CHB, CcB, ScB)                                                                       \
+        const bool has_p = (cmask & (2u << (3 * JJ))) != 0u;                                                                      \
+        if (has_p) {                                                                                                              \
+            double pA, rA_, pB, rB_;                                                                                              \
+            F2_SQ(erA, eiA, CcA, ScA, h1, dz1, fma(ls, u2rA, m1rA), fma(ls, u2iA, m1iA), pA)                                      \
+            F2_SQ(erB, eiB, CcB, ScB, h1, dz1, fma(ls, u2rB, m1rB), fma(ls, u2iB, m1iB), pB)                                      \
+            F2_SQ(erA, eiA, CcA, ScA, h2, dz2, fma(-ls, u1rA, m2rA), fma(-ls, u1iA, m2iA), rA_)                                   \
+            F2_SQ(erB, eiB, CcB, ScB, h2, dz2, fma(-ls, u1rB, m2rB), fma(-ls, u1iB, m2iB), rB_)                                   \
+            acc[JJ] += pA + pB; acc[10 + JJ] += rA_ + rB_;                                                                        \
+        }                                                                                                                         \
+        if (cmask & (1u << (3 * JJ))) {                                                                                           \
+            double qA, qB;                                                                                                        \
+            F2_SQ(erA, eiA, CcA, ScA, hq, dzq, mqrA, mqiA, qA)                                                                    \
+            F2_SQ(erB, eiB, CcB, ScB, hq, dzq, mqrB, mqiB, qB)                                                                    \
+            if (has_p) acc[20 + JJ] += qA + qB; else acc[JJ] += qA + qB;                                                          \
+        }                                                                                                                         \
     }
                     double2 WaA, HaA, WaB, HaB, WbA, HbA, WbB, HbB; double La, Lb;
                     {
@@ -613,7 +684,8 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
                     case 9: F2_P1_NODE(9, WbA, HbA, WbB, HbB, Lb, WaA, HaA, WaB, HaB, La); jj = 10;
                     }
 #undef F2_P1_NODE
-#undef F2_NODE_BIN
+#undef F2_SQ
+#undef F2_STEP_BIN
                 }
             }
             // warp sum of the 30 accumulators through a padded shared-memory transpose, 8 values per round (fixed order)
@@ -622,12 +694,18 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
                 const int row = lane & 7, part = lane >> 3;
 #pragma unroll
                 for (int rd = 0; rd < 4; rd++) {
+                    if (!(rmask & (1u << rd))) continue;          // no active direction among these eight slots (per design)
 #pragma unroll
                     for (int v = 0; v < F2_TRW; v++) tr[v * 33 + lane] = acc[rd * F2_TRW + v];
                     __syncwarp();
+#if F2_OPT_TREE
+                    const double *tp = tr + row * 33 + part * 8;                 // eight lanes' values, summed as a fixed tree
+                    double sum = ((tp[0] + tp[1]) + (tp[2] + tp[3])) + ((tp[4] + tp[5]) + (tp[6] + tp[7]));
+#else
                     double sum = 0.0;
 #pragma unroll
                     for (int x = 0; x < 8; x++) sum += tr[row * 33 + part * 8 + x];
+#endif
                     sum += __shfl_xor_sync(0xffffffffu, sum, 8);
                     sum += __shfl_xor_sync(0xffffffffu, sum, 16);
                     if (lane < 8) s_wpart[(ch * nwarps + warp) * 32 + rd * F2_TRW + lane] = sum;
@@ -635,6 +713,27 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
                 }
             }
         }
+#if F2_OPT_DSMEM
+        // cluster-wide sums straight from every CTA's per-warp partials (DSMEM): one cluster barrier, no per-CTA stage.
+        // (s_wpart of pass it+1 is written only after the flag exchange of pass it, i.e. after every CTA has read it here.)
+        if (CS > 1) cluster.sync(); else __syncthreads();
+        for (int t = tid; t < nchunk * 32; t += T) {
+            const int ch = t >> 5, l = t & 31;
+            double s = 0.0;
+            if ((unsigned)s_chunk[2 * ch + 1] & (1u << (l >> 3))) {
+#pragma unroll 1
+                for (int r = 0; r < CS; r++) {
+                    const double *rem = (CS > 1) ? cluster.map_shared_rank(s_wpart, r) : s_wpart;
+                    double sr = 0.0;
+#pragma unroll
+                    for (int wv = 0; wv < nwarps; wv++) sr += rem[(ch * nwarps + wv) * 32 + l];
+                    s += sr;
+                }
+            }
+            s_tot[t] = s;
+        }
+        __syncthreads();
+#else
         __syncthreads();
         for (int t = tid; t < nchunk * 32; t += T) {
             const int ch = t >> 5, l = t & 31;
@@ -658,11 +757,15 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
             for (int t = tid; t < nchunk * 32; t += T) s_tot[t] = s_sums[par * sums_stride + t];
         }
         __syncthreads();
+#endif
 
         // ================= linearised coefficients per node, member sums, B_drag ===================================
         for (int j = tid; j < Ns; j += T) {
             const int ch = j / CHUNK_NODES, jj = j - ch * CHUNK_NODES;
-            const double sq = s_tot[ch * 32 + 3 * jj], s1 = s_tot[ch * 32 + 3 * jj + 1], s2 = s_tot[ch * 32 + 3 * jj + 2];
+            const unsigned mk = ((unsigned)s_chunk[2 * ch] >> (3 * jj)) & 3u;
+            // slot layout of the chunk (k_fused_plan): transverse-1 | transverse-2 | axial-when-both; axial alone sits in slot 0
+            const double sA = s_tot[ch * 32 + jj], sB = s_tot[ch * 32 + 10 + jj], sC = s_tot[ch * 32 + 20 + jj];
+            const double sq = (mk & 1u) ? ((mk & 2u) ? sC : sA) : 0.0, s1 = (mk & 2u) ? sA : 0.0, s2 = (mk & 2u) ? sB : 0.0;
             const bool circ = s_imem[IMEM_STRIDE * s_nodem[j] + 2] != 0;
             const double vq = sqrt(0.5 * sq);
             const double v1 = circ ? sqrt(0.5 * (s1 + s2)) : sqrt(0.5 * s1);
@@ -732,7 +835,7 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
                 }
                 double AqrA = 0, AqiA = 0, A1rA = 0, A1iA = 0, A2rA = 0, A2iA = 0, L1rA = 0, L1iA = 0, L2rA = 0, L2iA = 0;
                 double AqrB = 0, AqiB = 0, A1rB = 0, A1iB = 0, A2rB = 0, A2iB = 0, L1rB = 0, L1iB = 0, L2rB = 0, L2iB = 0;
-#pragma unroll 2
+#pragma unroll kP2Unroll
                 for (int j = j0; j < j1; j++) {
                     const int ow = s_nodew[j], oh = s_nodeh[j];
                     const double2 WA = wtA[ow], HA = htA[oh], WB = wtB[ow], HB = htB[oh];
@@ -742,14 +845,19 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
                     apA *= HA.x; amA *= HA.y; apB *= HB.x; amB *= HB.y;
                     const double CcA = apA + amA, ScA = apA - amA, CcB = apB + amB, ScB = apB - amB;
                     double crA, ciA, crB, ciB;
-                    proj(erA, eiA, CcA, ScA, hq, dzq, crA, ciA); proj(erB, eiB, CcB, ScB, hq, dzq, crB, ciB);
-                    AqrA = fma(bq, crA, AqrA); AqiA = fma(bq, ciA, AqiA); AqrB = fma(bq, crB, AqrB); AqiB = fma(bq, ciB, AqiB);
-                    proj(erA, eiA, CcA, ScA, h1, dz1, crA, ciA); proj(erB, eiB, CcB, ScB, h1, dz1, crB, ciB);
-                    A1rA = fma(b1, crA, A1rA); A1iA = fma(b1, ciA, A1iA); L1rA = fma(lb1, crA, L1rA); L1iA = fma(lb1, ciA, L1iA);
-                    A1rB = fma(b1, crB, A1rB); A1iB = fma(b1, ciB, A1iB); L1rB = fma(lb1, crB, L1rB); L1iB = fma(lb1, ciB, L1iB);
-                    proj(erA, eiA, CcA, ScA, h2, dz2, crA, ciA); proj(erB, eiB, CcB, ScB, h2, dz2, crB, ciB);
-                    A2rA = fma(b2, crA, A2rA); A2iA = fma(b2, ciA, A2iA); L2rA = fma(lb2, crA, L2rA); L2iA = fma(lb2, ciA, L2iA);
-                    A2rB = fma(b2, crB, A2rB); A2iB = fma(b2, ciB, A2iB); L2rB = fma(lb2, crB, L2rB); L2iB = fma(lb2, ciB, L2iB);
+                    // a direction whose linearised coefficient is exactly zero adds exact zeros: skipped (same for every thread)
+                    if (bq != 0.0) {
+                        proj(erA, eiA, CcA, ScA, hq, dzq, crA, ciA); proj(erB, eiB, CcB, ScB, hq, dzq, crB, ciB);
+                        AqrA = fma(bq, crA, AqrA); AqiA = fma(bq, ciA, AqiA); AqrB = fma(bq, crB, AqrB); AqiB = fma(bq, ciB, AqiB);
+                    }
+                    if (b1 != 0.0 || b2 != 0.0) {
+                        proj(erA, eiA, CcA, ScA, h1, dz1, crA, ciA); proj(erB, eiB, CcB, ScB, h1, dz1, crB, ciB);
+                        A1rA = fma(b1, crA, A1rA); A1iA = fma(b1, ciA, A1iA); L1rA = fma(lb1, crA, L1rA); L1iA = fma(lb1, ciA, L1iA);
+                        A1rB = fma(b1, crB, A1rB); A1iB = fma(b1, ciB, A1iB); L1rB = fma(lb1, crB, L1rB); L1iB = fma(lb1, ciB, L1iB);
+                        proj(erA, eiA, CcA, ScA, h2, dz2, crA, ciA); proj(erB, eiB, CcB, ScB, h2, dz2, crB, ciB);
+                        A2rA = fma(b2, crA, A2rA); A2iA = fma(b2, ciA, A2iA); L2rA = fma(lb2, crA, L2rA); L2iA = fma(lb2, ciA, L2iA);
+                        A2rB = fma(b2, crB, A2rB); A2iB = fma(b2, ciB, A2iB); L2rB = fma(lb2, crB, L2rB); L2iB = fma(lb2, ciB, L2iB);
+                    }
                 }
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
@@ -829,6 +937,26 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
             }
         }
         passes++;
+#if F2_OPT_FLAGS
+        // one exchange for the three flags: bit 0 = some bin not converged, bits 1.. = NaN / singular flags; every warp
+        // publishes its OR, one barrier (cluster-wide when the unit spans CTAs), every thread combines all warps' words
+        int conv_all, nan_all;
+        {
+            const unsigned word = __reduce_or_sync(0xffffffffu, (unsigned)(conv_local ? 0 : 1) | ((unsigned)nan_local << 1));
+            int *fl = reinterpret_cast<int *>(s_sums + par * sums_stride + nchunk * 32);          // nwarps ints (16 bytes)
+            if (lane == 0) fl[warp] = (int)word;
+            if (CS > 1) cluster.sync(); else __syncthreads();
+            unsigned all = 0;
+#pragma unroll 1
+            for (int r = 0; r < CS; r++) {
+                const int *rem = (CS > 1) ? cluster.map_shared_rank(fl, r) : fl;
+#pragma unroll
+                for (int wv = 0; wv < nwarps; wv++) all |= (unsigned)rem[wv];
+            }
+            conv_all = !(all & 1u);
+            nan_all = (int)(all >> 1) & (RAFTK_FLAG_NAN | RAFTK_FLAG_SINGULAR);
+        }
+#else
         int conv_all = __syncthreads_and(conv_local);
         int nan_all = (__syncthreads_or(nan_local & RAFTK_FLAG_NAN) ? RAFTK_FLAG_NAN : 0)
                       | (__syncthreads_or(nan_local & RAFTK_FLAG_SINGULAR) ? RAFTK_FLAG_SINGULAR : 0);
@@ -844,6 +972,7 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
             }
             conv_all = ca; nan_all = na;
         }
+#endif
         par ^= 1;
         flags |= nan_all;
         if (nan_all & RAFTK_FLAG_NAN) break;

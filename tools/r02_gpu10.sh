@@ -1,0 +1,22 @@
+#!/bin/bash
+# round 2, tenth GPU pass: drag-direction masks in k_rao_fused2 -- parity suite, A/B against the previous build, ncu capture
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -6 | tee gpurun_out/r02_pytest_gpu10.txt
+ab() {
+  python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-extras $2 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+p = d.get('parity') or {}
+print('$1 $2', 'ms/step %.4f' % d['ms_per_step'], 'value %.4g' % d['value'], 'fp64 %s' % d['roofline_fp64']['frac'], 'parity %s/%s' % (p.get('max_rel_err'), p.get('pass_mismatch_units')))"
+}
+for lib in build_ab/base.so default; do
+  if [ "$lib" = default ]; then unset RAFTK_LIB; else export RAFTK_LIB="$PWD/$lib"; fi
+  ab $lib ""
+  ab $lib "--workload sweep --steps 3"
+  ab $lib "--workload cfg3 --steps 10"
+done
+unset RAFTK_LIB
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_rao_fused2 -c 1 -s 3 -o gpurun_out/r02_fused2_masks -f \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-extras > /dev/null 2>&1
+ls -la gpurun_out | tail -5
