@@ -418,11 +418,7 @@ static bool fused2_plan(const raftk_designs *d, int n_cases, int requested_cs, F
     if (d->max_nodes <= 0 || d->max_members <= 0) return false;
     int cs;
     if (requested_cs == 1 || requested_cs == 2 || requested_cs == 4 || requested_cs == 8) cs = requested_cs;
-#if F2_T == 96
-    else { cs = (d->nw + 2 * F2_T - 1) / (2 * F2_T); if (cs > 8) return false; }      // A/B build: any cluster size up to 8
-#else
     else { cs = 1; while (cs < 8 && (d->nw + cs - 1) / cs > 2 * F2_T) cs <<= 1; }
-#endif
     pl.CS = cs;
     pl.nwl = (d->nw + cs - 1) / cs;
     // two bins per thread pay when most threads own two: 192 < bins per CTA <= 256; otherwise the one-bin kernel runs
@@ -432,7 +428,7 @@ static bool fused2_plan(const raftk_designs *d, int n_cases, int requested_cs, F
     pl.maxH = d->max_h_classes > 0 ? d->max_h_classes : d->max_nodes;
     pl.maxZ = d->max_z_classes > 0 ? std::min(d->max_z_classes, d->max_members) : d->max_members;
     pl.smem = fused2_smem_bytes(d->max_members, d->max_nodes, pl.nchunk, pl.nwl, pl.maxW, pl.maxH, pl.maxZ);
-    if (pl.smem > (size_t)F2_SMEM_LIMIT) return false;                            // two CTAs per SM
+    if (pl.smem > (size_t)113 * 1024) return false;                               // two CTAs per SM
     const size_t units = (size_t)d->n_designs * n_cases;
     pl.blob = (size_t)plan_layout(d->max_members, d->max_nodes, pl.maxW, pl.maxH, pl.maxZ).total;
     size_t o = align_up(units * 6 * d->nw * sizeof(double2), 256);                 // F0 (same place as the first-generation kernel)

@@ -15,34 +15,8 @@
 //     the walking-state checkpoint between node chunks stays in registers.
 #pragma once
 
-#ifndef F2_T
-#define F2_T 128                 // threads per CTA (4 warps, 2 CTAs per SM at 254 registers); A/B: 96 (3 warps, 3 CTAs at 224)
-#endif
-#if F2_T == 96
-#define F2_KERNEL_ATTR __maxnreg__(224)
-#define F2_SMEM_LIMIT (75 * 1024)
-#else
-#define F2_KERNEL_ATTR __launch_bounds__(F2_T, 2)
-#define F2_SMEM_LIMIT (113 * 1024)
-#endif
+#define F2_T 128                 // threads per CTA (4 warps, 2 CTAs per SM at 254 registers)
 #define F2_TRW 8                 // values per round of the transposed warp reduction
-#ifndef F2_P2_UNROLL
-#define F2_P2_UNROLL 2           // node loop of the drag-excitation walk
-#endif
-constexpr int kP2Unroll = F2_P2_UNROLL;
-// A/B switches (profiles/r02_fused2_ab.txt)
-#ifndef F2_OPT_CONV
-#define F2_OPT_CONV 0
-#endif
-#ifndef F2_OPT_TREE
-#define F2_OPT_TREE 0
-#endif
-#ifndef F2_OPT_DSMEM
-#define F2_OPT_DSMEM 0
-#endif
-#ifndef F2_OPT_FLAGS
-#define F2_OPT_FLAGS 0
-#endif
 
 struct PlanLayout {
     int o_mem, o_node, nstr, o_mat, o_wkey, o_hkey, o_zkey, o_int, total;      // offsets / sizes in doubles
@@ -310,23 +284,17 @@ __host__ __device__ inline size_t fused2_smem_bytes(int Nm, int NsP, int nchunk,
 __device__ __forceinline__ bool conv_ok(double dr, double di, double xr, double xi, double tol)
 {
     const double a = fma(dr, dr, di * di), b = fma(xr, xr, xi * xi);
-#if F2_OPT_CONV
-    // decided without the square root when a is clearly below tol^2 |x|^2 <= rhs^2 or clearly above the bound that
-    // sqrt(b) <= (b + 1) / 2 gives for rhs^2; the band in between evaluates the reference's expression itself
-    const double t2 = tol * tol;
-    if (a < 0.999 * (t2 * b)) return true;
-    if (a > 1.001 * (t2 * (b + tol * (b + 1.0) + t2))) return false;
-#endif
     const double rhs = tol * (sqrt(b) + tol);
     return a < rhs * rhs;
 }
 
-__global__ void F2_KERNEL_ATTR
+__global__ void __launch_bounds__(F2_T, 2)
 k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
 {
     extern __shared__ __align__(16) double smem_raw[];
     __shared__ __align__(8) unsigned long long mbar;
     constexpr int T = F2_T, nwarps = F2_T / 32;
+    __shared__ int s_flw[nwarps];
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = P.CS;
     const int rank = (CS > 1) ? (int)cluster.block_rank() : 0;
@@ -698,14 +666,9 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
 #pragma unroll
                     for (int v = 0; v < F2_TRW; v++) tr[v * 33 + lane] = acc[rd * F2_TRW + v];
                     __syncwarp();
-#if F2_OPT_TREE
-                    const double *tp = tr + row * 33 + part * 8;                 // eight lanes' values, summed as a fixed tree
-                    double sum = ((tp[0] + tp[1]) + (tp[2] + tp[3])) + ((tp[4] + tp[5]) + (tp[6] + tp[7]));
-#else
                     double sum = 0.0;
 #pragma unroll
                     for (int x = 0; x < 8; x++) sum += tr[row * 33 + part * 8 + x];
-#endif
                     sum += __shfl_xor_sync(0xffffffffu, sum, 8);
                     sum += __shfl_xor_sync(0xffffffffu, sum, 16);
                     if (lane < 8) s_wpart[(ch * nwarps + warp) * 32 + rd * F2_TRW + lane] = sum;
@@ -713,27 +676,6 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
                 }
             }
         }
-#if F2_OPT_DSMEM
-        // cluster-wide sums straight from every CTA's per-warp partials (DSMEM): one cluster barrier, no per-CTA stage.
-        // (s_wpart of pass it+1 is written only after the flag exchange of pass it, i.e. after every CTA has read it here.)
-        if (CS > 1) cluster.sync(); else __syncthreads();
-        for (int t = tid; t < nchunk * 32; t += T) {
-            const int ch = t >> 5, l = t & 31;
-            double s = 0.0;
-            if ((unsigned)s_chunk[2 * ch + 1] & (1u << (l >> 3))) {
-#pragma unroll 1
-                for (int r = 0; r < CS; r++) {
-                    const double *rem = (CS > 1) ? cluster.map_shared_rank(s_wpart, r) : s_wpart;
-                    double sr = 0.0;
-#pragma unroll
-                    for (int wv = 0; wv < nwarps; wv++) sr += rem[(ch * nwarps + wv) * 32 + l];
-                    s += sr;
-                }
-            }
-            s_tot[t] = s;
-        }
-        __syncthreads();
-#else
         __syncthreads();
         for (int t = tid; t < nchunk * 32; t += T) {
             const int ch = t >> 5, l = t & 31;
@@ -744,11 +686,16 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
         if (CS > 1) {
             cluster.sync();
             for (int t = tid; t < nchunk * 32; t += T) {
+                // every rank's partial is requested before the first one is used (a remote shared-memory read takes ~200
+                // cycles); ranks beyond the cluster contribute an exact +0.0, so the sum keeps its order and value
                 double s = 0.0;
 #pragma unroll 1
-                for (int r = 0; r < CS; r++) {
-                    const double *rem = cluster.map_shared_rank(s_sums, r);
-                    s += rem[par * sums_stride + t];
+                for (int r0 = 0; r0 < CS; r0 += 4) {
+                    double v[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) v[r] = (r0 + r < CS) ? cluster.map_shared_rank(s_sums, r0 + r)[par * sums_stride + t] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < 4; r++) s += v[r];
                 }
                 s_tot[t] = s;
             }
@@ -757,7 +704,6 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
             for (int t = tid; t < nchunk * 32; t += T) s_tot[t] = s_sums[par * sums_stride + t];
         }
         __syncthreads();
-#endif
 
         // ================= linearised coefficients per node, member sums, B_drag ===================================
         for (int j = tid; j < Ns; j += T) {
@@ -835,7 +781,7 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
                 }
                 double AqrA = 0, AqiA = 0, A1rA = 0, A1iA = 0, A2rA = 0, A2iA = 0, L1rA = 0, L1iA = 0, L2rA = 0, L2iA = 0;
                 double AqrB = 0, AqiB = 0, A1rB = 0, A1iB = 0, A2rB = 0, A2iB = 0, L1rB = 0, L1iB = 0, L2rB = 0, L2iB = 0;
-#pragma unroll kP2Unroll
+#pragma unroll 2
                 for (int j = j0; j < j1; j++) {
                     const int ow = s_nodew[j], oh = s_nodeh[j];
                     const double2 WA = wtA[ow], HA = htA[oh], WB = wtB[ow], HB = htB[oh];
@@ -937,42 +883,35 @@ k_rao_fused2(DesignsDev D, CasesDev Cs, FusedParams P)
             }
         }
         passes++;
-#if F2_OPT_FLAGS
-        // one exchange for the three flags: bit 0 = some bin not converged, bits 1.. = NaN / singular flags; every warp
-        // publishes its OR, one barrier (cluster-wide when the unit spans CTAs), every thread combines all warps' words
+        // bit 0 = some bin not converged, bits 1.. = NaN / singular: one warp OR, one CTA barrier for all three flags
         int conv_all, nan_all;
         {
             const unsigned word = __reduce_or_sync(0xffffffffu, (unsigned)(conv_local ? 0 : 1) | ((unsigned)nan_local << 1));
-            int *fl = reinterpret_cast<int *>(s_sums + par * sums_stride + nchunk * 32);          // nwarps ints (16 bytes)
-            if (lane == 0) fl[warp] = (int)word;
-            if (CS > 1) cluster.sync(); else __syncthreads();
+            if (lane == 0) s_flw[warp] = (int)word;
+            __syncthreads();
             unsigned all = 0;
-#pragma unroll 1
-            for (int r = 0; r < CS; r++) {
-                const int *rem = (CS > 1) ? cluster.map_shared_rank(fl, r) : fl;
 #pragma unroll
-                for (int wv = 0; wv < nwarps; wv++) all |= (unsigned)rem[wv];
-            }
+            for (int wv = 0; wv < nwarps; wv++) all |= (unsigned)s_flw[wv];
             conv_all = !(all & 1u);
             nan_all = (int)(all >> 1) & (RAFTK_FLAG_NAN | RAFTK_FLAG_SINGULAR);
         }
-#else
-        int conv_all = __syncthreads_and(conv_local);
-        int nan_all = (__syncthreads_or(nan_local & RAFTK_FLAG_NAN) ? RAFTK_FLAG_NAN : 0)
-                      | (__syncthreads_or(nan_local & RAFTK_FLAG_SINGULAR) ? RAFTK_FLAG_SINGULAR : 0);
         if (CS > 1) {
             if (tid == 0) { s_sums[par * sums_stride + nchunk * 32] = (double)conv_all; s_sums[par * sums_stride + nchunk * 32 + 1] = (double)nan_all; }
             cluster.sync();
             int ca = 1, na = 0;
 #pragma unroll 1
-            for (int r = 0; r < CS; r++) {
-                const double *rem = cluster.map_shared_rank(s_sums, r);
-                ca &= (int)rem[par * sums_stride + nchunk * 32];
-                na |= (int)rem[par * sums_stride + nchunk * 32 + 1];
+            for (int r0 = 0; r0 < CS; r0 += 4) {
+                double fc[4], fn[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {                 // four ranks' flag words in flight at a time
+                    const double *rem = cluster.map_shared_rank(s_sums, r0 + r < CS ? r0 + r : 0) + par * sums_stride + nchunk * 32;
+                    fc[r] = rem[0]; fn[r] = rem[1];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++) { ca &= (int)fc[r]; na |= (int)fn[r]; }
             }
             conv_all = ca; nan_all = na;
         }
-#endif
         par ^= 1;
         flags |= nan_all;
         if (nan_all & RAFTK_FLAG_NAN) break;
