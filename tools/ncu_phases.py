@@ -39,7 +39,7 @@ marks = [("stage+classes", 1), ("prologue", find("prologue per frequency")), ("p
          ("assembly", find("double ar[6][6], ai[6][6];")), ("solve6 call+conv", find("const bool ok = solve6")),
          ("flags/cluster sync", find("passes++;"))]
 if "fused2" in kern:
-    marks = [("stage (TMA blob)", 1), ("prologue", find("prologue per frequency")), ("part1 walk", find("= pass part 1")),
+    marks = [("stage (TMA blob)", 1), ("prologue", find("---- prologue (a)")), ("part1 walk", find("= pass part 1")),
              ("part1 warp reduce", find("warp sum of the 30 accumulators")), ("cross-warp/cluster reduce", find("for (int t = tid; t < nchunk * 32; t += T) {")),
              ("coefficients+B_drag", find("= linearised coefficients per node")), ("part2 walk", find("= pass part 2")),
              ("park+assembly", find("bin B's drag excitation waits")), ("solve6 call+conv", find("const bool ok = solve6")),
