@@ -437,15 +437,22 @@ def measure(args, designs, cs, cfg, rank, world, dev, full):
             if world > 1:
                 dist.all_gather_into_tensor(gathered, Xi)      # fallback exchange: one NCCL collective per step
 
-    for _ in range(args.warmup):
-        step()
     # everything with a variable host cost (NVML initialisation of the clock sampler: several ms, different on every rank;
-    # event creation) happens BEFORE the barrier that aligns the ranks -- a rank that enters the timed loop late makes every
-    # other rank wait for it in the first exchange, and that wait would be booked as step time (round 1's N = 8 number)
+    # its first queries; event creation) happens BEFORE the warm-up steps and the barrier that aligns the ranks -- a rank that
+    # enters the timed loop late makes every other rank wait for it in the first exchange, and that wait would be booked as
+    # step time (round 1's N = 8 number).  The sampler thread already polls during the warm-up; its samples are reset below.
     sampler = ClockSampler(local)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler.start()
+    if not os.environ.get("RAFTK_BENCH_NO_SAMPLER"):          # diagnostic switch (tools/r02_n2c.sh): is the NVML thread visible in the step time?
+        sampler.start()
+    # N > 1: at least 10 untimed steps, so that both alternating gathered buffers of every peer have been written through
+    # their NVLink mappings several times before the clock starts (one N = 2 box needed more than 5: profiles/r02_scaling.md)
+    n_warm = args.warmup if world == 1 else max(args.warmup, 10)
+    for _ in range(n_warm):
+        step()
     torch.cuda.synchronize()
+    sampler.sm.clear()
+    sampler.reasons.clear()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -464,7 +471,7 @@ def measure(args, designs, cs, cfg, rank, world, dev, full):
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
     launches = solver.launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler.run or not sampler.ok else dict(sm_mhz=None, sm_max_mhz=sampler.max_mhz, reasons=["sampler disabled (diagnostic run)"], samples=0)
     ms = sum(a.elapsed_time(b) for a, b in ev)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -632,7 +639,8 @@ def measure(args, designs, cs, cfg, rank, world, dev, full):
     line = None
     if rank == 0:
         cfg.update(l2="flushed between timed steps (256 MiB write)", cluster_size=args.cluster or "auto",
-                   units_per_step=units * world, mean_passes=mean_passes, wall_s_timed_region=t_wall, collective=exch_note)
+                   units_per_step=units * world, mean_passes=mean_passes, wall_s_timed_region=t_wall, collective=exch_note,
+                   warmup_steps_run=n_warm)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic", config=cfg, clocks=clocks, e2e=e2e, gpu_launches=int(launches),
