@@ -16,15 +16,24 @@ def make_w(min_freq, max_freq):
 def wave_number(w, depth, e=0.001, g=9.81):
     """k(w) by the reference's fixed-point iteration k <- w^2 / (g tanh(k h))  (helpers.py:377-392).
 
-    Long waves (k h << 1) need tens of thousands of iterations; only the still-active bins are iterated."""
+    Long waves (k h << 1) need tens of thousands of iterations.  All bins iterate together while many are active; the last
+    few stragglers (the lowest frequencies) finish in the reference's own scalar loop, which costs ~1 us per iteration instead
+    of the ~7 us of a NumPy round over a one- or two-element index set (same operations, same ``np.tanh``: identical bits)."""
     w = np.atleast_1d(np.asarray(w, dtype=float))
     k1 = w * w / g
     k2 = w * w / (np.tanh(k1 * depth) * g)
     idx = np.nonzero(np.abs(k2 - k1) / k1 > e)[0]
-    while idx.size:
+    while idx.size > 4:
         k1[idx] = k2[idx]
         k2[idx] = w[idx] * w[idx] / (np.tanh(k1[idx] * depth) * g)
         idx = idx[np.abs(k2[idx] - k1[idx]) / k1[idx] > e]
+    tanh = np.tanh
+    for i in idx:
+        ww, a1, a2 = w[i] * w[i], k1[i], k2[i]
+        while abs(a2 - a1) / a1 > e:
+            a1 = a2
+            a2 = ww / (tanh(a1 * depth) * g)
+        k2[i] = a2
     return k2
 
 

@@ -86,3 +86,31 @@ def test_continuing_a_loop_from_its_own_iterate():
     c = solver.solve_dynamics(b, solver.CaseTable(cs, Xi_init=nxt), n_iter=8)
     assert np.array_equal(c["status"][0, :, 0] + 2, full["status"][0, :, 0])
     assert response_err(c["Xi"][0], full["Xi"][0]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["cfg2_VolturnUS-S_nw64", "cfg1_OC3spar"])
+def test_drag_direction_masks_vs_oracle(name, oracle):
+    """k_fused_plan's per-chunk direction masks (axial-only / transverse-only / both / none) and the accumulator slots they
+    select: the drag columns are edited so that every combination occurs inside one chunk and across chunk boundaries."""
+    from raft_b200 import grid, solver
+    _, P = load_golden(name)
+    Q = grid.regrid(P, 256, 0.40)
+    Q = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in Q.items()}
+    q, p1, p2 = Q["node_cd_q"], Q["node_cd_p1"], Q["node_cd_p2"]
+    n = len(q)
+    ref_q, ref_p = float(np.max(q)), float(np.max(p1))
+    for j in range(n):
+        kind = j % 5
+        if kind == 0:                                   # both: axial and transverse drag on the same node (third slot)
+            q[j], p1[j], p2[j] = ref_q, ref_p, 0.5 * ref_p
+        elif kind == 1:                                 # nothing active
+            q[j] = p1[j] = p2[j] = 0.0
+        elif kind == 2:                                 # second transverse direction only
+            q[j], p1[j], p2[j] = 0.0, 0.0, ref_p
+        # kinds 3, 4 keep the design's own pattern (axial-only ends, transverse-only strips)
+    cs = sea_states(24, 4)
+    out = solver.solve_dynamics(solver.DesignBatch(Q), solver.CaseTable(cs), n_iter=10, want=("Xi", "status", "B_drag", "F_drag"))
+    od = oracle.OracleDesign(Q)
+    Xi_o, st_o, _ = oracle.solve_cases(od, cs, nIter=10)
+    assert np.array_equal(out["status"][0, :, 0], st_o[:, 0]) and np.all(out["status"][0, :, 2] == 0)
+    assert response_err(out["Xi"][0], Xi_o) < RTOL
