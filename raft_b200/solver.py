@@ -277,15 +277,19 @@ def solve_dynamics(batch, cases, n_iter=10, tol=0.01, xi_start=0.0, cluster_size
 
 
 def solve_dynamics_farm(batch, cases, C_arr=None, M_arr=None, B_arr=None, n_iter=10, tol=0.01, xi_start=0.0, cluster_size=0,
-                        want=("Xi", "status", "B_drag")):
+                        want=("Xi", "status", "B_drag"), out=None):
     """Coupled farm response (raft_model.py:1164-1236), host buffers in/out, ONE call: the designs of ``batch`` are the N
     FOWTs of the array; every FOWT's drag linearisation runs as in ``solve_dynamics``, then the 6N x 6N system
     blockdiag(Z_i) + (-w^2 M_arr + i w B_arr + C_arr) is assembled and solved per (case, frequency) on the device.
-    -> the per-FOWT output dict plus ``Xi_sys`` complex [nC, 6N, nw] and ``info`` [nC, nw] (k+1 of a zero pivot)."""
+    -> the per-FOWT output dict plus ``Xi_sys`` complex [nC, 6N, nw] and ``info`` [nC, nw] (k+1 of a zero pivot).
+    ``out``: caller-owned result arrays (e.g. page-locked ones from ``pinned_empty``: device-to-host copies then run at
+    the link rate instead of through the driver's staging of pageable memory); missing ones are allocated."""
     N, nC, nw = batch.n_designs, cases.n_cases, batch.nw
     n = 6 * N
     want = tuple(dict.fromkeys(tuple(want) + ("Xi", "status")))
-    outs = _alloc_outputs(N, nC, nw, want)
+    outs = dict(out) if out is not None else {}
+    for k_, v in _alloc_outputs(N, nC, nw, tuple(k for k in want if k not in outs)).items():
+        outs[k_] = v
     mats = {}
     for nm, v in (("M_arr", M_arr), ("B_arr", B_arr), ("C_arr", C_arr)):
         if v is not None:
@@ -293,8 +297,12 @@ def solve_dynamics_farm(batch, cases, C_arr=None, M_arr=None, B_arr=None, n_iter
             if a.shape != (n, n):
                 raise ValueError("%s must be [%d, %d]" % (nm, n, n))
             mats[nm] = a
-    outs["Xi_sys"] = np.zeros([nC, n, nw], dtype=np.complex128)
-    outs["info"] = np.zeros([nC, nw], dtype=_I4)
+    if "Xi_sys" not in outs:
+        outs["Xi_sys"] = np.zeros([nC, n, nw], dtype=np.complex128)
+    if "info" not in outs:
+        outs["info"] = np.zeros([nC, nw], dtype=_I4)
+    if outs["Xi_sys"].shape != (nC, n, nw) or outs["Xi_sys"].dtype != np.complex128 or not outs["Xi_sys"].flags.c_contiguous:
+        raise ValueError("out['Xi_sys'] must be a C-contiguous complex128 array [%d, %d, %d]" % (nC, n, nw))
     f = RaftkFarm()
     f.n_fowt = N
     for nm in ("M_arr", "B_arr", "C_arr"):

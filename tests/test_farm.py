@@ -38,6 +38,14 @@ def test_farm_response_vs_reference_run():
     assert out["Xi_sys"].shape == ref.shape
     err = max(response_err(out["Xi_sys"][:, 6 * i:6 * i + 6], ref[:, 6 * i:6 * i + 6]) for i in range(N))
     assert err < RTOL, err
+    # caller-owned page-locked result arrays (the e2e path of bench.py --workload farm): the same numbers in the same arrays
+    nC, nw = len(z["cases"]), len(packs[0]["w"])
+    pin = dict(Xi=solver.pinned_empty([N, nC, 6, nw], np.complex128), status=solver.pinned_empty([N, nC, 4], np.int32),
+               Xi_sys=solver.pinned_empty([nC, n, nw], np.complex128), info=solver.pinned_empty([nC, nw], np.int32))
+    o2 = solver.solve_dynamics_farm(solver.DesignBatch(packs), solver.CaseTable(_cases(z["cases"])), C_arr=z["C_array"],
+                                    n_iter=int(z["n_iter"]), xi_start=float(z["xi_start"]), out=pin)
+    assert o2["Xi_sys"] is pin["Xi_sys"] and np.array_equal(o2["Xi_sys"], out["Xi_sys"]) and np.array_equal(o2["Xi"], out["Xi"])
+    assert np.array_equal(o2["status"], out["status"])
     # without the coupling stiffness the system response is the per-FOWT response
     unc = solver.solve_dynamics_farm(solver.DesignBatch(packs), solver.CaseTable(_cases(z["cases"])), n_iter=int(z["n_iter"]),
                                      xi_start=float(z["xi_start"]))
