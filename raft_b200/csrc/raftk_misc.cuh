@@ -241,6 +241,111 @@ __global__ void __launch_bounds__(WARP ? 32 * FARM_WPC : 256) k_farm_response(De
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3c: farm system response for the two-FOWT array (6N = 12; the template also builds for 18 / 24, where it measured slower than
+// the shared-memory warp kernel and is not launched): the augmented system lives in REGISTERS, one lane per row.
+// A group of LPS lanes (16 for 6N = 12: two systems per warp; 32 above) owns one (frequency, case) system; lane r holds row r
+// (N6 matrix entries + the right-hand side).  Elimination step k (fully unrolled, so every register index is static):
+// pivot = first maximum of |re| + |im| over rows >= k (butterfly over the group, LAPACK izamax tie-break), ONE shuffle per
+// entry moves the pivot row to everybody and old row k to the pivot's lane, every row below k eliminates itself.  No shared
+// memory, no barriers; back substitution broadcasts one unknown per step.  Same assembly arithmetic as k_farm_response.
+// ------------------------------------------------------------------------------------------------
+template <int N6>
+__global__ void __launch_bounds__(128) k_farm_rows(DesignsDev D, CasesDev Cs, FarmParams P)
+{
+    constexpr int LPS = N6 <= 16 ? 16 : 32, SPW = 32 / LPS, NC = N6 + 1;
+    const int nw = P.nw, lane = threadIdx.x & 31, r = lane & (LPS - 1);
+    const int sys = ((int)blockIdx.x * ((int)blockDim.x >> 5) + ((int)threadIdx.x >> 5)) * SPW + lane / LPS;
+    const int c = blockIdx.y;
+    const bool live = sys < nw;                        // a group beyond the grid keeps shuffling with its neighbours but never stores
+    const int iw = live ? sys : nw - 1;
+    const bool row_ok = r < N6;
+    const int a = row_ok ? r : 0;
+    const double w = D.w[iw], w2 = w * w;
+    const int cp = Cs.primary ? Cs.primary[c] : c;
+    const int i = a / 6, ea = a - 6 * i;
+    double2 row[NC];
+#pragma unroll
+    for (int b = 0; b < N6; b++) {
+        double zr = 0.0, zi = 0.0;
+        if (b / 6 == i) {
+            const int e = 6 * ea + (b - 6 * (b / 6));
+            double M = D.M0[(size_t)i * 36 + e], B = D.B0[(size_t)i * 36 + e] + P.B_drag[((size_t)i * P.nC + cp) * 36 + e];
+            if (D.A_w) { M += D.A_w[((size_t)i * 36 + e) * nw + iw]; B += D.B_w[((size_t)i * 36 + e) * nw + iw]; }
+            zr = fma(-w2, M, D.C0[(size_t)i * 36 + e]);
+            zi = w * B;
+        }
+        const int t = a * N6 + b;
+        if (P.C_arr) zr += P.C_arr[t];
+        if (P.M_arr) zr -= w2 * P.M_arr[t];
+        if (P.B_arr) zi += w * P.B_arr[t];
+        row[b] = make_double2(zr, zi);
+    }
+    {
+        const size_t o = (((size_t)i * P.nC + c) * 6 + ea) * nw + iw;
+        double2 f = P.F_drag[o];
+        const double2 h = P.F_iner[o];
+        f.x += h.x; f.y += h.y;
+        if (P.F_BEM) { const double2 q = P.F_BEM[o]; f.x += q.x; f.y += q.y; }
+        if (Cs.F_2nd) f.x += Cs.F_2nd[o];
+        row[N6] = f;
+    }
+    int bad = 0;
+    static_for<0, N6>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        double best = (row_ok && r >= k) ? fabs(row[k].x) + fabs(row[k].y) : -1.0;
+        int p = r;
+#pragma unroll
+        for (int o = LPS / 2; o >= 1; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o, LPS);
+            const int op = __shfl_xor_sync(0xffffffffu, p, o, LPS);
+            if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+        }
+        // one shuffle per entry: the pivot's lane fetches old row k, every other lane the pivot row
+        const int src = (r == p) ? k : p;
+        double2 piv[NC];
+        static_for<k, NC>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            double2 t;
+            t.x = __shfl_sync(0xffffffffu, row[j].x, src, LPS);
+            t.y = __shfl_sync(0xffffffffu, row[j].y, src, LPS);
+            if (r == p) { piv[j] = row[j]; row[j] = t; }
+            else { piv[j] = t; if (r == k) row[j] = t; }
+        });
+        const double den = piv[k].x * piv[k].x + piv[k].y * piv[k].y;
+        double2 ri = make_double2(0.0, 0.0);
+        if (den > 0.0) ri = make_double2(piv[k].x / den, -piv[k].y / den);
+        else if (bad == 0) bad = k + 1;
+        if (row_ok && r > k) {
+            const double2 v = row[k];
+            const double2 l = make_double2(v.x * ri.x - v.y * ri.y, v.x * ri.y + v.y * ri.x);
+            static_for<k + 1, NC>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                row[j].x -= l.x * piv[j].x - l.y * piv[j].y;
+                row[j].y -= l.x * piv[j].y + l.y * piv[j].x;
+            });
+        }
+    });
+    // back substitution: lane k divides by its diagonal, everybody above subtracts
+    double2 x = make_double2(0.0, 0.0);
+    static_for<0, N6>([&](auto KK) {
+        constexpr int k = N6 - 1 - decltype(KK)::value;
+        const double2 pv = row[k], s = row[N6];
+        const double den = pv.x * pv.x + pv.y * pv.y;
+        const double2 xk_own = make_double2((s.x * pv.x + s.y * pv.y) / den, (s.y * pv.x - s.x * pv.y) / den);
+        double2 xk;
+        xk.x = __shfl_sync(0xffffffffu, xk_own.x, k, LPS);
+        xk.y = __shfl_sync(0xffffffffu, xk_own.y, k, LPS);
+        if (r == k) x = xk;
+        if (r < k) {
+            row[N6].x -= pv.x * xk.x - pv.y * xk.y;
+            row[N6].y -= pv.x * xk.y + pv.y * xk.x;
+        }
+    });
+    if (live && row_ok) P.Xi[((size_t)c * N6 + r) * nw + iw] = x;
+    if (live && r == 0 && P.info) P.info[(size_t)c * nw + iw] = bad;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: response statistics (std, PSD) -- one CTA per (unit, dof), fixed-order block reduction over frequency
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_response_stats(int nw, double dw, int rot_deg, const double2 *Xi, double *sd, double *psd)

@@ -96,18 +96,31 @@ def test_drag_direction_masks_vs_oracle(name, oracle):
     _, P = load_golden(name)
     Q = grid.regrid(P, 256, 0.40)
     Q = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in Q.items()}
-    q, p1, p2 = Q["node_cd_q"], Q["node_cd_p1"], Q["node_cd_p2"]
-    n = len(q)
-    ref_q, ref_p = float(np.max(q)), float(np.max(p1))
+    # the raw columns (what the checker reads) are edited and the derived ones (what the kernels read) recomputed exactly as
+    # packer.py:110-112 does: cd_q = pref (a_q Cd_q + a_End Cd_End), cd_p = pref a_p Cd_p, pref = sqrt(8/pi) rho / 2
+    pref = np.sqrt(8.0 / np.pi) * 0.5 * float(Q["rho"])
+    n = len(Q["node_cd_q"])
+    for key in ("node_a_q", "node_Cd_q", "node_a_End", "node_Cd_End", "node_a_p1", "node_Cd_p1", "node_a_p2", "node_Cd_p2"):
+        assert len(Q[key]) == n
+    a_ref = float(np.max(Q["node_a_p1"]))
     for j in range(n):
         kind = j % 5
         if kind == 0:                                   # both: axial and transverse drag on the same node (third slot)
-            q[j], p1[j], p2[j] = ref_q, ref_p, 0.5 * ref_p
+            Q["node_a_End"][j], Q["node_Cd_End"][j] = 0.5 * a_ref, 0.6
+            Q["node_a_p1"][j], Q["node_Cd_p1"][j], Q["node_a_p2"][j], Q["node_Cd_p2"][j] = a_ref, 0.8, a_ref, 0.8
         elif kind == 1:                                 # nothing active
-            q[j] = p1[j] = p2[j] = 0.0
-        elif kind == 2:                                 # second transverse direction only
-            q[j], p1[j], p2[j] = 0.0, 0.0, ref_p
+            for key in ("node_Cd_q", "node_Cd_End", "node_Cd_p1", "node_Cd_p2"):
+                Q[key][j] = 0.0
+        elif kind == 2:                                 # one transverse coefficient only (the other is an exact zero)
+            Q["node_Cd_q"][j] = Q["node_Cd_End"][j] = Q["node_Cd_p1"][j] = 0.0
+            Q["node_a_p2"][j], Q["node_Cd_p2"][j] = a_ref, 0.8
         # kinds 3, 4 keep the design's own pattern (axial-only ends, transverse-only strips)
+    Q["node_cd_q"] = pref * (Q["node_a_q"] * Q["node_Cd_q"] + Q["node_a_End"] * Q["node_Cd_End"])
+    Q["node_cd_p1"] = pref * Q["node_a_p1"] * Q["node_Cd_p1"]
+    Q["node_cd_p2"] = pref * Q["node_a_p2"] * Q["node_Cd_p2"]
+    both = (Q["node_cd_q"] != 0) & ((Q["node_cd_p1"] != 0) | (Q["node_cd_p2"] != 0))
+    none = (Q["node_cd_q"] == 0) & (Q["node_cd_p1"] == 0) & (Q["node_cd_p2"] == 0)
+    assert both.any() and none.any()
     cs = sea_states(24, 4)
     out = solver.solve_dynamics(solver.DesignBatch(Q), solver.CaseTable(cs), n_iter=10, want=("Xi", "status", "B_drag", "F_drag"))
     od = oracle.OracleDesign(Q)
