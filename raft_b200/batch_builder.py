@@ -181,26 +181,27 @@ def _member_tables(mi, heading, geom, nD, dlsMax, rho, g, Rp, r0, nw_unused=0):
 
 
 def _added_mass(T, r_ref):
-    """sum over submerged nodes of translateMatrix3to6DOF(Amat, r - r_ref) (raft_member.py:1361) for every design."""
+    """sum over submerged nodes of translateMatrix3to6DOF(Amat, r - r_ref) (raft_member.py:1361) for every design.
+
+    Amat_j = a1_j p1 p1^T + a2_j p2 p2^T + aq_j q q^T with the member's (per-design) unit vectors, and H(r) v = v x r, so with
+    c_j = d x (r_j - r_ref) for each direction d: sum Amat = (sum a_j) d d^T, sum Amat H = -d (sum a_j c_j)^T, sum H Amat H^T =
+    sum a_j c_j c_j^T -- weighted sums over the node axis instead of [nD, S] batched 3 x 3 products (5 ms -> 0.6 ms per member)."""
     nD = T["q"].shape[0]
     A = np.zeros([nD, 6, 6])
     if not (np.any(T["ad_q"]) or np.any(T["ad_p1"]) or np.any(T["ad_p2"])):
         return A
-    qq = np.einsum("da,db->dab", T["q"], T["q"])
-    p11 = np.einsum("da,db->dab", T["p1"], T["p1"])
-    p22 = np.einsum("da,db->dab", T["p2"], T["p2"])
-    m = (T["ad_p1"][:, :, None, None] * p11[:, None] + T["ad_p2"][:, :, None, None] * p22[:, None]) + T["ad_q"][:, :, None, None] * qq[:, None]
-    m = np.where(T["sub"][:, :, None, None], m, 0.0)                                       # [nD,S,3,3]
-    rr = T["r"] - r_ref[None, None, :]
-    H = np.zeros(rr.shape[:2] + (3, 3))
-    H[..., 0, 1], H[..., 0, 2] = rr[..., 2], -rr[..., 1]
-    H[..., 1, 0], H[..., 1, 2] = -rr[..., 2], rr[..., 0]
-    H[..., 2, 0], H[..., 2, 1] = rr[..., 1], -rr[..., 0]
-    mH = m @ H
-    A[:, :3, :3] = m.sum(axis=1)
-    A[:, :3, 3:] = mH.sum(axis=1)
-    A[:, 3:, :3] = np.swapaxes(mH, -1, -2).sum(axis=1)
-    A[:, 3:, 3:] = (H @ m @ np.swapaxes(H, -1, -2)).sum(axis=1)
+    rr = T["r"] - r_ref[None, None, :]                                                     # [nD,S,3]
+    for d, a in ((T["p1"], T["ad_p1"]), (T["p2"], T["ad_p2"]), (T["q"], T["ad_q"])):
+        a = np.where(T["sub"], a, 0.0)                                                     # [nD,S]
+        c = np.cross(d[:, None, :], rr)                                                    # [nD,S,3]  = H(rr) d
+        ac = a[:, :, None] * c
+        s0 = a.sum(axis=1)                                                                 # [nD]
+        s1 = ac.sum(axis=1)                                                                # [nD,3]
+        A[:, :3, :3] += s0[:, None, None] * (d[:, :, None] * d[:, None, :])
+        off = -d[:, :, None] * s1[:, None, :]                                              # sum_j Amat_j H_j
+        A[:, :3, 3:] += off
+        A[:, 3:, :3] += np.swapaxes(off, 1, 2)
+        A[:, 3:, 3:] += np.einsum("dsa,dsb->dab", ac, c)
     return A
 
 
@@ -311,3 +312,4 @@ def build_family(family, w, k, depth, matrices, r6=None):
                  int(max(1, (has & ~zdup).sum(axis=1).max()))))
     batch.A_hydro_morison = A_mor
     return batch
+
