@@ -297,11 +297,17 @@ class ShardedSolve:
         """Host buffers in and out: H2D of every table and the case columns, solve + fused exchange + arrival barrier,
         D2H of this rank's responses and status; synchronises.  -> (Xi host, status host, h2d bytes, d2h bytes)."""
         pin_in, xi_h, st_h = self.host_buffers()
-        h2d = 0
-        for name, h in pin_in.items():
-            dst = self.sess.ct[name[5:]] if name.startswith("case:") else self.sess.dt[name]
-            dst.copy_(h, non_blocking=True)
-            h2d += h.numel() * h.element_size()
+        if getattr(self, "_h2d", None) is None:
+            dsts = [self.sess.ct[name[5:]] if name.startswith("case:") else self.sess.dt[name] for name in pin_in]
+            srcs = list(pin_in.values())
+            self._h2d = (dsts, srcs, int(sum(h.numel() * h.element_size() for h in srcs)))
+        dsts, srcs, h2d = self._h2d
+        try:
+            # ~30 small tables: one call into the C++ copy loop instead of 30 Python-level copy_ calls (~0.15 ms per step)
+            self.torch._foreach_copy_(dsts, srcs, non_blocking=True)
+        except Exception:                                  # noqa: BLE001  (older torch: per-tensor copies)
+            for dst, h in zip(dsts, srcs):
+                dst.copy_(h, non_blocking=True)
         self.sess._plan_key = None                     # fresh tables from the host: the per-design plan is rebuilt
         g, s = self.step(**kw)
         xi_h.copy_(g[self.rank], non_blocking=True)
