@@ -679,9 +679,25 @@ class DeviceSession:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.batch, self.cases = batch, cases
         with torch.cuda.device(self.device):
-            self.dt = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.float64) if v.dtype == np.complex128 else v).to(self.device)
-                       for k, v in batch.arrays.items()}
-            self.ct = {k: torch.from_numpy(v).to(self.device) for k, v in cases.arrays.items()}
+            # every input table (design + case columns) lives in ONE device block, 256-byte aligned slots: a caller that
+            # refreshes the tables from the host (sweep.ShardedSolve.step_host) sends them with a single copy
+            items, total = [], 0
+            for grp, arrs in (("d", batch.arrays), ("c", cases.arrays)):
+                for k, v in arrs.items():
+                    v = np.ascontiguousarray(v)
+                    v = v.view(np.float64) if v.dtype == np.complex128 else v
+                    items.append((grp, k, v, total))
+                    total += (v.nbytes + 255) // 256 * 256
+            host_block = np.zeros(max(total, 256), dtype=np.uint8)
+            for _, _, v, off in items:
+                host_block[off:off + v.nbytes] = v.reshape(-1).view(np.uint8)
+            self.tables = torch.from_numpy(host_block).to(self.device)
+            self.table_bytes = int(total)
+            self.dt, self.ct = {}, {}
+            for grp, k, v, off in items:
+                tdt = torch.from_numpy(np.empty(0, dtype=v.dtype)).dtype
+                t = self.tables[off:off + v.nbytes].view(tdt).view(v.shape) if v.nbytes else torch.from_numpy(v).to(self.device)
+                (self.dt if grp == "d" else self.ct)[k] = t
             self.d_struct = batch.struct(lambda name: self.dt[name].data_ptr())
             self.c_struct = cases.struct(lambda name: self.ct[name].data_ptr())
             need = (lib.raftk_workspace_bytes if tables else lib.raftk_solve_workspace_bytes)(C.byref(self.d_struct), cases.n_cases)

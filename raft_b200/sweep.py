@@ -280,34 +280,24 @@ class ShardedSolve:
         return self.px.gathered[b].view(self.world, nD, nC, 6, nw), self.px.status[b].view(self.world, nD, nC, 4)
 
     def host_buffers(self):
-        """Pinned host mirrors of the inputs and of this rank's output block (allocated once)."""
+        """Pinned host mirrors of the input block (all tables, ``DeviceSession.tables``) and of this rank's output block
+        (allocated once)."""
         if self._pin is None:
             torch = self.torch
-            pin_in = {}
-            for name, t in list(self.sess.dt.items()) + [("case:" + k, v) for k, v in self.sess.ct.items()]:
-                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                h.copy_(t)
-                pin_in[name] = h
+            pin_in = torch.empty(self.sess.tables.shape, dtype=torch.uint8, pin_memory=True)
+            pin_in.copy_(self.sess.tables)
             nD, nC, _, nw = self.shape
             self._pin = (pin_in, torch.empty(self.shape, dtype=torch.complex128, pin_memory=True),
                          torch.empty((nD, nC, 4), dtype=torch.int32, pin_memory=True))
         return self._pin
 
     def step_host(self, **kw):
-        """Host buffers in and out: H2D of every table and the case columns, solve + fused exchange + arrival barrier,
-        D2H of this rank's responses and status; synchronises.  -> (Xi host, status host, h2d bytes, d2h bytes)."""
+        """Host buffers in and out: H2D of every table and the case columns (one copy of the session's table block), solve +
+        fused exchange + arrival barrier, D2H of this rank's responses and status; synchronises.
+        -> (Xi host, status host, h2d bytes, d2h bytes)."""
         pin_in, xi_h, st_h = self.host_buffers()
-        if getattr(self, "_h2d", None) is None:
-            dsts = [self.sess.ct[name[5:]] if name.startswith("case:") else self.sess.dt[name] for name in pin_in]
-            srcs = list(pin_in.values())
-            self._h2d = (dsts, srcs, int(sum(h.numel() * h.element_size() for h in srcs)))
-        dsts, srcs, h2d = self._h2d
-        try:
-            # ~30 small tables: one call into the C++ copy loop instead of 30 Python-level copy_ calls (~0.15 ms per step)
-            self.torch._foreach_copy_(dsts, srcs, non_blocking=True)
-        except Exception:                                  # noqa: BLE001  (older torch: per-tensor copies)
-            for dst, h in zip(dsts, srcs):
-                dst.copy_(h, non_blocking=True)
+        self.sess.tables.copy_(pin_in, non_blocking=True)
+        h2d = self.sess.table_bytes
         self.sess._plan_key = None                     # fresh tables from the host: the per-design plan is rebuilt
         g, s = self.step(**kw)
         xi_h.copy_(g[self.rank], non_blocking=True)
