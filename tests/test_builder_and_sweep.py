@@ -240,3 +240,41 @@ def test_batched_builder_general_members():
         f.calcHydroConstants()
         per.append(f.pack())
     _batch_tables_equal(solver.DesignBatch(per), bat)
+
+
+def test_wave_number_is_the_references_scalar_iteration():
+    """grid.wave_number (vectorised rounds + scalar finish for the last stragglers) against the reference's loop written out
+    (helpers.py:377-392): identical bits, also where the long-wave bins need thousands of iterations."""
+    from raft_b200 import grid
+
+    def scalar(omega, h, e=0.001, g=9.81):
+        k1 = omega * omega / g
+        k2 = omega * omega / (np.tanh(k1 * h) * g)
+        while np.abs(k2 - k1) / k1 > e:
+            k1 = k2
+            k2 = omega * omega / (np.tanh(k1 * h) * g)
+        return k2
+
+    for nw, max_freq, depth in ((64, 0.32, 200.0), (256, 0.256, 320.0), (80, 0.40, 50.0)):
+        w = grid.make_w(max_freq / nw, max_freq)
+        k = grid.wave_number(w, depth)
+        assert np.array_equal(k, np.array([scalar(x, depth) for x in w]))
+
+
+def test_host_struct_cache_follows_table_edits():
+    """solver._host_struct: the cached C struct of the host-buffer calls is rebuilt when a table is replaced (its address
+    changes) and kept when arrays are edited in place."""
+    from raft_b200 import solver
+    _, P = load_golden("cfg2_VolturnUS-S_nw64")
+    b = solver.DesignBatch([P])
+    s1 = solver._host_struct(b)
+    assert solver._host_struct(b) is s1
+    b.arrays["node_ls"][0] += 0.0                                  # in place: same address, same struct
+    assert solver._host_struct(b) is s1 and s1.node_ls == b.arrays["node_ls"].ctypes.data
+    b.arrays["node_ls"] = b.arrays["node_ls"].copy()               # replaced: new address, new struct
+    s2 = solver._host_struct(b)
+    assert s2 is not s1 and s2.node_ls == b.arrays["node_ls"].ctypes.data
+    c = solver.CaseTable(dict(Hs=[1.0], Tp=[8.0], gamma=[0.0], beta_deg=[0.0], spec=np.zeros(1, dtype=np.int32)))
+    t1 = solver._host_struct(c)
+    c.arrays.update(Hs=np.array([2.0]))
+    assert solver._host_struct(c) is not t1
