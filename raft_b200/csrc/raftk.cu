@@ -760,7 +760,7 @@ static int farm_launch(const raftk_designs *d, const raftk_cases *c, const raftk
     P.Xi = reinterpret_cast<double2 *>(f->Xi_sys); P.info = f->info;
     {
         ProfScope ps(st, 1);
-        // 6N = 12 (the shipped two-FOWT farm): rows in registers, one lane per row, two systems per warp (k_farm_rows: 0.259 ms
+        // 6N = 12 (the shipped two-FOWT farm): rows in registers, one lane per row, two systems per warp (k_farm_rows: 0.188 ms
         // against 0.398 ms for 65 536 systems); RAFTK_FARM_SMEM=1 keeps the shared-memory warp kernel (A/B).  At 6N = 18 / 24 the
         // register rows need 188 / 238 registers and lose (6N = 24: 2.46 ms against 1.37 ms), so those stay on the warp kernel.
         const bool rows = n == 12 && !getenv("RAFTK_FARM_SMEM");

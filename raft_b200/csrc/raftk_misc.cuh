@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(128) k_farm_rows(DesignsDev D, CasesDev Cs, Fa
         row[N6] = f;
     }
     int bad = 0;
+    double2 myinv = make_double2(0.0, 0.0);
     static_for<0, N6>([&](auto K) {
         constexpr int k = decltype(K)::value;
         double best = (row_ok && r >= k) ? fabs(row[k].x) + fabs(row[k].y) : -1.0;
@@ -313,8 +314,9 @@ __global__ void __launch_bounds__(128) k_farm_rows(DesignsDev D, CasesDev Cs, Fa
         });
         const double den = piv[k].x * piv[k].x + piv[k].y * piv[k].y;
         double2 ri = make_double2(0.0, 0.0);
-        if (den > 0.0) ri = make_double2(piv[k].x / den, -piv[k].y / den);
+        if (den > 0.0) { const double inv = 1.0 / den; ri = make_double2(piv[k].x * inv, -piv[k].y * inv); }      // one division per step
         else if (bad == 0) bad = k + 1;
+        if (r == k) myinv = ri;                          // 1 / U_kk stays with row k for the back substitution
         if (row_ok && r > k) {
             const double2 v = row[k];
             const double2 l = make_double2(v.x * ri.x - v.y * ri.y, v.x * ri.y + v.y * ri.x);
@@ -325,13 +327,12 @@ __global__ void __launch_bounds__(128) k_farm_rows(DesignsDev D, CasesDev Cs, Fa
             });
         }
     });
-    // back substitution: lane k divides by its diagonal, everybody above subtracts
+    // back substitution: lane k multiplies by the reciprocal of its diagonal kept from the elimination, everybody above subtracts
     double2 x = make_double2(0.0, 0.0);
     static_for<0, N6>([&](auto KK) {
         constexpr int k = N6 - 1 - decltype(KK)::value;
         const double2 pv = row[k], s = row[N6];
-        const double den = pv.x * pv.x + pv.y * pv.y;
-        const double2 xk_own = make_double2((s.x * pv.x + s.y * pv.y) / den, (s.y * pv.x - s.x * pv.y) / den);
+        const double2 xk_own = make_double2(s.x * myinv.x - s.y * myinv.y, s.x * myinv.y + s.y * myinv.x);      // only lane k's value is used
         double2 xk;
         xk.x = __shfl_sync(0xffffffffu, xk_own.x, k, LPS);
         xk.y = __shfl_sync(0xffffffffu, xk_own.y, k, LPS);
