@@ -213,9 +213,17 @@ def _count_classes(keys, valid, rel):
         return np.zeros(keys.shape[0], dtype=np.int64)
     # run-length compression first: a strip whose key repeats its predecessor's (the interior of a uniformly divided
     # section) cannot open a class, so only run starts enter the pairwise comparison (a few per member)
-    mag = np.abs(keys).sum(axis=2)
+    # (reductions over the tiny trailing component axis are written out per component: NumPy's axis reductions cost ~10x
+    # more than the arithmetic on a length-1 or length-2 axis)
+    nc = keys.shape[2]
+    comp = lambda a: [a[..., i] for i in range(nc)]
+    mag = sum(np.abs(x) for x in comp(keys))
+    close = np.ones(valid[:, 1:].shape, bool)
+    tol1 = rel * mag[:, 1:]
+    for x in comp(keys):
+        close &= np.abs(x[:, 1:] - x[:, :-1]) <= tol1
     rep = np.zeros(valid.shape, bool)
-    rep[:, 1:] = valid[:, :-1] & np.all(np.abs(keys[:, 1:] - keys[:, :-1]) <= (rel * mag[:, 1:])[:, :, None], axis=2)
+    rep[:, 1:] = valid[:, :-1] & close
     valid = valid & ~rep
     pmax = int(valid.sum(axis=1).max())
     if pmax == 0:
@@ -223,10 +231,11 @@ def _count_classes(keys, valid, rel):
     order = np.argsort(~valid, axis=1, kind="stable")[:, :pmax]
     keys = np.take_along_axis(keys, order[:, :, None], axis=1)
     valid = np.take_along_axis(valid, order, axis=1)
-    mag = np.abs(keys).sum(axis=2)
-    tol = rel * mag
-    same = np.all(np.abs(keys[:, :, None, :] - keys[:, None, :, :]) <= tol[:, :, None, None], axis=3)      # [nD,P(j),P(x)]
-    earlier = np.tril(np.ones(keys.shape[1:2] * 2, bool), -1)[None]                                          # x < j
+    tol = rel * sum(np.abs(x) for x in comp(keys))
+    same = np.ones((keys.shape[0], pmax, pmax), bool)                                                        # [nD,P(j),P(x)]
+    for x in comp(keys):
+        same &= np.abs(x[:, :, None] - x[:, None, :]) <= tol[:, :, None]
+    earlier = np.tril(np.ones((pmax, pmax), bool), -1)[None]                                                 # x < j
     dup = np.any(same & earlier & valid[:, None, :], axis=2)
     return (valid & ~dup).sum(axis=1)
 
