@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RAFTK_VERSION 130 /* 0.1.3: + peer exchange over NVLink, farm system response on device, blocked generalised-DOF solve */
+#define RAFTK_VERSION 131 /* 0.1.3.1: + native node-table builder for design families (raftk_family_sizes / raftk_build_family_host) */
 
 enum {
     RAFTK_OK = 0,
@@ -418,6 +418,48 @@ void raftk_host_free(void *p);
 
 /* FP64 FMA micro-benchmark: returns achieved GFLOP/s on the current device (roofline denominator). */
 double raftk_fp64_peak_gflops(int iters);
+
+/*
+ * Native node-table builder for a FAMILY of designs on one topology (a design sweep, the reference's parametersweep.py:29-95):
+ * what Member.__init__ / setPosition / calcHydroConstants / calcImat (raft_member.py:190-271, 312-377, 1261-1448) and
+ * FOWT.calcHydroConstants (raft_fowt.py:1589-1625) leave behind per design, written straight into the CSR tables of
+ * raftk_designs.  Pure host code (no CUDA).  One raftk_family_member per member COPY (a member entry with several headings
+ * appears once per heading); per-design geometry arrays have n_designs rows.  Rigid circular / rectangular members without
+ * MacCamy-Fuchs tables.  raftk_family_sizes returns the totals the caller needs to allocate raftk_family_tables;
+ * raftk_build_family_host fills them (error -1: an end point on the waterplane or stations not ascending, as the reference raises).
+ */
+typedef struct raftk_family_member {
+    int32_t n_stations;        /* n                                                              */
+    int32_t circular;          /* 1 circular (d [nD][n][1]), 0 rectangular (d [nD][n][2])      */
+    int32_t pot_mod;           /* strips carry drag only (inertia from BEM)                      */
+    int32_t _pad0;
+    double gamma_deg, heading_deg, dls_max;
+    const double *stations;    /* [n] as in the design file                                     */
+    const double *rA, *rB;     /* [nD][3] end points before the heading rotation                */
+    const double *d;           /* [nD][n][1 or 2]                                               */
+    const double *Cd_q, *Cd_p1, *Cd_p2, *Cd_End, *Ca_p1, *Ca_p2, *Ca_End;   /* [n] per station  */
+} raftk_family_member;
+
+typedef struct raftk_family {
+    int32_t n_designs, n_members;
+    double rho, g;
+    double Rp[9];              /* platform rotation (helpers.rotationMatrix of r6[3:6]), row-major */
+    double r0[3];              /* platform reference point r6[0:3]                               */
+    const raftk_family_member *members;
+} raftk_family;
+
+typedef struct raftk_family_tables {
+    int32_t *member_offset;    /* [nD+1]                                                         */
+    int32_t *mem_node_start;   /* [n_members_total+1]                                            */
+    int32_t *mem_circ;         /* [n_members_total]                                              */
+    double *mem_frame, *mem_rA, *mem_arm;      /* [n_members_total][9], [..][3], [..][3]        */
+    double *node_ls, *node_cd_q, *node_cd_p1, *node_cd_p2, *node_in_q, *node_in_p1, *node_in_p2, *node_pa;   /* [n_nodes_total] */
+    double *A_morison;         /* [nD][36]  A_hydro_morison about r0                             */
+    int32_t max_nodes, max_members, max_w_classes, max_h_classes, max_z_classes, _pad0;        /* out */
+} raftk_family_tables;
+
+int raftk_family_sizes(const raftk_family *f, int32_t *n_members_total, int32_t *n_nodes_total);
+int raftk_build_family_host(const raftk_family *f, raftk_family_tables *t);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,31 @@ class RaftkSlender(C.Structure):
 
 
 # every symbol include/raftk.h declares (tests/test_abi.py checks the header against this list)
+
+class RaftkFamilyMember(C.Structure):
+    """include/raftk.h raftk_family_member: one member copy of a design family (template constants + per-design geometry)."""
+    _fields_ = [("n_stations", C.c_int32), ("circular", C.c_int32), ("pot_mod", C.c_int32), ("_pad0", C.c_int32),
+                ("gamma_deg", C.c_double), ("heading_deg", C.c_double), ("dls_max", C.c_double),
+                ("stations", C.c_void_p), ("rA", C.c_void_p), ("rB", C.c_void_p), ("d", C.c_void_p),
+                ("Cd_q", C.c_void_p), ("Cd_p1", C.c_void_p), ("Cd_p2", C.c_void_p), ("Cd_End", C.c_void_p),
+                ("Ca_p1", C.c_void_p), ("Ca_p2", C.c_void_p), ("Ca_End", C.c_void_p)]
+
+
+class RaftkFamily(C.Structure):
+    _fields_ = [("n_designs", C.c_int32), ("n_members", C.c_int32), ("rho", C.c_double), ("g", C.c_double),
+                ("Rp", C.c_double * 9), ("r0", C.c_double * 3), ("members", C.POINTER(RaftkFamilyMember))]
+
+
+class RaftkFamilyTables(C.Structure):
+    _fields_ = [("member_offset", C.c_void_p), ("mem_node_start", C.c_void_p), ("mem_circ", C.c_void_p),
+                ("mem_frame", C.c_void_p), ("mem_rA", C.c_void_p), ("mem_arm", C.c_void_p),
+                ("node_ls", C.c_void_p), ("node_cd_q", C.c_void_p), ("node_cd_p1", C.c_void_p), ("node_cd_p2", C.c_void_p),
+                ("node_in_q", C.c_void_p), ("node_in_p1", C.c_void_p), ("node_in_p2", C.c_void_p), ("node_pa", C.c_void_p),
+                ("A_morison", C.c_void_p),
+                ("max_nodes", C.c_int32), ("max_members", C.c_int32), ("max_w_classes", C.c_int32), ("max_h_classes", C.c_int32),
+                ("max_z_classes", C.c_int32), ("_pad0", C.c_int32)]
+
+
 SYMBOLS = [
     "raftk_version", "raftk_last_error", "raftk_launch_count", "raftk_profile_enable", "raftk_profile_read",
     "raftk_workspace_bytes", "raftk_solve_workspace_bytes",
@@ -103,6 +128,7 @@ SYMBOLS = [
     "raftk_peer_alloc", "raftk_peer_free", "raftk_peer_open", "raftk_peer_close",
     "raftk_solve_dynamics_gather_dev", "raftk_peer_barrier_dev",
     "raftk_farm_response_dev", "raftk_solve_dynamics_farm_host",
+    "raftk_family_sizes", "raftk_build_family_host",
 ]
 
 
@@ -177,6 +203,10 @@ def _load():
     lib.raftk_solve_dynamics_farm_host.argtypes = [P(RaftkDesigns), P(RaftkCases), P(RaftkSolveOpts), P(RaftkOutputs), P(RaftkFarm)]
     lib.raftk_farm_response_dev.restype = C.c_int
     lib.raftk_solve_dynamics_farm_host.restype = C.c_int
+    lib.raftk_family_sizes.argtypes = [P(RaftkFamily), P(C.c_int32), P(C.c_int32)]
+    lib.raftk_build_family_host.argtypes = [P(RaftkFamily), P(RaftkFamilyTables)]
+    lib.raftk_family_sizes.restype = C.c_int
+    lib.raftk_build_family_host.restype = C.c_int
     for fn in ("raftk_peer_alloc", "raftk_peer_open", "raftk_peer_free", "raftk_peer_close", "raftk_solve_dynamics_gather_dev",
                "raftk_peer_barrier_dev"):
         getattr(lib, fn).restype = C.c_int

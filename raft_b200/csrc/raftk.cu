@@ -134,6 +134,7 @@ extern "C" long long raftk_launch_count(void) { return g_launches; }
 #include "raftk_slender.cuh"
 #include "raftk_general.cuh"
 #include "raftk_misc.cuh"
+#include "raftk_builder.h"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -777,6 +778,87 @@ extern "C" int raftk_farm_response_dev(const raftk_designs *d, const raftk_cases
                                        void *stream)
 {
     return farm_launch(d, c, solved, f, (cudaStream_t)stream);
+}
+
+
+// ---- native node-table builder for design families (pure host code, raftk_builder.h) ---------------------------------
+static int set_err_i(int code, const char *fmt, int a = 0, int b = 0)
+{
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+static int family_run(const raftk_family *f, raftk_family_tables *t, int32_t *n_mem_total, int32_t *n_node_total)
+{
+    if (!f || f->n_designs <= 0 || f->n_members <= 0 || !f->members) return set_err(RAFTK_EINVAL, "family: empty family");
+    for (int m = 0; m < f->n_members; m++) {
+        const raftk_family_member &M = f->members[m];
+        if (M.n_stations < 2) return set_err_i(RAFTK_EINVAL, "family: member %d: at least two stations entries must be provided", m);
+        if (!M.stations || !M.rA || !M.rB || !M.d || !M.Cd_q || !M.Cd_p1 || !M.Cd_p2 || !M.Cd_End || !M.Ca_p1 || !M.Ca_p2 || !M.Ca_End)
+            return set_err_i(RAFTK_EINVAL, "family: member %d: null array", m);
+        if (!(M.dls_max > 0.0)) return set_err_i(RAFTK_EINVAL, "family: member %d: dls_max must be positive", m);
+    }
+    std::vector<rkb::MemberOut> mem(f->n_members);
+    int64_t nm = 0, nn = 0;
+    int max_nodes = 0, max_members = 0, mw = 0, mh = 0, mz = 0;
+    if (t) t->member_offset[0] = 0, t->mem_node_start[0] = 0;
+    for (int d = 0; d < f->n_designs; d++) {
+        double A[36];
+        for (int i = 0; i < 36; i++) A[i] = 0.0;
+        int kept = 0, nodes = 0;
+        for (int m = 0; m < f->n_members; m++) {
+            const int rc = rkb::build_member(f->members[m], d, f->rho, f->g, f->Rp, f->r0, mem[m], A, t == nullptr);
+            if (rc == -1) return set_err_i(RAFTK_EINVAL, "RAFT Members cannot start or end on the waterplane (design %d, member %d)", d, m);
+            if (rc) return set_err_i(RAFTK_EINVAL, "family: the station list of member %d is not in ascending order", m);
+            if (!mem[m].nodes.empty()) { kept++; nodes += (int)mem[m].nodes.size(); }
+        }
+        if (t) {
+            for (int m = 0; m < f->n_members; m++) {
+                const rkb::MemberOut &M = mem[m];
+                if (M.nodes.empty()) continue;
+                for (int a = 0; a < 3; a++) {
+                    t->mem_frame[9 * nm + a] = M.q[a]; t->mem_frame[9 * nm + 3 + a] = M.p1[a]; t->mem_frame[9 * nm + 6 + a] = M.p2[a];
+                    t->mem_rA[3 * nm + a] = M.rA[a]; t->mem_arm[3 * nm + a] = M.rA[a] - f->r0[a];
+                }
+                t->mem_circ[nm] = M.circ;
+                for (const rkb::Node &N : M.nodes) {
+                    t->node_ls[nn] = N.ls; t->node_cd_q[nn] = N.cd_q; t->node_cd_p1[nn] = N.cd_p1; t->node_cd_p2[nn] = N.cd_p2;
+                    t->node_in_q[nn] = N.in_q; t->node_in_p1[nn] = N.in_p1; t->node_in_p2[nn] = N.in_p2; t->node_pa[nn] = N.pa;
+                    nn++;
+                }
+                nm++;
+                t->mem_node_start[nm] = (int32_t)nn;
+            }
+            t->member_offset[d + 1] = (int32_t)nm;
+            for (int i = 0; i < 36; i++) t->A_morison[36 * (size_t)d + i] = A[i];
+            int nW, nH, nZ;
+            rkb::count_classes(mem, nW, nH, nZ);
+            mw = std::max(mw, nW); mh = std::max(mh, nH); mz = std::max(mz, nZ);
+        } else { nm += kept; nn += nodes; }
+        max_nodes = std::max(max_nodes, nodes); max_members = std::max(max_members, kept);
+        if (nn > 2000000000LL) return set_err(RAFTK_EINVAL, "family: more than 2^31 nodes");
+    }
+    if (n_mem_total) *n_mem_total = (int32_t)nm;
+    if (n_node_total) *n_node_total = (int32_t)nn;
+    if (t) {
+        t->max_nodes = std::max(1, max_nodes); t->max_members = std::max(1, max_members);
+        t->max_w_classes = std::max(1, mw); t->max_h_classes = std::max(1, mh); t->max_z_classes = std::max(1, mz);
+    }
+    return RAFTK_OK;
+}
+
+extern "C" int raftk_family_sizes(const raftk_family *f, int32_t *n_members_total, int32_t *n_nodes_total)
+{
+    if (!n_members_total || !n_nodes_total) return set_err(RAFTK_EINVAL, "family sizes: null output");
+    return family_run(f, nullptr, n_members_total, n_nodes_total);
+}
+
+extern "C" int raftk_build_family_host(const raftk_family *f, raftk_family_tables *t)
+{
+    if (!t || !t->member_offset || !t->mem_node_start || !t->mem_circ || !t->mem_frame || !t->mem_rA || !t->mem_arm || !t->node_ls ||
+        !t->node_cd_q || !t->node_cd_p1 || !t->node_cd_p2 || !t->node_in_q || !t->node_in_p1 || !t->node_in_p2 || !t->node_pa || !t->A_morison)
+        return set_err(RAFTK_EINVAL, "family tables: null array");
+    return family_run(f, t, nullptr, nullptr);
 }
 
 // ---- host-pointer front ends -------------------------------------------------------------------------

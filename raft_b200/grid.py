@@ -13,6 +13,9 @@ def make_w(min_freq, max_freq):
     return np.arange(min_freq, max_freq + 0.5 * min_freq, min_freq) * 2 * np.pi
 
 
+_K_CACHE = {}
+
+
 def wave_number(w, depth, e=0.001, g=9.81):
     """k(w) by the reference's fixed-point iteration k <- w^2 / (g tanh(k h))  (helpers.py:377-392).
 
@@ -20,6 +23,9 @@ def wave_number(w, depth, e=0.001, g=9.81):
     few stragglers (the lowest frequencies) finish in the reference's own scalar loop, which costs ~1 us per iteration instead
     of the ~7 us of a NumPy round over a one- or two-element index set (same operations, same ``np.tanh``: identical bits)."""
     w = np.atleast_1d(np.asarray(w, dtype=float))
+    key = (w.tobytes(), float(depth), float(e), float(g))
+    if key in _K_CACHE:                                   # a sweep builds every shard on the same grid
+        return _K_CACHE[key].copy()
     k1 = w * w / g
     k2 = w * w / (np.tanh(k1 * depth) * g)
     idx = np.nonzero(np.abs(k2 - k1) / k1 > e)[0]
@@ -34,6 +40,9 @@ def wave_number(w, depth, e=0.001, g=9.81):
             a1 = a2
             a2 = ww / (tanh(a1 * depth) * g)
         k2[i] = a2
+    if len(_K_CACHE) >= 8:
+        _K_CACHE.pop(next(iter(_K_CACHE)))
+    _K_CACHE[key] = k2.copy()
     return k2
 
 

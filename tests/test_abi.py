@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SYMBOLS) == declared
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.raftk_version() == 130
+    assert _lib.lib.raftk_version() == 131
 
 
 def test_struct_layout_matches_header(tmp_path):
@@ -35,12 +35,16 @@ def test_struct_layout_matches_header(tmp_path):
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "raftk.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
                     'sizeof(raftk_designs), offsetof(raftk_designs, X_BEM), sizeof(raftk_cases), offsetof(raftk_cases, zeta),'
-                    'sizeof(raftk_solve_opts), sizeof(raftk_outputs), offsetof(raftk_designs, node_in_p1_w));return 0;}\n')
+                    'sizeof(raftk_solve_opts), sizeof(raftk_outputs), offsetof(raftk_designs, node_in_p1_w));'
+                    'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(raftk_family_member), offsetof(raftk_family_member, Ca_End), sizeof(raftk_family),'
+                    'offsetof(raftk_family, members), sizeof(raftk_family_tables), offsetof(raftk_family_tables, max_nodes));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(_lib.RaftkDesigns), _lib.RaftkDesigns.X_BEM.offset, C.sizeof(_lib.RaftkCases), _lib.RaftkCases.zeta.offset,
-            C.sizeof(_lib.RaftkSolveOpts), C.sizeof(_lib.RaftkOutputs), _lib.RaftkDesigns.node_in_p1_w.offset]
+            C.sizeof(_lib.RaftkSolveOpts), C.sizeof(_lib.RaftkOutputs), _lib.RaftkDesigns.node_in_p1_w.offset,
+            C.sizeof(_lib.RaftkFamilyMember), _lib.RaftkFamilyMember.Ca_End.offset, C.sizeof(_lib.RaftkFamily), _lib.RaftkFamily.members.offset,
+            C.sizeof(_lib.RaftkFamilyTables), _lib.RaftkFamilyTables.max_nodes.offset]
     assert got == want
 
 

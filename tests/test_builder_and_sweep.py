@@ -278,3 +278,58 @@ def test_host_struct_cache_follows_table_edits():
     t1 = solver._host_struct(c)
     c.arrays.update(Hs=np.array([2.0]))
     assert solver._host_struct(c) is not t1
+
+
+def _general_family():
+    from raft_b200 import batch_builder, grid
+    members = [
+        dict(name="col", type="rigid", rA=[10.0, 0, -18], rB=[10.0, 0, 12], shape="circ", stations=[0, 10, 10, 30], d=[9.0, 9.0, 6.0, 6.0],
+             heading=[0.0, 120.0, 240.0], Cd=0.8, Ca=[1.0, 1.0, 0.9, 0.8], CdEnd=0.6, CaEnd=0.6),
+        dict(name="pon", type="rigid", rA=[2.0, 0, -15], rB=[9.0, 1.0, -13], shape="rect", stations=[0, 1], d=[[4.0, 3.0], [3.0, 2.0]],
+             heading=[60.0, 180.0], gamma=10.0, Cd=[0.9, 1.1], Ca=[0.8, 0.9], potMod=True),
+        dict(name="brace", type="rigid", rA=[1.0, 0.5, -12], rB=[8.0, 2.0, 6.0], shape="circ", stations=[0, 2], d=0.9, Cd=1.0, Ca=1.0),
+        dict(name="vert", type="rigid", rA=[0.0, 0, -20], rB=[0.0, 0, 5.0], shape="rect", stations=[0, 5, 25], d=[[5.0, 4.0], [5.0, 4.0], [3.0, 2.5]],
+             heading=[0.0, 45.0], gamma=5.0, Cd=[[0.7, 0.9], [0.7, 0.9], [0.8, 1.0]], Ca=[[1.0, 0.9], [0.9, 0.8], [0.8, 0.7]], CdEnd=0.5, CaEnd=0.7),
+    ]
+    base = dict(site=dict(rho_water=1025.0, g=9.81), platform=dict(potModMaster=0, dlsMax=3.0, members=members))
+    rng = np.random.default_rng(3)
+    nD = 9
+    geom = dict(col=dict(d=np.array([[9.0, 9.0, 6.0, 6.0]]) * rng.uniform(0.8, 1.2, (nD, 1)),
+                         rA=np.column_stack([np.full(nD, 10.0), np.zeros(nD), -18 * rng.uniform(0.7, 1.3, nD)])),
+                pon=dict(d=np.array([[[4.0, 3.0], [3.0, 2.0]]]) * rng.uniform(0.8, 1.2, (nD, 1, 1))),
+                brace=dict(rB=np.column_stack([8.0 * rng.uniform(0.9, 1.1, nD), np.full(nD, 2.0), np.full(nD, 6.0)])))
+    w = grid.make_w(0.01, 0.2)
+    return batch_builder.DesignFamily(base, geom, nD), w, grid.wave_number(w, 150.0)
+
+
+def test_native_builder_matches_numpy_builder():
+    """raftk_build_family_host (csrc/raftk_builder.h, plain C++ loops) against batch_builder.build_family: identical counts, offsets
+    and step-class hints, tables to rounding -- on the sweep family, on a family with headings / tapered rectangular members / a
+    flat step / inclined and vertical members / potMod, and with a rotated, shifted platform."""
+    from raft_b200 import batch_builder, sweep
+    G, P = load_golden("cfg2_VolturnUS-S_nw64")
+    mats = dict(M_struc=P["M0"] - G["A_hydro_morison"], C_struc=P["C0"] - G["C_moor"], C_moor=G["C_moor"])
+    fac = sweep.sample_factors(64, seed=41)
+    num = sweep.build_variants_batched(DESIGNS["cfg2_VolturnUS-S_nw64"], mats, fac, nw=64, max_freq=0.32, depth=float(P["depth"]), native=False)
+    nat = sweep.build_variants_batched(DESIGNS["cfg2_VolturnUS-S_nw64"], mats, fac, nw=64, max_freq=0.32, depth=float(P["depth"]), native=True)
+    _batch_tables_equal(num, nat)
+    assert relerr(nat.A_hydro_morison, num.A_hydro_morison) < 1e-13
+    fam, w, k = _general_family()
+    mats2 = dict(M_struc=np.eye(6) * 1e7, C_struc=np.eye(6) * 1e6)
+    for r6 in (None, np.array([3.0, -2.0, 0.5, 0.02, -0.03, 0.4])):
+        a = batch_builder.build_family(fam, w, k, 150.0, mats2, r6=r6)
+        b = batch_builder.build_family_native(fam, w, k, 150.0, mats2, r6=r6)
+        _batch_tables_equal(a, b)
+        assert relerr(b.A_hydro_morison, a.A_hydro_morison) < 1e-13
+
+
+def test_native_builder_errors_like_the_reference():
+    from raft_b200 import _lib, batch_builder, grid
+    members = [dict(name="col", type="rigid", rA=[0.0, 0, -10], rB=[0.0, 0, 0.0], shape="circ", stations=[0, 10], d=5.0)]
+    base = dict(site=dict(rho_water=1025.0, g=9.81), platform=dict(potModMaster=0, dlsMax=3.0, members=members))
+    w = grid.make_w(0.05, 0.2)
+    with pytest.raises(_lib.RaftkError, match="cannot start or end on the waterplane"):
+        batch_builder.build_family_native(batch_builder.DesignFamily(base, {}, 2), w, grid.wave_number(w, 100.0), 100.0, {})
+    members[0].update(rB=[0.0, 0, 5.0], stations=[0, 10, 5])
+    with pytest.raises(ValueError, match="not in ascending order"):
+        batch_builder.build_family_native(batch_builder.DesignFamily(base, {}, 2), w, grid.wave_number(w, 100.0), 100.0, {})
