@@ -388,7 +388,7 @@ def main():
         d2, c2, g2 = build_workload(a2, rank, world)
         t_build = g2["table_build_s"]
         sw = measure(a2, d2, c2, g2, rank, world, dev, full=False)
-        if rank == 0:
+        if rank == 0 and sw is not None:
             sw["e2e_including_table_build"] = dict(
                 value=sw["config"]["units_per_step"] / (t_build + sw["e2e"]["ms_per_step"] * 1e-3) if sw.get("e2e") else None, unit=UNIT,
                 value_later_shards=sw["config"]["units_per_step"] / (g2["table_build_warm_s"] + sw["e2e"]["ms_per_step"] * 1e-3) if sw.get("e2e") else None,
